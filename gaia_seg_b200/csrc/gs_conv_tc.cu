@@ -1,0 +1,720 @@
+// gs_conv_tc.cu -- elastic-width convolutions as tcgen05 / TMEM implicit GEMMs (sm_100a).
+//
+// Two kernels:
+//   igemm_kernel : forward conv and data-gradient.  Persistent (one CTA per SM), warp-specialised:
+//       warp 0   TMA producer   -- per (tap r,s ; 64-channel K chunk) one 4-D box of the NHWC
+//                                  activation (shifted by the tap, OOB = zero padding) and one
+//                                  box of the max-width weight; the tensor-map extents are the
+//                                  ACTIVE prefix slice, the strides the MAX widths => the slice
+//                                  is addressed in place, no copy.
+//       warp 1   MMA issuer     -- tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), M = 128 pixels,
+//                                  N = up to 256 output channels, accumulators double-buffered
+//                                  in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
+//                                  the main loop of tile i+1.
+//       warps 2-5 epilogue      -- tcgen05.ld -> affine / residual / ReLU -> bf16 -> swizzled smem
+//                                  staging -> TMA store; per-channel sum / sum^2 (DynBN batch
+//                                  statistics) from the staged tile -> fp64 atomics.
+//   wgrad_kernel : weight gradient, split-K over pixels, both operands MN-major (pixels are K).
+//
+// GEMM view (forward):  Y[pix, co] = sum_{r,s,ci} X[pix shifted by (r,s), ci] * W[co, r, s, ci]
+#include <cuda_bf16.h>
+
+#include "../../include/gaiaseg_b200.h"
+#include "gs_host.h"
+#include "gs_ptx.cuh"
+
+namespace gs {
+
+// ------------------------------------------------------------------------------------------------
+// igemm (fwd / dgrad)
+// ------------------------------------------------------------------------------------------------
+constexpr int kIgStages = 3;
+constexpr int kIgABytes = 128 * 64 * 2;       // 128 pixels x 64 channels bf16
+constexpr int kIgBBytes = 256 * 64 * 2;       // up to 256 out-channels x 64 channels
+constexpr int kIgStageBytes = kIgABytes + kIgBBytes;
+constexpr int kIgStagingBytes = 128 * 256 * 2;  // epilogue tile, 4 sub-tiles of [128][64] bf16
+constexpr int kIgBarBytes = 256;
+constexpr int kIgSmemBytes = 1024 + kIgStages * kIgStageBytes + kIgStagingBytes + kIgBarBytes;
+constexpr int kIgThreads = 192;
+
+struct IgemmParams {
+    int N, Ho, Wo;        // output pixels
+    int TH, TW;           // spatial tile, TH*TW = 128
+    int tiles_h, tiles_w;
+    int m_tiles, n_tiles;
+    int Cout;             // active GEMM-N (output channels)
+    int Kc;               // active reduction channels per tap
+    int kchunks;          // ceil(Kc / 64)
+    int taps_h, taps_w;
+    int in_mul, base, step;  // input coord of tap t for output o:  o*in_mul + base + t*step
+    int b_box_rows;       // rows of the weight box (<= 256)
+    // epilogue
+    int direct;           // 1: per-thread global stores (fp32 out or unaligned), 0: TMA store
+    int out_f32;
+    int relu;
+    void* out;
+    long long out_ld;
+    const float* scale;
+    const float* shift;
+    const __nv_bfloat16* residual;
+    long long res_ld;
+    double* stats;
+};
+
+__global__ void __launch_bounds__(kIgThreads, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ IgemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint8_t* staging = smem + kIgStages * kIgStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kIgStagingBytes);
+    uint64_t* full_bar = bars;                  // [kIgStages]
+    uint64_t* empty_bar = bars + kIgStages;     // [kIgStages]
+    uint64_t* tfull_bar = bars + 2 * kIgStages; // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (!p.direct) tma_prefetch_desc(&tmC);
+        for (int i = 0; i < kIgStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int tiles_hw = p.tiles_h * p.tiles_w;
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = kIgABytes + p.b_box_rows * 128;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                const int mt = tile / p.n_tiles;
+                const int img = mt / tiles_hw;
+                const int rem = mt - img * tiles_hw;
+                const int h0 = (rem / p.tiles_w) * p.TH;
+                const int w0 = (rem % p.tiles_w) * p.TW;
+                const int n0 = nt * 256;
+                for (int r = 0; r < p.taps_h; ++r) {
+                    const int ih = h0 * p.in_mul + p.base + r * p.step;
+                    for (int s = 0; s < p.taps_w; ++s) {
+                        const int iw = w0 * p.in_mul + p.base + s * p.step;
+                        for (int kc = 0; kc < p.kchunks; ++kc) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            uint8_t* a_dst = stage_base + stage * kIgStageBytes;
+                            uint8_t* b_dst = a_dst + kIgABytes;
+                            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                            tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * 64, iw, ih, img);
+                            tma_load_4d(b_dst, &tmB, &full_bar[stage], kc * 64, s, r, n0);
+                            if (++stage == kIgStages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            const int iters = p.taps_h * p.taps_w * p.kchunks;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                int n_valid = p.Cout - nt * 256;
+                if (n_valid > 256) n_valid = 256;
+                const uint32_t umma_n = (n_valid + 15) & ~15;
+                const uint32_t idesc = make_idesc_bf16(128, umma_n, false, false);
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                uint32_t accumulate = 0;
+                int kc = 0;
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem_u32(stage_base + stage * kIgStageBytes);
+                    const uint32_t b_addr = a_addr + kIgABytes;
+                    int krem = p.Kc - kc * 64;
+                    const int ksteps = krem >= 64 ? 4 : (krem + 15) >> 4;
+#pragma unroll 1
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+                        accumulate = 1;
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++kc == p.kchunks) kc = 0;
+                    if (++stage == kIgStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // =========================== epilogue (warps 2..5) ===========================
+        const int q = warp & 3;            // TMEM sub-partition of this warp
+        const int row = q * 32 + lane;     // accumulator row == pixel within the tile
+        const int ep_tid = threadIdx.x - 64;
+        const int th = row / p.TW;
+        const int tw = row - th * p.TW;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles;
+            const int mt = tile / p.n_tiles;
+            const int img = mt / tiles_hw;
+            const int rem = mt - img * tiles_hw;
+            const int h0 = (rem / p.tiles_w) * p.TH;
+            const int w0 = (rem % p.tiles_w) * p.TW;
+            const int n0 = nt * 256;
+            int n_valid = p.Cout - n0;
+            if (n_valid > 256) n_valid = 256;
+            const int nchunks = (n_valid + 31) >> 5;
+            const int h = h0 + th, w = w0 + tw;
+            const bool valid = (h < p.Ho) && (w < p.Wo);
+            const long long pix = (static_cast<long long>(img) * p.Ho + h) * p.Wo + w;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after_sync();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t raw[32];
+                tmem_ld_32x32b_x32(t_addr + c * 32, raw);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                const int col0 = n0 + c * 32;
+                if (p.scale != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (col0 + i < p.Cout) v[i] *= __ldg(p.scale + col0 + i);
+                }
+                if (p.shift != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (col0 + i < p.Cout) v[i] += __ldg(p.shift + col0 + i);
+                }
+                if (p.residual != nullptr && valid) {
+                    const __nv_bfloat16* rp = p.residual + pix * p.res_ld + col0;
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        if (col0 + g8 * 8 < p.Cout) {
+                            const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + g8 * 8));
+                            v[g8 * 8 + 0] += bf16_lo(u.x); v[g8 * 8 + 1] += bf16_hi(u.x);
+                            v[g8 * 8 + 2] += bf16_lo(u.y); v[g8 * 8 + 3] += bf16_hi(u.y);
+                            v[g8 * 8 + 4] += bf16_lo(u.z); v[g8 * 8 + 5] += bf16_hi(u.z);
+                            v[g8 * 8 + 6] += bf16_lo(u.w); v[g8 * 8 + 7] += bf16_hi(u.w);
+                        }
+                    }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (p.direct) {
+                    if (valid) {
+                        if (p.out_f32) {
+                            float* op = reinterpret_cast<float*>(p.out) + pix * p.out_ld + col0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (col0 + i < p.Cout) op[i] = v[i];
+                        } else {
+                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + col0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (col0 + i < p.Cout) op[i] = __float2bfloat16_rn(v[i]);
+                        }
+                    }
+                } else {
+                    if (!valid) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = 0.f;  // keeps OOB pixels out of the statistics
+                    }
+                    // staging: sub-tile j = c/2 is [128 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
+                    uint8_t* sub = staging + (c >> 1) * (128 * 128) + row * 128;
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        const int chunk = ((c & 1) * 4 + g8) ^ (row & 7);
+                        uint4 u;
+                        u.x = pack_bf16x2(v[g8 * 8 + 0], v[g8 * 8 + 1]);
+                        u.y = pack_bf16x2(v[g8 * 8 + 2], v[g8 * 8 + 3]);
+                        u.z = pack_bf16x2(v[g8 * 8 + 4], v[g8 * 8 + 5]);
+                        u.w = pack_bf16x2(v[g8 * 8 + 6], v[g8 * 8 + 7]);
+                        *reinterpret_cast<uint4*>(sub + chunk * 16) = u;
+                    }
+                }
+            }
+            // accumulator buffer drained -> hand it back to the MMA warp
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+
+            if (!p.direct) {
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (ep_tid == 0) {
+                    const int nsub = (n_valid + 63) >> 6;
+                    for (int j = 0; j < nsub; ++j) tma_store_4d(&tmC, staging + j * (128 * 128), n0 + j * 64, w0, h0, img);
+                    tma_store_commit();
+                }
+                if (p.stats != nullptr) {
+                    // thread t owns columns 2t, 2t+1 of the tile
+                    const int cpair = ep_tid * 2;
+                    if (cpair < n_valid) {
+                        const uint8_t* sub = staging + (cpair >> 6) * (128 * 128);
+                        const int cin = cpair & 63;
+                        const int chunk = cin >> 3;
+                        const int word = (cin & 7) >> 1;
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+                        for (int r = 0; r < 128; ++r) {
+                            const uint32_t wv =
+                                *reinterpret_cast<const uint32_t*>(sub + r * 128 + ((chunk ^ (r & 7)) << 4) + word * 4);
+                            const float a = bf16_lo(wv), b = bf16_hi(wv);
+                            s0 += a; q0 = fmaf(a, a, q0);
+                            s1 += b; q1 = fmaf(b, b, q1);
+                        }
+                        const int gc = n0 + cpair;
+                        atomicAdd(p.stats + gc, static_cast<double>(s0));
+                        atomicAdd(p.stats + p.Cout + gc, static_cast<double>(q0));
+                        if (cpair + 1 < n_valid) {
+                            atomicAdd(p.stats + gc + 1, static_cast<double>(s1));
+                            atomicAdd(p.stats + p.Cout + gc + 1, static_cast<double>(q1));
+                        }
+                    }
+                }
+                if (ep_tid == 0) tma_store_wait_read0();
+                named_bar_sync(1, 128);  // staging may be overwritten by the next tile
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (!p.direct && ep_tid == 0) tma_store_wait_all0();
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// Spatial tile of `total` (128 or 64) pixels: widest power-of-two row segment that fits.
+static void choose_tile(int Wo, int total, int* TH, int* TW) {
+    int tw = 1;
+    while (tw < total && tw < Wo) tw <<= 1;
+    *TW = tw;
+    *TH = total / tw;
+}
+
+struct IgemmLaunch {
+    // activation ("input" of the GEMM A operand)
+    const void* a_ptr; int a_C; long long a_ld; int a_H, a_W;
+    int a_estride;         // element stride of the spatial traversal (fwd conv stride), 1 or 2
+    // weights: 4-D [rows_max][kh][kw][cols_max] with active extents rows (=Cout) x cols (=Kc)
+    const void* b_ptr; int b_rows_max, b_cols_max;
+    int N, Ho, Wo, Cout, Kc, kh, kw;
+    int in_mul, base, step;
+    void* out; long long out_ld; int out_f32;
+    const float* scale; const float* shift; const void* residual; long long res_ld; int relu; double* stats;
+};
+
+static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
+    GS_REQUIRE(L.a_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(L.a_ptr) & 15) == 0,
+               "conv: activation pitch (%lld) must be a multiple of 8 elements and 16-byte aligned", L.a_ld);
+    GS_REQUIRE(L.b_cols_max % 8 == 0 && (reinterpret_cast<uintptr_t>(L.b_ptr) & 15) == 0,
+               "conv: weight inner extent (%d) must be a multiple of 8", L.b_cols_max);
+    GS_REQUIRE(L.a_estride >= 1 && L.a_estride <= 2, "conv: stride %d not supported (1 or 2)", L.a_estride);
+    IgemmParams p{};
+    p.N = L.N; p.Ho = L.Ho; p.Wo = L.Wo;
+    choose_tile(L.Wo, 128, &p.TH, &p.TW);
+    p.tiles_h = (int)gs_ceil_div(L.Ho, p.TH);
+    p.tiles_w = (int)gs_ceil_div(L.Wo, p.TW);
+    p.m_tiles = L.N * p.tiles_h * p.tiles_w;
+    p.n_tiles = (int)gs_ceil_div(L.Cout, 256);
+    p.Cout = L.Cout; p.Kc = L.Kc; p.kchunks = (int)gs_ceil_div(L.Kc, 64);
+    p.taps_h = L.kh; p.taps_w = L.kw;
+    p.in_mul = L.in_mul; p.base = L.base; p.step = L.step;
+    p.b_box_rows = L.Cout >= 256 ? 256 : gs_round_up(L.Cout, 16);
+    p.out = L.out; p.out_ld = L.out_ld; p.out_f32 = L.out_f32; p.relu = L.relu;
+    p.scale = L.scale; p.shift = L.shift;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(L.residual); p.res_ld = L.res_ld;
+    p.stats = L.stats;
+    const bool tma_store_ok = !L.out_f32 && (L.out_ld % 8 == 0) && (L.Cout % 8 == 0) &&
+                              ((reinterpret_cast<uintptr_t>(L.out) & 15) == 0);
+    p.direct = tma_store_ok ? 0 : 1;
+    GS_REQUIRE(!(p.direct && L.stats), "conv: statistics need the bf16 TMA-store epilogue (Co %% 8 == 0)");
+    if (L.residual) {
+        GS_REQUIRE(L.res_ld % 8 == 0 && L.Cout % 8 == 0 && (reinterpret_cast<uintptr_t>(L.residual) & 15) == 0,
+                   "conv: residual needs Co %% 8 == 0 and 16-byte alignment");
+    }
+
+    CUtensorMap tmA, tmB, tmC;
+    {
+        const uint64_t dims[4] = {(uint64_t)L.a_C, (uint64_t)L.a_W, (uint64_t)L.a_H, (uint64_t)L.N};
+        const uint64_t str[3] = {(uint64_t)L.a_ld * 2, (uint64_t)L.a_ld * 2 * L.a_W, (uint64_t)L.a_ld * 2 * L.a_W * L.a_H};
+        const uint32_t box[4] = {64, (uint32_t)(p.TW * L.a_estride), (uint32_t)(p.TH * L.a_estride), 1};
+        const uint32_t es[4] = {1, (uint32_t)L.a_estride, (uint32_t)L.a_estride, 1};
+        if (encode_tmap_4d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.a_ptr, dims, str, box, es,
+                           CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)L.Kc, (uint64_t)L.kw, (uint64_t)L.kh, (uint64_t)L.Cout};
+        const uint64_t str[3] = {(uint64_t)L.b_cols_max * 2, (uint64_t)L.b_cols_max * 2 * L.kw,
+                                 (uint64_t)L.b_cols_max * 2 * L.kw * L.kh};
+        const uint32_t box[4] = {64, 1, 1, (uint32_t)p.b_box_rows};
+        const uint32_t es[4] = {1, 1, 1, 1};
+        if (encode_tmap_4d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.b_ptr, dims, str, box, es,
+                           CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    }
+    if (!p.direct) {
+        const uint64_t dims[4] = {(uint64_t)L.Cout, (uint64_t)L.Wo, (uint64_t)L.Ho, (uint64_t)L.N};
+        const uint64_t str[3] = {(uint64_t)L.out_ld * 2, (uint64_t)L.out_ld * 2 * L.Wo,
+                                 (uint64_t)L.out_ld * 2 * L.Wo * L.Ho};
+        const uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        const uint32_t es[4] = {1, 1, 1, 1};
+        if (encode_tmap_4d(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.out, dims, str, box, es,
+                           CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    } else {
+        tmC = tmA;  // unused
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        GS_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kIgSmemBytes));
+        attr_set = true;
+    }
+    const int total = p.m_tiles * p.n_tiles;
+    const int grid = total < num_sms() ? total : num_sms();
+    igemm_kernel<<<grid, kIgThreads, kIgSmemBytes, stream>>>(tmA, tmB, tmC, p);
+    GS_LAUNCHED();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// zero insertion for the data gradient of strided convolutions:
+//   up[n, ho*S, wo*S, :] = dy[n, ho, wo, :], zero elsewhere.   (memory-bound, 16-byte vectors)
+// ------------------------------------------------------------------------------------------------
+__global__ void zero_insert_kernel(const uint4* __restrict__ dy, long long dy_ld8, uint4* __restrict__ up, int N,
+                                   int Ho, int Wo, int Hu, int Wu, int S, int C8) {
+    const long long total = static_cast<long long>(N) * Hu * Wu * C8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = static_cast<int>(i % C8);
+        long long t = i / C8;
+        const int wu = static_cast<int>(t % Wu); t /= Wu;
+        const int hu = static_cast<int>(t % Hu);
+        const int n = static_cast<int>(t / Hu);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if ((hu % S) == 0 && (wu % S) == 0) {
+            const long long pix = (static_cast<long long>(n) * Ho + hu / S) * Wo + wu / S;
+            v = __ldg(dy + pix * dy_ld8 + c);
+        }
+        up[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: dW[co][r][s][ci] += sum_pix dY[pix, co] * X[pix shifted by (r,s), ci]
+//   M = 128 output channels (A = dY, MN-major), N <= 256 input channels (B = X, MN-major),
+//   K = pixels, 64 per pipeline stage.  grid.x = co_tiles * ci_tiles * taps, grid.y = split-K.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgStages = 4;
+constexpr int kWgBoxBytes = 64 * 64 * 2;           // [64 pixels][64 channels] bf16
+constexpr int kWgABytes = 2 * kWgBoxBytes;
+constexpr int kWgBBytes = 4 * kWgBoxBytes;
+constexpr int kWgStageBytes = kWgABytes + kWgBBytes;
+constexpr int kWgSmemBytes = 1024 + kWgStages * kWgStageBytes + 256;
+constexpr int kWgThreads = 192;
+
+struct WgradParams {
+    int N, Ho, Wo, TH, TW, tiles_h, tiles_w, chunks_total, splitk;
+    int Co, Ci, co_tiles, ci_tiles;
+    int kh, kw, stride, pad, dil;
+    float* dw;
+    long long row_stride;  // kh*kw*Ci_max
+    int Ci_max;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+             const __grid_constant__ WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kWgStages;
+    uint64_t* tfull_bar = bars + 2 * kWgStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // work item
+    int t = blockIdx.x;
+    const int tap = t % (p.kh * p.kw); t /= (p.kh * p.kw);
+    const int cit = t % p.ci_tiles;
+    const int cot = t / p.ci_tiles;
+    const int r = tap / p.kw, s = tap - r * p.kw;
+    const int co0 = cot * 128, ci0 = cit * 256;
+    int ci_valid = p.Ci - ci0; if (ci_valid > 256) ci_valid = 256;
+    int co_valid = p.Co - co0; if (co_valid > 128) co_valid = 128;
+    const int a_boxes = (co_valid + 63) >> 6;
+    const int b_boxes = (ci_valid + 63) >> 6;
+    const uint32_t umma_n = (ci_valid + 15) & ~15;
+    const int per = (p.chunks_total + p.splitk - 1) / p.splitk;
+    const int c_begin = blockIdx.y * per;
+    int c_end = c_begin + per; if (c_end > p.chunks_total) c_end = p.chunks_total;
+    const int tiles_hw = p.tiles_h * p.tiles_w;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmDY);
+        tma_prefetch_desc(&tmX);
+        for (int i = 0; i < kWgStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(tfull_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 256);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+    const bool has_work = c_begin < c_end;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t tx = (a_boxes + b_boxes) * kWgBoxBytes;
+            for (int c = c_begin; c < c_end; ++c) {
+                const int img = c / tiles_hw;
+                const int rem = c - img * tiles_hw;
+                const int ho0 = (rem / p.tiles_w) * p.TH;
+                const int wo0 = (rem % p.tiles_w) * p.TW;
+                const int ih = ho0 * p.stride - p.pad + r * p.dil;
+                const int iw = wo0 * p.stride - p.pad + s * p.dil;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* a_dst = smem + stage * kWgStageBytes;
+                uint8_t* b_dst = a_dst + kWgABytes;
+                mbar_arrive_expect_tx(&full_bar[stage], tx);
+                for (int j = 0; j < a_boxes; ++j)
+                    tma_load_4d(a_dst + j * kWgBoxBytes, &tmDY, &full_bar[stage], co0 + j * 64, wo0, ho0, img);
+                for (int j = 0; j < b_boxes; ++j)
+                    tma_load_4d(b_dst + j * kWgBoxBytes, &tmX, &full_bar[stage], ci0 + j * 64, iw, ih, img);
+                if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one() && has_work) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t idesc = make_idesc_bf16(128, umma_n, true, true);
+            uint32_t accumulate = 0;
+            for (int c = c_begin; c < c_end; ++c) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after_sync();
+                const uint32_t a_addr = smem_u32(smem + stage * kWgStageBytes);
+                const uint32_t b_addr = a_addr + kWgABytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 2048, kWgBoxBytes, 1024);
+                    const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 2048, kWgBoxBytes, 1024);
+                    umma_bf16_ss(tmem_base, adesc, bdesc, idesc, accumulate);
+                    accumulate = 1;
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull_bar);
+        }
+    } else if (has_work) {
+        const int q = warp & 3;
+        const int co = co0 + q * 32 + lane;
+        mbar_wait(tfull_bar, 0);
+        tc_fence_after_sync();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        float* dst_row = p.dw + static_cast<long long>(co) * p.row_stride + static_cast<long long>(r * p.kw + s) * p.Ci_max + ci0;
+        const int nchunks = (ci_valid + 31) >> 5;
+        const bool vec_ok = (p.Ci_max % 4 == 0) && (p.Ci % 4 == 0);
+        for (int c = 0; c < nchunks; ++c) {
+            uint32_t raw[32];
+            tmem_ld_32x32b_x32(t_addr + c * 32, raw);
+            tmem_ld_wait();
+            if (co < p.Co) {
+                if (vec_ok) {
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const int col = c * 32 + g4 * 4;
+                        if (col < ci_valid)
+                            red_add_v4(dst_row + col, __uint_as_float(raw[g4 * 4 + 0]), __uint_as_float(raw[g4 * 4 + 1]),
+                                       __uint_as_float(raw[g4 * 4 + 2]), __uint_as_float(raw[g4 * 4 + 3]));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int col = c * 32 + i;
+                        if (col < ci_valid) atomicAdd(dst_row + col, __uint_as_float(raw[i]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+static int launch_wgrad(const gs_conv_geom* g, const void* x, const void* dy, float* dw, cudaStream_t stream) {
+    GS_REQUIRE(g->x_ld % 8 == 0 && g->y_ld % 8 == 0, "wgrad: pitches must be multiples of 8 elements");
+    GS_REQUIRE(g->stride >= 1 && g->stride <= 2, "wgrad: stride %d not supported", g->stride);
+    WgradParams p{};
+    p.N = g->N; p.Ho = g->Ho; p.Wo = g->Wo;
+    choose_tile(g->Wo, 64, &p.TH, &p.TW);
+    p.tiles_h = (int)gs_ceil_div(g->Ho, p.TH);
+    p.tiles_w = (int)gs_ceil_div(g->Wo, p.TW);
+    p.chunks_total = g->N * p.tiles_h * p.tiles_w;
+    p.Co = g->Co; p.Ci = g->Ci;
+    p.co_tiles = (int)gs_ceil_div(g->Co, 128);
+    p.ci_tiles = (int)gs_ceil_div(g->Ci, 256);
+    p.kh = g->kh; p.kw = g->kw; p.stride = g->stride; p.pad = g->pad; p.dil = g->dil;
+    p.dw = dw; p.Ci_max = g->Ci_max;
+    p.row_stride = static_cast<long long>(g->kh) * g->kw * g->Ci_max;
+    const int items = p.co_tiles * p.ci_tiles * g->kh * g->kw;
+    int splitk = (int)gs_ceil_div(2 * num_sms(), items);
+    if (splitk > p.chunks_total) splitk = p.chunks_total;
+    if (splitk < 1) splitk = 1;
+    // keep at least 8 pixel-chunks (512 pixels) per CTA so the fp32 atomics stay a small tail
+    const int max_split = (int)gs_ceil_div(p.chunks_total, 8);
+    if (splitk > max_split) splitk = max_split;
+    p.splitk = splitk;
+
+    CUtensorMap tmDY, tmX;
+    {
+        const uint64_t dims[4] = {(uint64_t)g->Co, (uint64_t)g->Wo, (uint64_t)g->Ho, (uint64_t)g->N};
+        const uint64_t str[3] = {(uint64_t)g->y_ld * 2, (uint64_t)g->y_ld * 2 * g->Wo, (uint64_t)g->y_ld * 2 * g->Wo * g->Ho};
+        const uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        const uint32_t es[4] = {1, 1, 1, 1};
+        if (encode_tmap_4d(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dy, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B))
+            return -1;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)g->Ci, (uint64_t)g->W, (uint64_t)g->H, (uint64_t)g->N};
+        const uint64_t str[3] = {(uint64_t)g->x_ld * 2, (uint64_t)g->x_ld * 2 * g->W, (uint64_t)g->x_ld * 2 * g->W * g->H};
+        const uint32_t box[4] = {64, (uint32_t)(p.TW * g->stride), (uint32_t)(p.TH * g->stride), 1};
+        const uint32_t es[4] = {1, (uint32_t)g->stride, (uint32_t)g->stride, 1};
+        if (encode_tmap_4d(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B))
+            return -1;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        GS_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+        attr_set = true;
+    }
+    dim3 grid(items, splitk);
+    wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, stream>>>(tmDY, tmX, p);
+    GS_LAUNCHED();
+    return 0;
+}
+
+}  // namespace gs
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace gs;
+
+static int check_geom(const gs_conv_geom* g) {
+    GS_REQUIRE(g != nullptr, "conv: null geometry");
+    GS_REQUIRE(g->N > 0 && g->H > 0 && g->W > 0 && g->Ho > 0 && g->Wo > 0, "conv: empty tensor");
+    GS_REQUIRE(g->Ci > 0 && g->Co > 0 && g->Ci <= g->Ci_max && g->Co <= g->Co_max,
+               "conv: active slice [%d,%d] exceeds max-width weight [%d,%d]", g->Co, g->Ci, g->Co_max, g->Ci_max);
+    GS_REQUIRE(g->kh >= 1 && g->kw >= 1 && g->dil >= 1 && g->pad >= 0, "conv: bad kernel geometry");
+    GS_REQUIRE(g->x_ld >= g->Ci && g->y_ld >= g->Co, "conv: pitch smaller than channel count");
+    const int ho = (g->H + 2 * g->pad - g->dil * (g->kh - 1) - 1) / g->stride + 1;
+    const int wo = (g->W + 2 * g->pad - g->dil * (g->kw - 1) - 1) / g->stride + 1;
+    GS_REQUIRE(ho == g->Ho && wo == g->Wo, "conv: output size (%d,%d) inconsistent with geometry (expect %d,%d)",
+               g->Ho, g->Wo, ho, wo);
+    return 0;
+}
+
+extern "C" int gs_conv2d_fwd(const gs_conv_geom* g, const void* x, const void* w_krsc, void* y, const float* scale,
+                             const float* shift, const void* residual, int32_t res_ld, int32_t flags, double* stats,
+                             void* stream) {
+    if (check_geom(g)) return -1;
+    IgemmLaunch L{};
+    L.a_ptr = x; L.a_C = g->Ci; L.a_ld = g->x_ld; L.a_H = g->H; L.a_W = g->W; L.a_estride = g->stride;
+    L.b_ptr = w_krsc; L.b_rows_max = g->Co_max; L.b_cols_max = g->Ci_max;
+    L.N = g->N; L.Ho = g->Ho; L.Wo = g->Wo; L.Cout = g->Co; L.Kc = g->Ci; L.kh = g->kh; L.kw = g->kw;
+    L.in_mul = g->stride; L.base = -g->pad; L.step = g->dil;
+    L.out = y; L.out_ld = g->y_ld; L.out_f32 = (flags & GS_EPI_OUT_F32) ? 1 : 0;
+    L.scale = scale; L.shift = shift; L.residual = residual; L.res_ld = res_ld;
+    L.relu = (flags & GS_EPI_RELU) ? 1 : 0; L.stats = stats;
+    return launch_igemm(L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int64_t gs_conv2d_dgrad_workspace_bytes(const gs_conv_geom* g) {
+    if (g == nullptr || g->stride == 1) return 0;
+    const int64_t Hu = (int64_t)(g->Ho - 1) * g->stride + 1, Wu = (int64_t)(g->Wo - 1) * g->stride + 1;
+    return (int64_t)g->N * Hu * Wu * gs_round_up(g->Co, 8) * 2;
+}
+
+extern "C" int gs_conv2d_dgrad(const gs_conv_geom* g, const void* dy, const void* w_crsk, void* dx,
+                               const void* residual, int32_t res_ld, void* workspace, void* stream_) {
+    if (check_geom(g)) return -1;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    IgemmLaunch L{};
+    if (g->stride == 1) {
+        L.a_ptr = dy; L.a_C = g->Co; L.a_ld = g->y_ld; L.a_H = g->Ho; L.a_W = g->Wo;
+    } else {
+        GS_REQUIRE(workspace != nullptr, "dgrad: stride %d needs a workspace", g->stride);
+        GS_REQUIRE(g->Co % 8 == 0 && g->y_ld % 8 == 0, "dgrad: strided path needs Co %% 8 == 0");
+        const int Hu = (g->Ho - 1) * g->stride + 1, Wu = (g->Wo - 1) * g->stride + 1;
+        const int C8 = g->Co / 8;
+        const long long total = (long long)g->N * Hu * Wu * C8;
+        const int blocks = (int)(gs_ceil_div(total, 256) < 148 * 16 ? gs_ceil_div(total, 256) : 148 * 16);
+        zero_insert_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(dy), g->y_ld / 8,
+                                                       reinterpret_cast<uint4*>(workspace), g->N, g->Ho, g->Wo, Hu, Wu,
+                                                       g->stride, C8);
+        GS_LAUNCHED();
+        L.a_ptr = workspace; L.a_C = g->Co; L.a_ld = g->Co; L.a_H = Hu; L.a_W = Wu;
+    }
+    L.a_estride = 1;
+    L.b_ptr = w_crsk; L.b_rows_max = g->Ci_max; L.b_cols_max = g->Co_max;
+    L.N = g->N; L.Ho = g->H; L.Wo = g->W; L.Cout = g->Ci; L.Kc = g->Co; L.kh = g->kh; L.kw = g->kw;
+    // dx[h] = sum_r dy_up[h + pad - r*dil] * w[:, r]
+    L.in_mul = 1; L.base = g->pad; L.step = -g->dil;
+    L.out = dx; L.out_ld = g->x_ld; L.out_f32 = 0;
+    L.scale = nullptr; L.shift = nullptr; L.residual = residual; L.res_ld = res_ld; L.relu = 0; L.stats = nullptr;
+    return launch_igemm(L, stream);
+}
+
+extern "C" int gs_conv2d_wgrad(const gs_conv_geom* g, const void* x, const void* dy, float* dw_krsc, void* stream) {
+    if (check_geom(g)) return -1;
+    return launch_wgrad(g, x, dy, dw_krsc, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,475 @@
+// gs_norm.cu -- DynamicBatchNorm2d / DynamicSyncBatchNorm kernels (memory-bound, sm_100a).
+//
+// Replaces [EXT] gaiavision DynBN / DynSyncBN == F.batch_norm on the channel-prefix slice
+// (sites: gaiaseg/models/backbones/dynamic_resnet.py:267-300, gaiaseg/models/utils/dynamic_res_layer.py:92).
+// Statistics travel as fp64 [2C] = (sum, sum of squares): the conv epilogue or gs_bn_stats
+// produces them, the host all-reduces them over the SyncBN group (packed, one message per layer),
+// gs_bn_finalize turns them into mean / invstd / scale / shift and updates the running stats.
+//
+// Algorithmic bytes (E = P*C elements, bf16):  stats E*2 | apply 2E*2 (+E*2 residual)
+//   bwd_reduce 3E*2 (dz, y, z) | bwd_apply 4E*2 (+E*2 when the residual gradient is written).
+#include "../../include/gaiaseg_b200.h"
+#include "gs_host.h"
+#include "gs_vec.cuh"
+
+namespace gs {
+
+// ------------------------------------------------------------------------------------------------
+// block reduction of 16 per-thread partials over the R pixel rows of a ColMap block, then fp64 atomics
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_reduce16_atomic(float (&a)[8], float (&b)[8], float* red, int Vc, int R, int cv0,
+                                                      int C8, int C, double* out) {
+    const int tid = threadIdx.x;
+    __syncthreads();  // previous chunk finished reading `red`
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        red[tid * 16 + i] = a[i];
+        red[tid * 16 + 8 + i] = b[i];
+    }
+    __syncthreads();
+    const int nthreads = Vc * R;
+    for (int o = tid; o < 16 * Vc; o += nthreads) {
+        const int cx = o >> 4, i = o & 15;
+        const int cv = cv0 + cx;
+        if (cv >= C8) continue;
+        float s = 0.f;
+        for (int r = 0; r < R; ++r) s += red[(r * Vc + cx) * 16 + i];
+        const int c = cv * 8 + (i & 7);
+        atomicAdd(out + (i < 8 ? c : C + c), static_cast<double>(s));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stats: sum / sumsq
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_stats_kernel(const uint4* __restrict__ x, long long ld8, long long P, int C,
+                                                       int C8, int Vc, int R, double* __restrict__ stats) {
+    __shared__ float red[256 * 16];
+    const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
+    const long long S = (long long)gridDim.x * R;
+    for (int cv0 = 0; cv0 < C8; cv0 += Vc) {
+        const int cv = cv0 + cx;
+        float s[8], q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+        if (cv < C8) {
+            long long p = (long long)blockIdx.x * R + ry;
+            for (; p + 3 * S < P; p += 4 * S) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = ldg_stream(x + (p + u * S) * ld8 + cv);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float f[8];
+                    unpack8(v[u], f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+                }
+            }
+            for (; p < P; p += S) {
+                float f[8];
+                unpack8(ldg_stream(x + p * ld8 + cv), f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+            }
+        }
+        block_reduce16_atomic(s, q, red, Vc, R, cv0, C8, C, stats);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize / eval affine (tiny)
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ rm, float* __restrict__ rv,
+                                   float momentum, float eps, float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = stats[c] / count;
+    double var = stats[C + c] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    const float mf = static_cast<float>(m);
+    const float istd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float g = gamma ? gamma[c] : 1.f;
+    const float b = beta ? beta[c] : 0.f;
+    const float sc = g * istd;
+    if (mean) mean[c] = mf;
+    if (invstd) invstd[c] = istd;
+    scale[c] = sc;
+    shift[c] = b - mf * sc;
+    if (rm) rm[c] = (1.f - momentum) * rm[c] + momentum * mf;
+    if (rv) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        rv[c] = (1.f - momentum) * rv[c] + momentum * static_cast<float>(unbiased);
+    }
+}
+
+__global__ void bn_eval_affine_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float g = gamma ? gamma[c] : 1.f;
+    const float b = beta ? beta[c] : 0.f;
+    const float sc = g * rsqrtf(rv[c] + eps);
+    scale[c] = sc;
+    shift[c] = b - rm[c] * sc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply: z = relu?( y*scale + shift (+ res) )
+// ------------------------------------------------------------------------------------------------
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, long long y_ld8,
+                                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                                       const uint4* __restrict__ res, long long res_ld8, int relu,
+                                                       uint4* __restrict__ z, long long z_ld8, long long P, int C8,
+                                                       int Vc, int R) {
+    const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
+    const long long S = (long long)gridDim.x * R;
+    for (int cv = cx; cv < C8; cv += Vc) {
+        float sc[8], sh[8];
+        if (scale) load8f(scale + cv * 8, sc);
+        else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sc[i] = 1.f;
+        }
+        if (shift) load8f(shift + cv * 8, sh);
+        else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sh[i] = 0.f;
+        }
+        long long p = (long long)blockIdx.x * R + ry;
+        for (; p + 3 * S < P; p += 4 * S) {
+            uint4 v[4], rr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = ldg_stream(y + (p + u * S) * y_ld8 + cv);
+                if (HAS_RES) rr[u] = ldg_stream(res + (p + u * S) * res_ld8 + cv);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f[8], g[8];
+                unpack8(v[u], f);
+                if (HAS_RES) unpack8(rr[u], g);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float t = fmaf(f[i], sc[i], sh[i]);
+                    if (HAS_RES) t += g[i];
+                    f[i] = relu ? fmaxf(t, 0.f) : t;
+                }
+                stg_stream(z + (p + u * S) * z_ld8 + cv, pack8(f));
+            }
+        }
+        for (; p < P; p += S) {
+            float f[8], g[8];
+            unpack8(ldg_stream(y + p * y_ld8 + cv), f);
+            if (HAS_RES) unpack8(ldg_stream(res + p * res_ld8 + cv), g);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float t = fmaf(f[i], sc[i], sh[i]);
+                if (HAS_RES) t += g[i];
+                f[i] = relu ? fmaxf(t, 0.f) : t;
+            }
+            stg_stream(z + p * z_ld8 + cv, pack8(f));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 1: per-channel sums of g and g*xhat, g = dz * [z > 0]
+// ------------------------------------------------------------------------------------------------
+template <bool HAS_Z>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restrict__ dz, long long dz_ld8,
+                                                            const uint4* __restrict__ y, long long y_ld8,
+                                                            const uint4* __restrict__ z, long long z_ld8,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, long long P, int C,
+                                                            int C8, int Vc, int R, double* __restrict__ sums) {
+    __shared__ float red[256 * 16];
+    const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
+    const long long S = (long long)gridDim.x * R;
+    for (int cv0 = 0; cv0 < C8; cv0 += Vc) {
+        const int cv = cv0 + cx;
+        float sg[8], sx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sg[i] = 0.f; sx[i] = 0.f; }
+        if (cv < C8) {
+            float mu[8], is[8];
+            load8f(mean + cv * 8, mu);
+            load8f(invstd + cv * 8, is);
+            long long p = (long long)blockIdx.x * R + ry;
+            for (; p + S < P; p += 2 * S) {
+                uint4 a[2], b[2], c[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    a[u] = ldg_stream(dz + (p + u * S) * dz_ld8 + cv);
+                    b[u] = ldg_stream(y + (p + u * S) * y_ld8 + cv);
+                    if (HAS_Z) c[u] = ldg_stream(z + (p + u * S) * z_ld8 + cv);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    float g[8], yy[8], zz[8];
+                    unpack8(a[u], g);
+                    unpack8(b[u], yy);
+                    if (HAS_Z) unpack8(c[u], zz);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float gi = (HAS_Z && !(zz[i] > 0.f)) ? 0.f : g[i];
+                        sg[i] += gi;
+                        sx[i] = fmaf(gi, (yy[i] - mu[i]) * is[i], sx[i]);
+                    }
+                }
+            }
+            for (; p < P; p += S) {
+                float g[8], yy[8], zz[8];
+                unpack8(ldg_stream(dz + p * dz_ld8 + cv), g);
+                unpack8(ldg_stream(y + p * y_ld8 + cv), yy);
+                if (HAS_Z) unpack8(ldg_stream(z + p * z_ld8 + cv), zz);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float gi = (HAS_Z && !(zz[i] > 0.f)) ? 0.f : g[i];
+                    sg[i] += gi;
+                    sx[i] = fmaf(gi, (yy[i] - mu[i]) * is[i], sx[i]);
+                }
+            }
+        }
+        block_reduce16_atomic(sg, sx, red, Vc, R, cv0, C8, C, sums);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 2: dy = gamma*invstd*( g - sum_g/count - xhat*sum_gx/count ); dres = g
+// ------------------------------------------------------------------------------------------------
+template <bool HAS_Z, bool HAS_DRES>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ dz, long long dz_ld8,
+                                                           const uint4* __restrict__ y, long long y_ld8,
+                                                           const uint4* __restrict__ z, long long z_ld8,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma,
+                                                           const double* __restrict__ sums, double inv_count,
+                                                           long long P, int C, int C8, int Vc, int R,
+                                                           uint4* __restrict__ dy, long long dy_ld8,
+                                                           uint4* __restrict__ dres, long long dres_ld8) {
+    const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
+    const long long S = (long long)gridDim.x * R;
+    for (int cv = cx; cv < C8; cv += Vc) {
+        float mu[8], is[8], k0[8], k1[8], k2[8];
+        load8f(mean + cv * 8, mu);
+        load8f(invstd + cv * 8, is);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = cv * 8 + i;
+            const float g = gamma ? __ldg(gamma + c) : 1.f;
+            k0[i] = g * is[i];                                               // gamma * invstd
+            k1[i] = static_cast<float>(sums[c] * inv_count);                 // mean of g
+            k2[i] = static_cast<float>(sums[C + c] * inv_count);             // mean of g*xhat
+        }
+        for (long long p = (long long)blockIdx.x * R + ry; p < P; p += S) {
+            float g[8], yy[8], zz[8], o[8];
+            unpack8(ldg_stream(dz + p * dz_ld8 + cv), g);
+            unpack8(ldg_stream(y + p * y_ld8 + cv), yy);
+            if (HAS_Z) unpack8(ldg_stream(z + p * z_ld8 + cv), zz);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float gi = (HAS_Z && !(zz[i] > 0.f)) ? 0.f : g[i];
+                g[i] = gi;
+                const float xh = (yy[i] - mu[i]) * is[i];
+                o[i] = k0[i] * (gi - k1[i] - xh * k2[i]);
+            }
+            stg_stream(dy + p * dy_ld8 + cv, pack8(o));
+            if (HAS_DRES) stg_stream(dres + p * dres_ld8 + cv, pack8(g));
+        }
+    }
+}
+
+// eval-mode / frozen BN backward: dy = scale * g (no statistics terms); dres = g
+template <bool HAS_Z, bool HAS_DRES>
+__global__ void __launch_bounds__(256) affine_bwd_kernel(const uint4* __restrict__ dz, long long dz_ld8,
+                                                         const uint4* __restrict__ z, long long z_ld8,
+                                                         const float* __restrict__ scale, long long P, int C8, int Vc,
+                                                         int R, uint4* __restrict__ dy, long long dy_ld8,
+                                                         uint4* __restrict__ dres, long long dres_ld8) {
+    const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
+    const long long S = (long long)gridDim.x * R;
+    for (int cv = cx; cv < C8; cv += Vc) {
+        float sc[8];
+        if (scale) load8f(scale + cv * 8, sc);
+        else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sc[i] = 1.f;
+        }
+        for (long long p = (long long)blockIdx.x * R + ry; p < P; p += S) {
+            float g[8], zz[8], o[8];
+            unpack8(ldg_stream(dz + p * dz_ld8 + cv), g);
+            if (HAS_Z) unpack8(ldg_stream(z + p * z_ld8 + cv), zz);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float gi = (HAS_Z && !(zz[i] > 0.f)) ? 0.f : g[i];
+                g[i] = gi;
+                o[i] = sc[i] * gi;
+            }
+            stg_stream(dy + p * dy_ld8 + cv, pack8(o));
+            if (HAS_DRES) stg_stream(dres + p * dres_ld8 + cv, pack8(g));
+        }
+    }
+}
+
+__global__ void bn_bwd_param_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float dg = static_cast<float>(sums[C + c]);
+    const float db = static_cast<float>(sums[c]);
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + db : db;
+}
+
+static int check_act(const void* p, long long ld, int C, const char* what) {
+    GS_REQUIRE(p != nullptr, "%s: null pointer", what);
+    GS_REQUIRE(C > 0 && C % 8 == 0, "%s: channels (%d) must be a positive multiple of 8", what, C);
+    GS_REQUIRE(ld >= C && ld % 8 == 0, "%s: pitch (%lld) must be >= C and a multiple of 8", what, ld);
+    GS_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "%s: pointer must be 16-byte aligned", what);
+    return 0;
+}
+
+}  // namespace gs
+
+using namespace gs;
+
+extern "C" int gs_bn_stats(const void* x, int64_t P, int32_t C, int32_t ld, double* stats, void* stream) {
+    if (check_act(x, ld, C, "bn_stats x")) return -1;
+    GS_REQUIRE(stats != nullptr, "bn_stats: null stats");
+    if (P <= 0) return 0;
+    const ColMap m = make_colmap(C);
+    const int grid = colmap_grid(m, P, 32, 148 * 4);
+    bn_stats_kernel<<<grid, m.threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint4*>(x), ld / 8, P, C, m.C8, m.Vc, m.R, stats);
+    GS_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gs_bn_finalize(const double* stats, double count, int32_t C, const float* gamma, const float* beta,
+                              float* running_mean, float* running_var, float momentum, float eps, float* mean,
+                              float* invstd, float* scale, float* shift, void* stream) {
+    GS_REQUIRE(stats && scale && shift, "bn_finalize: null pointer");
+    GS_REQUIRE(C > 0 && count > 0, "bn_finalize: empty reduction (C=%d count=%f)", C, count);
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        stats, count, C, gamma, beta, running_mean, running_var, momentum, eps, mean, invstd, scale, shift);
+    GS_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gs_bn_eval_affine(int32_t C, const float* gamma, const float* beta, const float* running_mean,
+                                 const float* running_var, float eps, float* scale, float* shift, void* stream) {
+    GS_REQUIRE(running_mean && running_var && scale && shift, "bn_eval_affine: null pointer");
+    GS_REQUIRE(C > 0, "bn_eval_affine: C=%d", C);
+    bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        C, gamma, beta, running_mean, running_var, eps, scale, shift);
+    GS_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gs_bn_apply(const void* y, int32_t y_ld, const float* scale, const float* shift, const void* residual,
+                           int32_t res_ld, int32_t relu, void* z, int32_t z_ld, int64_t P, int32_t C, void* stream) {
+    if (check_act(y, y_ld, C, "bn_apply y") || check_act(z, z_ld, C, "bn_apply z")) return -1;
+    if (residual && check_act(residual, res_ld, C, "bn_apply residual")) return -1;
+    if (P <= 0) return 0;
+    const ColMap m = make_colmap(C);
+    const int grid = colmap_grid(m, P, 8, 148 * 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (residual)
+        bn_apply_kernel<true><<<grid, m.threads, 0, st>>>(reinterpret_cast<const uint4*>(y), y_ld / 8, scale, shift,
+                                                          reinterpret_cast<const uint4*>(residual), res_ld / 8, relu,
+                                                          reinterpret_cast<uint4*>(z), z_ld / 8, P, m.C8, m.Vc, m.R);
+    else
+        bn_apply_kernel<false><<<grid, m.threads, 0, st>>>(reinterpret_cast<const uint4*>(y), y_ld / 8, scale, shift,
+                                                           nullptr, 0, relu, reinterpret_cast<uint4*>(z), z_ld / 8, P,
+                                                           m.C8, m.Vc, m.R);
+    GS_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gs_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z,
+                                int32_t z_ld, const float* mean, const float* invstd, int64_t P, int32_t C,
+                                double* sums, void* stream) {
+    if (check_act(dz, dz_ld, C, "bn_bwd_reduce dz") || check_act(y, y_ld, C, "bn_bwd_reduce y")) return -1;
+    if (z && check_act(z, z_ld, C, "bn_bwd_reduce z")) return -1;
+    GS_REQUIRE(mean && invstd && sums, "bn_bwd_reduce: null pointer");
+    if (P <= 0) return 0;
+    const ColMap m = make_colmap(C);
+    const int grid = colmap_grid(m, P, 32, 148 * 4);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (z)
+        bn_bwd_reduce_kernel<true><<<grid, m.threads, 0, st>>>(
+            reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8,
+            reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, P, C, m.C8, m.Vc, m.R, sums);
+    else
+        bn_bwd_reduce_kernel<false><<<grid, m.threads, 0, st>>>(
+            reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8, nullptr, 0,
+            mean, invstd, P, C, m.C8, m.Vc, m.R, sums);
+    GS_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gs_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z, int32_t z_ld,
+                               const float* mean, const float* invstd, const float* gamma, const double* sums,
+                               double count, int64_t P, int32_t C, void* dy, int32_t dy_ld, void* dres,
+                               int32_t dres_ld, void* stream) {
+    if (check_act(dz, dz_ld, C, "bn_bwd_apply dz") || check_act(y, y_ld, C, "bn_bwd_apply y") ||
+        check_act(dy, dy_ld, C, "bn_bwd_apply dy"))
+        return -1;
+    if (z && check_act(z, z_ld, C, "bn_bwd_apply z")) return -1;
+    if (dres && check_act(dres, dres_ld, C, "bn_bwd_apply dres")) return -1;
+    GS_REQUIRE(mean && invstd && sums && count > 0, "bn_bwd_apply: null pointer / empty count");
+    if (P <= 0) return 0;
+    const ColMap m = make_colmap(C);
+    const int grid = colmap_grid(m, P, 8, 148 * 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double inv_count = 1.0 / count;
+#define GS_BWD_APPLY(HZ, HD)                                                                                         \
+    bn_bwd_apply_kernel<HZ, HD><<<grid, m.threads, 0, st>>>(                                                         \
+        reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8,                  \
+        reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, gamma, sums, inv_count, P, C, m.C8, m.Vc, m.R,    \
+        reinterpret_cast<uint4*>(dy), dy_ld / 8, reinterpret_cast<uint4*>(dres), dres_ld / 8)
+    if (z && dres) GS_BWD_APPLY(true, true);
+    else if (z) GS_BWD_APPLY(true, false);
+    else if (dres) GS_BWD_APPLY(false, true);
+    else GS_BWD_APPLY(false, false);
+#undef GS_BWD_APPLY
+    GS_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gs_affine_bwd(const void* dz, int32_t dz_ld, const void* z, int32_t z_ld, const float* scale, int64_t P,
+                             int32_t C, void* dy, int32_t dy_ld, void* dres, int32_t dres_ld, void* stream) {
+    if (check_act(dz, dz_ld, C, "affine_bwd dz") || check_act(dy, dy_ld, C, "affine_bwd dy")) return -1;
+    if (z && check_act(z, z_ld, C, "affine_bwd z")) return -1;
+    if (dres && check_act(dres, dres_ld, C, "affine_bwd dres")) return -1;
+    if (P <= 0) return 0;
+    const ColMap m = make_colmap(C);
+    const int grid = colmap_grid(m, P, 8, 148 * 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define GS_AFF_BWD(HZ, HD)                                                                                      \
+    affine_bwd_kernel<HZ, HD><<<grid, m.threads, 0, st>>>(                                                      \
+        reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(z), z_ld / 8, scale, P,   \
+        m.C8, m.Vc, m.R, reinterpret_cast<uint4*>(dy), dy_ld / 8, reinterpret_cast<uint4*>(dres), dres_ld / 8)
+    if (z && dres) GS_AFF_BWD(true, true);
+    else if (z) GS_AFF_BWD(true, false);
+    else if (dres) GS_AFF_BWD(false, true);
+    else GS_AFF_BWD(false, false);
+#undef GS_AFF_BWD
+    GS_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gs_bn_bwd_param(const double* sums_local, int32_t C, float* dgamma, float* dbeta, int32_t accumulate,
+                               void* stream) {
+    GS_REQUIRE(sums_local != nullptr && C > 0, "bn_bwd_param: null pointer");
+    bn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums_local, C, dgamma, dbeta,
+                                                                                      accumulate);
+    GS_LAUNCHED();
+    return 0;
+}

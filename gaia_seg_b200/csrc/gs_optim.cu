@@ -1,0 +1,91 @@
+// gs_optim.cu -- fused SGD(momentum, weight decay) over the flat fp32 master buffer + refresh of the
+// bf16 shadow weights the tcgen05 convolutions read through TMA.
+// replaces torch.optim.SGD.step (configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:175-178).
+//
+// Master conv weights are stored [Co_max][kh][kw][Ci_max] (channels_last memory of the OIHW
+// parameter), so the forward shadow `w_krsc` is an element-wise bf16 cast at the same flat index;
+// the dgrad shadow `w_crsk` [Ci_max][kh][kw][Co_max] is a tiled transpose-cast per tensor.
+#include "../../include/gaiaseg_b200.h"
+#include "gs_host.h"
+
+#include <cuda_bf16.h>
+
+namespace gs {
+
+__global__ void __launch_bounds__(256) sgd_flat_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                                                       float4* __restrict__ buf, long long n4, float lr, float mom,
+                                                       float wd, float gscale, int first, uint2* __restrict__ shadow) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        float4 pv = p[i];
+        const float4 gv = g[i];
+        float4 bv;
+        const float d0 = fmaf(wd, pv.x, gv.x * gscale), d1 = fmaf(wd, pv.y, gv.y * gscale);
+        const float d2 = fmaf(wd, pv.z, gv.z * gscale), d3 = fmaf(wd, pv.w, gv.w * gscale);
+        if (first) {
+            bv = make_float4(d0, d1, d2, d3);
+        } else {
+            bv = buf[i];
+            bv.x = fmaf(mom, bv.x, d0); bv.y = fmaf(mom, bv.y, d1);
+            bv.z = fmaf(mom, bv.z, d2); bv.w = fmaf(mom, bv.w, d3);
+        }
+        buf[i] = bv;
+        pv.x -= lr * bv.x; pv.y -= lr * bv.y; pv.z -= lr * bv.z; pv.w -= lr * bv.w;
+        p[i] = pv;
+        if (shadow) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(pv.x, pv.y), b = __floats2bfloat162_rn(pv.z, pv.w);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&a);
+            o.y = *reinterpret_cast<uint32_t*>(&b);
+            shadow[i] = o;
+        }
+    }
+}
+
+// src fp32 [Co][R][Ci]  ->  dst bf16 [Ci][R][Co]   (32x32 tiles over (co, ci) for each r)
+__global__ void transpose_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Co, int R,
+                                      int Ci) {
+    __shared__ float tile[32][33];
+    const int r = blockIdx.z;
+    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int co = co0 + j, ci = ci0 + threadIdx.x;
+        tile[j][threadIdx.x] = (co < Co && ci < Ci) ? src[((long long)co * R + r) * Ci + ci] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int ci = ci0 + j, co = co0 + threadIdx.x;
+        if (ci < Ci && co < Co) dst[((long long)ci * R + r) * Co + co] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    }
+}
+
+}  // namespace gs
+
+using namespace gs;
+
+extern "C" int gs_sgd_flat(float* p, const float* g, float* momentum_buf, int64_t n, float lr, float momentum,
+                           float weight_decay, float grad_scale, int32_t first_step, void* shadow_bf16, void* stream) {
+    GS_REQUIRE(p && g && momentum_buf, "sgd_flat: null pointer");
+    GS_REQUIRE(n % 4 == 0, "sgd_flat: n (%lld) must be a multiple of 4 (flat buffers are padded)", (long long)n);
+    GS_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                 reinterpret_cast<uintptr_t>(momentum_buf)) & 15) == 0, "sgd_flat: buffers must be 16-byte aligned");
+    if (n == 0) return 0;
+    const long long n4 = n / 4;
+    long long grid = (n4 + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    sgd_flat_kernel<<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(momentum_buf), n4,
+        lr, momentum, weight_decay, grad_scale, first_step, reinterpret_cast<uint2*>(shadow_bf16));
+    GS_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gs_transpose_cast(const float* w_krsc_f32, void* w_crsk_bf16, int32_t Co, int32_t R, int32_t Ci,
+                                 void* stream) {
+    GS_REQUIRE(w_krsc_f32 && w_crsk_bf16 && Co > 0 && R > 0 && Ci > 0, "transpose_cast: bad arguments");
+    dim3 grid((Ci + 31) / 32, (Co + 31) / 32, R);
+    transpose_cast_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+        w_krsc_f32, reinterpret_cast<__nv_bfloat16*>(w_crsk_bf16), Co, R, Ci);
+    GS_LAUNCHED();
+    return 0;
+}

@@ -1,0 +1,225 @@
+/* gaiaseg_b200.h -- C ABI of libgaiaseg_b200.so (hand-written sm_100a kernels).
+ *
+ * This is the drop-in boundary for the GAIA-seg supernet train / eval hot path.  The
+ * reference has NO native code: every entry below replaces a PyTorch /
+ * cuDNN / ATen library call that the reference reaches from Python.  The reference call
+ * site each entry replaces is cited as `file:line` relative to /root/reference (symbols
+ * marked [EXT] live in gaiavision / mmseg, which the reference imports but does not vendor).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; gs_last_error() gives the message
+ *     (thread-local).  No exceptions, no torch types, plain pointers and sizes.
+ *   - all pointers are DEVICE pointers unless named host_*; buffers are owned by the caller
+ *     and must outlive the (asynchronous) call.  Work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*); no host synchronisation inside.
+ *   - activations are NHWC ("channels last"), bf16 unless stated; `*_ld` is the pixel pitch
+ *     in ELEMENTS (>= channels) so a tensor may be a channel slice of a wider buffer
+ *     (concat without copy).  Pitches and base pointers of bf16 tensors are 16-byte aligned.
+ *   - conv weights are the MAX-WIDTH supernet tensors; kernels address the active
+ *     channel-prefix slice [0:Co, 0:Ci] in place through TMA descriptors (no slice copy):
+ *       w_krsc : bf16 [Co_max][kh][kw][Ci_max]   (forward  B operand)
+ *       w_crsk : bf16 [Ci_max][kh][kw][Co_max]   (dgrad    B operand)
+ *       dw_krsc: fp32 [Co_max][kh][kw][Ci_max]   (wgrad accumulator; == channels_last OIHW)
+ *   - statistics buffers are fp64 [2*C]: sum[0:C], sum of squares [C:2C].
+ */
+#ifndef GAIASEG_B200_H_
+#define GAIASEG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_ABI_VERSION 1
+
+/* ---- library / device ------------------------------------------------------------------ */
+int gs_version(void);
+const char* gs_last_error(void);
+/* 0 iff the current CUDA device is compute capability 10.x (B200); <0 otherwise. */
+int gs_device_check(void);
+/* number of kernels launched by this library in this process since gs_reset_launch_count */
+int64_t gs_launch_count(void);
+void gs_reset_launch_count(void);
+
+/* ---- convolution (tcgen05 / TMEM implicit GEMM) ---------------------------------------- */
+/* Geometry of one DynamicConv2d call.
+ * replaces: [EXT] gaiavision DynamicConv2d.forward ==
+ *   F.conv2d(x, weight[:Co, :x.size(1)], bias[:Co], stride, padding, dilation)
+ *   built at gaiaseg/models/backbones/dynamic_resnet.py:259-297,
+ *   gaiaseg/models/utils/dynamic_res_layer.py:84-91, gaiaseg/models/decode_heads/dynamic_fcn_head.py:76,94-126 */
+typedef struct gs_conv_geom {
+    int32_t N, H, W;        /* input  pixels */
+    int32_t Ho, Wo;         /* output pixels */
+    int32_t Ci, Co;         /* ACTIVE channels (prefix slice) */
+    int32_t Ci_max, Co_max; /* extents of the max-width weight */
+    int32_t kh, kw, stride, pad, dil;
+    int32_t x_ld, y_ld;     /* pixel pitch (elements) of the x / y (dx / dy) buffers */
+} gs_conv_geom;
+
+/* epilogue flags */
+#define GS_EPI_RELU 1     /* y = max(y, 0) after affine / residual */
+#define GS_EPI_OUT_F32 2  /* y is fp32 (logits) instead of bf16 */
+
+/* y = epi( conv(x, w[:Co,:Ci]) ).
+ *   epi(v)[c] = relu?( v*scale[c] + shift[c] + residual[c] ), each part optional (NULL).
+ *   scale/shift: fp32 [Co]   (bias -> shift with scale NULL; eval-mode BN -> both)
+ *   residual   : bf16 NHWC with pitch res_ld, same pixels as y
+ *   stats      : fp64 [2*Co], ACCUMULATED (+=) with per-channel sum / sum-of-squares of the
+ *                values written to y (after rounding to bf16) -- the DynBN batch statistics;
+ *                NULL to skip.  Only legal with bf16 output. */
+int gs_conv2d_fwd(const gs_conv_geom* g, const void* x, const void* w_krsc, void* y, const float* scale,
+                  const float* shift, const void* residual, int32_t res_ld, int32_t flags, double* stats,
+                  void* stream);
+
+/* dx = conv_transpose(dy, w[:Co,:Ci]) (+ residual).  replaces autograd of F.conv2d (cuDNN dgrad).
+ * For stride > 1 `workspace` must hold gs_conv2d_dgrad_workspace_bytes(g) bytes. */
+int64_t gs_conv2d_dgrad_workspace_bytes(const gs_conv_geom* g);
+int gs_conv2d_dgrad(const gs_conv_geom* g, const void* dy, const void* w_crsk, void* dx, const void* residual,
+                    int32_t res_ld, void* workspace, void* stream);
+
+/* dw_krsc[:Co, :, :, :Ci] += dy^T * im2col(x).  replaces autograd of F.conv2d (cuDNN wgrad);
+ * entries outside the active slice are untouched (they stay zero, as in the reference where the
+ * slice backward scatters into a zero tensor). */
+int gs_conv2d_wgrad(const gs_conv_geom* g, const void* x, const void* dy, float* dw_krsc, void* stream);
+
+/* First conv of the network (Ci = 3): explicit im2col of the fp32 NCHW image into a bf16
+ * [N][Ho][Wo][Kpad] matrix, column order (r, s, c), zero padded to Kpad (multiple of 16).
+ * replaces: F.conv2d on the image at gaiaseg/models/backbones/dynamic_resnet.py:406-409 (stem). */
+int gs_im2col_image(const float* img_nchw, int32_t N, int32_t C, int32_t H, int32_t W, int32_t kh, int32_t kw,
+                    int32_t stride, int32_t pad, int32_t Ho, int32_t Wo, int32_t Kpad, void* out, void* stream);
+
+/* Debug / triage twins of the three convolution entry points on CUDA cores (one thread per output,
+ * same arguments and math contract; dgrad reads w_krsc).  Not the product path. */
+int gs_conv2d_fwd_simt(const gs_conv_geom* g, const void* x, const void* w_krsc, void* y, const float* scale,
+                       const float* shift, const void* residual, int32_t res_ld, int32_t flags, double* stats,
+                       void* stream);
+int gs_conv2d_dgrad_simt(const gs_conv_geom* g, const void* dy, const void* w_krsc, void* dx, const void* residual,
+                         int32_t res_ld, void* stream);
+int gs_conv2d_wgrad_simt(const gs_conv_geom* g, const void* x, const void* dy, float* dw_krsc, void* stream);
+
+/* ---- dynamic batch norm ------------------------------------------------------------------ */
+/* replaces: [EXT] DynamicBatchNorm2d / DynamicSyncBatchNorm.forward == F.batch_norm on
+ *   running_mean[:C], running_var[:C], weight[:C], bias[:C] (momentum 0.1, eps 1e-5), sites
+ *   gaiaseg/models/backbones/dynamic_resnet.py:267-300, gaiaseg/models/utils/dynamic_res_layer.py:92 */
+
+/* stats[0:C] += sum_x, stats[C:2C] += sum_x^2 over P pixels of a bf16 NHWC tensor. */
+int gs_bn_stats(const void* x, int64_t P, int32_t C, int32_t ld, double* stats, void* stream);
+
+/* From (possibly all-reduced) sums over `count` elements per channel:
+ *   mean, var(biased) -> invstd; scale = gamma*invstd; shift = beta - mean*scale;
+ *   running_mean = (1-m)*rm + m*mean; running_var = (1-m)*rv + m*var*count/(count-1)  (if non-NULL)
+ * gamma/beta may be NULL (1 / 0).  All vectors fp32 [C] (prefix of the max-width params). */
+int gs_bn_finalize(const double* stats, double count, int32_t C, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, float momentum, float eps, float* mean,
+                   float* invstd, float* scale, float* shift, void* stream);
+
+/* eval mode: scale = gamma*rsqrt(rv+eps), shift = beta - rm*scale */
+int gs_bn_eval_affine(int32_t C, const float* gamma, const float* beta, const float* running_mean,
+                      const float* running_var, float eps, float* scale, float* shift, void* stream);
+
+/* z = relu?( y*scale + shift (+ residual) ), bf16 NHWC, P pixels.  scale / shift may be NULL (1 / 0). */
+int gs_bn_apply(const void* y, int32_t y_ld, const float* scale, const float* shift, const void* residual,
+                int32_t res_ld, int32_t relu, void* z, int32_t z_ld, int64_t P, int32_t C, void* stream);
+
+/* Backward pass 1: g = dz * [z > 0] (z == NULL: no activation mask);
+ * sums[0:C] += sum g ; sums[C:2C] += sum g * xhat, xhat = (y-mean)*invstd. */
+int gs_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z, int32_t z_ld,
+                     const float* mean, const float* invstd, int64_t P, int32_t C, double* sums, void* stream);
+
+/* Backward pass 2 (sums all-reduced over the SyncBN group, count = elements per channel in the group):
+ *   dy = gamma*invstd*( g - sum_g/count - xhat*sum_gx/count )           -> dy (bf16)
+ *   dres = g (bf16)                      if dres != NULL (gradient of the residual branch) */
+int gs_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z, int32_t z_ld,
+                    const float* mean, const float* invstd, const float* gamma, const double* sums, double count,
+                    int64_t P, int32_t C, void* dy, int32_t dy_ld, void* dres, int32_t dres_ld, void* stream);
+
+/* Backward of a per-channel affine (+ReLU) with FIXED statistics (eval-mode / frozen BN, conv bias):
+ *   g = dz * [z > 0];  dy = scale * g;  dres = g. */
+int gs_affine_bwd(const void* dz, int32_t dz_ld, const void* z, int32_t z_ld, const float* scale, int64_t P,
+                  int32_t C, void* dy, int32_t dy_ld, void* dres, int32_t dres_ld, void* stream);
+
+/* dgamma[0:C] (+)= sums_local[C:2C], dbeta[0:C] (+)= sums_local[0:C]  (fp64 -> fp32) */
+int gs_bn_bwd_param(const double* sums_local, int32_t C, float* dgamma, float* dbeta, int32_t accumulate,
+                    void* stream);
+
+/* ---- pooling / layout -------------------------------------------------------------------- */
+/* replaces nn.MaxPool2d(3, 2, 1) at gaiaseg/models/backbones/dynamic_resnet.py:302.
+ * idx (uint8 [N][Ho][Wo][C], may be NULL for inference) records the winning tap r*3+s (first maximum in
+ * scan order, as ATen) for the backward pass. */
+int gs_maxpool3x3s2_fwd(const void* x, int32_t N, int32_t H, int32_t W, int32_t C, int32_t x_ld, void* y,
+                        int32_t Ho, int32_t Wo, int32_t y_ld, void* idx, void* stream);
+int gs_maxpool3x3s2_bwd(const void* dy, int32_t dy_ld, const void* idx, int32_t N, int32_t H, int32_t W, int32_t C,
+                        int32_t Ho, int32_t Wo, void* dx, int32_t dx_ld, void* stream);
+/* replaces nn.AdaptiveAvgPool2d(S) of the PSP pyramid, gaiaseg/models/decode_heads/dynamic_psp_head.py:51.
+ * y: bf16 [N][S][S][y_ld]. */
+int gs_adaptive_avgpool_fwd(const void* x, int32_t N, int32_t H, int32_t W, int32_t C, int32_t x_ld, int32_t S,
+                            void* y, int32_t y_ld, void* stream);
+int gs_adaptive_avgpool_bwd(const void* dy, int32_t dy_ld, int32_t N, int32_t H, int32_t W, int32_t C, int32_t S,
+                            void* dx, int32_t dx_ld, int32_t accumulate, void* stream);
+/* strided 2-D copy of bf16 rows (concat, torch.cat at dynamic_fcn_head.py:133): dst[p, 0:C] = src[p, 0:C] */
+int gs_copy_channels(const void* src, int32_t src_ld, void* dst, int32_t dst_ld, int64_t P, int32_t C, void* stream);
+/* dst[p, 0:C] += src[p, 0:C] (bf16, fp32 math) */
+int gs_add_channels(const void* src, int32_t src_ld, void* dst, int32_t dst_ld, int64_t P, int32_t C, void* stream);
+/* fp32 NCHW -> bf16 NHWC (pitch ld; channels C..Cpad zero-filled) and back */
+int gs_nchw_f32_to_nhwc_bf16(const float* src, int32_t N, int32_t C, int32_t H, int32_t W, void* dst, int32_t ld,
+                             int32_t Cpad, void* stream);
+int gs_nhwc_bf16_to_nchw_f32(const void* src, int32_t ld, int32_t N, int32_t C, int32_t H, int32_t W, float* dst,
+                             void* stream);
+/* per-(n, c) scale of a bf16 NHWC tensor: Dropout2d mask * 1/(1-p)  (fcn_head.py:248-253) */
+int gs_scale_nc(const void* x, int32_t x_ld, const float* scale_nc, void* y, int32_t y_ld, int32_t N, int64_t HW,
+                int32_t C, void* stream);
+/* fp32 [P][src_ld] (C used) -> bf16 [P][dst_ld], columns C..dst_ld zero-filled (dlogits -> MMA operand,
+ * first-conv weight -> zero-padded im2col shadow) */
+int gs_cast_f32_bf16(const float* src, int32_t src_ld, void* dst, int32_t dst_ld, int64_t P, int32_t C, void* stream);
+/* out[c] += sum_p src[p][c]  (fp32; bias gradient of conv_seg) */
+int gs_colsum_f32(const float* src, int32_t ld, int64_t P, int32_t C, float* out, void* stream);
+
+/* ---- loss / inference head --------------------------------------------------------------- */
+/* Fused  bilinear upsample (align_corners = False)  ->  cross entropy(ignore_index)  ->  top-1
+ * accuracy, never materialising the N*K*H*W tensor, and its gradient w.r.t. the LOW-RES logits.
+ * replaces: losses() at gaiaseg/models/decode_heads/dynamic_fcn_head.py:137-159
+ *   (resize :141-145, [EXT] mmseg CrossEntropyLoss restated at
+ *    gaiaseg/models/losses/cross_entropy_loss.py:67-94 + utils.py:26-55, accuracy accuracy.py:4-49)
+ *   logits : fp32 [N][h][w][ld] (K classes used), labels : int64 [N][H][W]
+ *   out_sum (fp64 [1])     += sum over non-ignored pixels of CE
+ *   out_counts (int64 [2]) += { #ignored pixels, #pixels with argmax == label }
+ *   pix_rec : gs_upsample_ce_record_bytes(N,H,W) bytes of scratch the backward pass re-reads (may be NULL
+ *             for forward-only);  loss = loss_weight * out_sum / (N*H*W)   (mean over ALL pixels).
+ *   labels outside [0,K) other than ignore_index count as ignored (the reference would raise).
+ * backward: dlogits[n,i,j,k] = grad_scale * d(sum CE)/dlogit  (written, not accumulated; gather form). */
+int64_t gs_upsample_ce_record_bytes(int32_t N, int32_t H, int32_t W);
+int gs_upsample_ce_fwd(const float* logits, int32_t N, int32_t h, int32_t w, int32_t K, int32_t ld,
+                       const int64_t* labels, int32_t H, int32_t W, int32_t ignore_index, double* out_sum,
+                       int64_t* out_counts, void* pix_rec, void* stream);
+int gs_upsample_ce_bwd(const float* logits, int32_t N, int32_t h, int32_t w, int32_t K, int32_t ld,
+                       const void* pix_rec, int32_t H, int32_t W, float grad_scale, float* dlogits, int32_t dl_ld,
+                       void* stream);
+
+/* Fused bilinear upsample -> argmax (softmax is monotone, skipped).  Ties -> lowest class index.
+ * replaces: whole_inference + softmax + argmax, restated at
+ *   gaiaseg/models/segmentors/dynamic_distiller.py:252-262,461-521
+ *   labels_out: int64 [N][H][W] */
+int gs_upsample_argmax(const float* logits, int32_t N, int32_t h, int32_t w, int32_t K, int32_t ld, int32_t H,
+                       int32_t W, int64_t* labels_out, void* stream);
+
+/* Plain bilinear resize of fp32 NHWC logits (align_corners = False), used for the two-step
+ * resize (to input size, then to ori_shape) of whole_inference when the sizes differ. */
+int gs_upsample_bilinear_f32(const float* src, int32_t N, int32_t h, int32_t w, int32_t K, int32_t ld, float* dst,
+                             int32_t H, int32_t W, int32_t dst_ld, void* stream);
+
+/* ---- optimizer ---------------------------------------------------------- */
+/* SGD(momentum, weight decay) over the FLAT fp32 master buffer (all parameters back to back, each padded
+ * to a multiple of 64 elements) + refresh of the flat bf16 forward shadow at the same indices:
+ *   g' = grad_scale*g + wd*p ; buf = mom*buf + g' (buf = g' on the first step) ; p -= lr*buf ;
+ *   shadow = bf16(p)
+ * replaces torch.optim.SGD.step (configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:175-178) */
+int gs_sgd_flat(float* p, const float* g, float* momentum_buf, int64_t n, float lr, float momentum,
+                float weight_decay, float grad_scale, int32_t first_step, void* shadow_bf16, void* stream);
+/* dgrad shadow of one conv weight: fp32 [Co][R][Ci] (R = kh*kw) -> bf16 [Ci][R][Co] */
+int gs_transpose_cast(const float* w_krsc_f32, void* w_crsk_bf16, int32_t Co, int32_t R, int32_t Ci, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAIASEG_B200_H_ */
