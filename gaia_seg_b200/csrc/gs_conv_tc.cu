@@ -705,7 +705,7 @@ extern "C" int gs_conv2d_dgrad(const gs_conv_geom* g, const void* dy, const void
         L.a_ptr = workspace; L.a_C = g->Co; L.a_ld = g->Co; L.a_H = Hu; L.a_W = Wu;
     }
     L.a_estride = 1;
-    L.b_ptr = w_crsk; L.b_rows_max = g->Ci_max; L.b_cols_max = g->Co_max;
+    L.b_ptr = w_crsk; L.b_rows_max = g->Ci_max; L.b_cols_max = gs_round_up(g->Co_max, 8);
     L.N = g->N; L.Ho = g->H; L.Wo = g->W; L.Cout = g->Ci; L.Kc = g->Co; L.kh = g->kh; L.kw = g->kw;
     // dx[h] = sum_r dy_up[h + pad - r*dil] * w[:, r]
     L.in_mul = 1; L.base = g->pad; L.step = -g->dil;

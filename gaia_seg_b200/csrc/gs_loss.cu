@@ -121,8 +121,10 @@ __global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const float* __res
 __global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const float* __restrict__ logits, int N, int h, int w,
                                                               int K, int ld, const PixRec* __restrict__ rec, int H,
                                                               int W, float rh, float rw, float grad_scale,
+                                                              const float* __restrict__ grad_scale_dev,
                                                               float* __restrict__ dlogits, int dl_ld) {
     const long long total = (long long)N * h * w * K;
+    if (grad_scale_dev) grad_scale *= __ldg(grad_scale_dev);
     const float inv_rh = 1.f / rh, inv_rw = 1.f / rw;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -241,13 +243,14 @@ extern "C" int gs_upsample_ce_fwd(const float* logits, int32_t N, int32_t h, int
 }
 
 extern "C" int gs_upsample_ce_bwd(const float* logits, int32_t N, int32_t h, int32_t w, int32_t K, int32_t ld,
-                                  const void* pix_rec, int32_t H, int32_t W, float grad_scale, float* dlogits,
-                                  int32_t dl_ld, void* stream) {
+                                  const void* pix_rec, int32_t H, int32_t W, float grad_scale,
+                                  const float* grad_scale_dev, float* dlogits, int32_t dl_ld, void* stream) {
     GS_REQUIRE(logits && pix_rec && dlogits, "upsample_ce_bwd: null pointer");
     GS_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && K > 0 && ld >= K && dl_ld >= K, "upsample_ce_bwd: bad shape");
     const float rh = static_cast<float>(h) / static_cast<float>(H), rw = static_cast<float>(w) / static_cast<float>(W);
     upsample_ce_bwd_kernel<<<loss_grid((long long)N * h * w * K), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        logits, N, h, w, K, ld, reinterpret_cast<const PixRec*>(pix_rec), H, W, rh, rw, grad_scale, dlogits, dl_ld);
+        logits, N, h, w, K, ld, reinterpret_cast<const PixRec*>(pix_rec), H, W, rh, rw, grad_scale, grad_scale_dev, dlogits,
+        dl_ld);
     GS_LAUNCHED();
     return 0;
 }

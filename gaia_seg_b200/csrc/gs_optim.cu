@@ -42,11 +42,12 @@ __global__ void __launch_bounds__(256) sgd_flat_kernel(float4* __restrict__ p, c
     }
 }
 
-// src fp32 [Co][R][Ci]  ->  dst bf16 [Ci][R][Co]   (32x32 tiles over (co, ci) for each r)
+// src fp32 [Co][R][Ci]  ->  dst bf16 [Ci][R][CoP], CoP = round_up(Co, 8)   (32x32 tiles over (co, ci) per r)
 __global__ void transpose_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Co, int R,
                                       int Ci) {
     __shared__ float tile[32][33];
     const int r = blockIdx.z;
+    const int CoP = (Co + 7) & ~7;
     const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         const int co = co0 + j, ci = ci0 + threadIdx.x;
@@ -55,7 +56,7 @@ __global__ void transpose_cast_kernel(const float* __restrict__ src, __nv_bfloat
     __syncthreads();
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         const int ci = ci0 + j, co = co0 + threadIdx.x;
-        if (ci < Ci && co < Co) dst[((long long)ci * R + r) * Co + co] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+        if (ci < Ci && co < Co) dst[((long long)ci * R + r) * CoP + co] = __float2bfloat16_rn(tile[threadIdx.x][j]);
     }
 }
 

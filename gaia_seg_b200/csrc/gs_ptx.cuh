@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 #include <cuda.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace gs {
 
@@ -58,11 +59,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped kernel (a CUDA error the host
-// reports), never as a hung GPU box.  2^26 probes of a HW-sleeping try_wait is seconds.
+// reports), never as a hung GPU box.  Wall-clock bound (2 s on %globaltimer), checked every 256 probes.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = global_timer_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if ((++spins & 255u) == 0 && global_timer_ns() - t0 > 2000000000ull) {
+            printf("gaiaseg_b200: mbarrier wait timed out (block %d thread %d bar smem 0x%x parity %u)\n",
+                   (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
     }
 }
 

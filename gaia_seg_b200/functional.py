@@ -1,0 +1,714 @@
+"""Host-side launch layer: tensors in, C-ABI calls out.
+
+Every function here enqueues hand-written sm_100a kernels from libgaiaseg_b200.so on torch's current
+CUDA stream.  PyTorch is only used for device memory (caching allocator), streams and autograd
+bookkeeping.  Activations are bf16 "NHWC with pitch": a torch tensor of logical shape [N, C, H, W]
+whose memory is [N][H][W][ld] (ld >= C), i.e. channels_last or a channel slice of a wider buffer.
+
+Reference semantics being replaced (all [EXT] gaiavision / mmseg):
+  DynamicConv2d.forward      F.conv2d(x, W[:width_state, :x.size(1)], b[:width_state], s, p, d)
+  DynamicBatchNorm2d.forward F.batch_norm(x, rm[:C], rv[:C], w[:C], b[:C], training, 0.1, 1e-5)
+  DynamicBottleneck.forward  relu(bn3(conv3(relu(bn2(conv2(relu(bn1(conv1 x))))))) + identity)
+"""
+import ctypes
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import ConvGeom, GsError, call
+
+BF16 = torch.bfloat16
+
+# 'tc' = tcgen05 implicit GEMM (product path); 'simt' = CUDA-core triage kernels (debug only)
+CONV_IMPL = os.environ.get('GS_CONV_IMPL', 'tc')
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+# ------------------------------------------------------------------------------------------------
+# activation tensors
+# ------------------------------------------------------------------------------------------------
+def new_act(N, C, H, W, device, dtype=BF16, ld=None):
+    """Uninitialised [N, C, H, W] activation with NHWC memory and pixel pitch ld (default C)."""
+    ld = C if ld is None else ld
+    t = torch.empty((N, H, W, ld), dtype=dtype, device=device).permute(0, 3, 1, 2)
+    return t if ld == C else t[:, :C]
+
+
+def act_ld(t):
+    """Pixel pitch (elements) of an NHWC-with-pitch tensor, or None when the layout is anything else."""
+    N, C, H, W = t.shape
+    s = t.stride()
+    if C > 1 and s[1] != 1:
+        return None
+    if W > 1:
+        ld = s[3]
+    elif H > 1:
+        ld = s[2]
+    elif N > 1:
+        ld = s[0]
+    else:
+        ld = C
+    if ld < C:
+        return None
+    if (W > 1 and s[3] != ld) or (H > 1 and s[2] != W * ld) or (N > 1 and s[0] != H * W * ld):
+        return None
+    return ld
+
+
+def as_act(t, dtype=BF16):
+    """Return `t` as an NHWC-with-pitch tensor of `dtype` the kernels can address (16-byte aligned
+    vectors); converts only when the layout does not already qualify."""
+    if not t.is_cuda:
+        raise GsError('gaia_seg_b200: activation is not on a CUDA device -- the hot path has no CPU fallback')
+    if t.dim() != 4:
+        raise GsError(f'expected a 4-D activation, got shape {tuple(t.shape)}')
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    ld = act_ld(t)
+    esz = t.element_size()
+    if ld is None or (ld * esz) % 16 != 0 or t.data_ptr() % 16 != 0:
+        t = t.contiguous(memory_format=torch.channels_last)
+        if act_ld(t) is None:  # degenerate shapes for which torch keeps NCHW strides
+            N, C, H, W = t.shape
+            o = new_act(N, C, H, W, t.device, dtype)
+            o.copy_(t)
+            t = o
+    return t
+
+
+def _pixels(t):
+    return t.shape[0] * t.shape[2] * t.shape[3]
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------------
+class ConvCall:
+    """Geometry of one DynamicConv2d invocation (mirrors struct gs_conv_geom)."""
+    __slots__ = ('geom', 'image', 'Kpad', 'N', 'Ho', 'Wo', 'Co', 'Ci')
+
+
+def _conv_attrs(conv):
+    kh, kw = conv.kernel_size
+    if conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1] or conv.dilation[0] != conv.dilation[1]:
+        raise GsError('DynamicConv2d: only square stride / padding / dilation are supported')
+    if conv.groups != 1:
+        raise GsError('DynamicConv2d: groups != 1 is not on the GAIA-seg hot path')
+    return kh, kw, conv.stride[0], conv.padding[0], conv.dilation[0]
+
+
+def is_image_conv(conv):
+    return conv.in_channels < 8
+
+
+def image_kpad(conv):
+    kh, kw = conv.kernel_size
+    return round_up(kh * kw * conv.in_channels, 16)
+
+
+def ensure_krsc(conv):
+    """The fp32 master weight must be stored [Co][kh][kw][Ci] (channels_last memory of OIHW)."""
+    w = conv.weight
+    if not w.permute(0, 2, 3, 1).is_contiguous():
+        w.data = w.data.contiguous(memory_format=torch.channels_last)
+        if not w.permute(0, 2, 3, 1).is_contiguous():
+            Co, Ci, kh, kw = w.shape
+            buf = torch.empty((Co, kh, kw, Ci), dtype=w.dtype, device=w.device)
+            buf.copy_(w.data.permute(0, 2, 3, 1))
+            w.data = buf.permute(0, 3, 1, 2)
+    return w
+
+
+def conv_shadows(conv):
+    """bf16 shadows of the max-width weight (forward KRSC, dgrad CRSK); rebuilt when the fp32 master
+    was modified by anything other than the fused optimizer (tracked through tensor._version)."""
+    w = ensure_krsc(conv)
+    if w.dtype != torch.float32 or not w.is_cuda:
+        raise GsError('DynamicConv2d: master weight must be fp32 on a CUDA device')
+    key = (w.data_ptr(), w._version)
+    if getattr(conv, '_gs_key', None) == key:
+        return conv._gs_w_krsc, conv._gs_w_crsk
+    Co, Ci, kh, kw = w.shape
+    R = kh * kw
+    st = _stream()
+    if is_image_conv(conv):
+        K, Kpad = R * Ci, image_kpad(conv)
+        krsc = getattr(conv, '_gs_w_krsc', None)
+        if krsc is None or krsc.numel() != Co * Kpad or krsc.device != w.device:
+            krsc = torch.empty(Co * Kpad, dtype=BF16, device=w.device)
+        call('gs_cast_f32_bf16', w.data_ptr(), K, krsc.data_ptr(), Kpad, Co, K, st)
+        crsk = None
+    else:
+        n = w.numel()
+        krsc = getattr(conv, '_gs_w_krsc', None)
+        if krsc is None or krsc.numel() != n or krsc.device != w.device:
+            krsc = torch.empty(n, dtype=BF16, device=w.device)
+        call('gs_cast_f32_bf16', w.data_ptr(), n, krsc.data_ptr(), n, 1, n, st)
+        crsk = getattr(conv, '_gs_w_crsk', None)
+        cop = round_up(Co, 8)
+        if crsk is None or crsk.numel() != Ci * R * cop or crsk.device != w.device:
+            crsk = torch.empty(Ci * R * cop, dtype=BF16, device=w.device)
+        call('gs_transpose_cast', w.data_ptr(), crsk.data_ptr(), Co, R, Ci, st)
+    conv._gs_w_krsc, conv._gs_w_crsk, conv._gs_key = krsc, crsk, key
+    return krsc, crsk
+
+
+def refresh_crsk(conv):
+    """Called by the fused optimizer after it rewrote master + KRSC shadow through raw pointers."""
+    if is_image_conv(conv):
+        w = conv.weight
+        Co, Ci, kh, kw = w.shape
+        K, Kpad = kh * kw * Ci, image_kpad(conv)
+        call('gs_cast_f32_bf16', w.data_ptr(), K, conv._gs_w_krsc.data_ptr(), Kpad, Co, K, _stream())
+        return
+    w = conv.weight
+    Co, Ci, kh, kw = w.shape
+    call('gs_transpose_cast', w.data_ptr(), conv._gs_w_crsk.data_ptr(), Co, kh * kw, Ci, _stream())
+
+
+def _geom(N, H, W, Ci, Co, Ci_max, Co_max, kh, kw, stride, pad, dil, x_ld, y_ld):
+    Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+    if Ho <= 0 or Wo <= 0:
+        raise GsError(f'conv: empty output for input {H}x{W}')
+    return ConvGeom(N, H, W, Ho, Wo, Ci, Co, Ci_max, Co_max, kh, kw, stride, pad, dil, x_ld, y_ld)
+
+
+def conv_forward(x, conv, Co, scale=None, shift=None, residual=None, relu=False, out_f32=False, want_stats=False):
+    """y = epi(conv(x, W[:Co, :Ci])).  Returns (y, stats, a_operand, geom): `a_operand` is the tensor the
+    weight gradient must be taken against (x itself, or the im2col matrix of the image conv)."""
+    _lib.require_device()
+    krsc, _ = conv_shadows(conv)
+    kh, kw, stride, pad, dil = _conv_attrs(conv)
+    Co_max, Ci_max = conv.out_channels, conv.in_channels
+    if not (0 < Co <= Co_max):
+        raise GsError(f'DynamicConv2d: active width {Co} outside (0, {Co_max}]')
+    dev = x.device
+    st = _stream()
+    if is_image_conv(conv):
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        N, Ci, H, W = x.shape
+        if Ci != Ci_max:
+            raise GsError(f'image conv expects {Ci_max} channels, got {Ci}')
+        Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+        if dil != 1:
+            raise GsError('image conv: dilation is not supported')
+        Kpad = image_kpad(conv)
+        cols = new_act(N, Kpad, Ho, Wo, dev)
+        call('gs_im2col_image', x.data_ptr(), N, Ci, H, W, kh, kw, stride, pad, Ho, Wo, Kpad, cols.data_ptr(), st)
+        a = cols
+        g = _geom(N, Ho, Wo, Kpad, Co, Kpad, Co_max, 1, 1, 1, 0, 1, Kpad, 0)
+    else:
+        a = as_act(x)
+        N, Ci, H, W = a.shape
+        if Ci > Ci_max:
+            raise GsError(f'DynamicConv2d: input has {Ci} channels, max-width weight only {Ci_max}')
+        g = _geom(N, H, W, Ci, Co, Ci_max, Co_max, kh, kw, stride, pad, dil, act_ld(a), 0)
+    y_ld = Co if not out_f32 else Co
+    y = new_act(N, Co, g.Ho, g.Wo, dev, torch.float32 if out_f32 else BF16, ld=y_ld)
+    g.y_ld = y_ld
+    stats = None
+    if want_stats:
+        stats = torch.zeros(2 * Co, dtype=torch.float64, device=dev)
+    flags = (1 if relu else 0) | (2 if out_f32 else 0)
+    res_ld = 0
+    if residual is not None:
+        residual = as_act(residual)
+        res_ld = act_ld(residual)
+    fn = 'gs_conv2d_fwd' if CONV_IMPL == 'tc' else 'gs_conv2d_fwd_simt'
+    call(fn, ctypes.byref(g), a.data_ptr(), krsc.data_ptr(), y.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
+         res_ld, flags, _ptr(stats), st)
+    return y, stats, a, g
+
+
+def _weight_grad(conv):
+    w = conv.weight
+    if w.grad is None:
+        w.grad = torch.zeros_like(w, memory_format=torch.preserve_format)
+        if not w.grad.permute(0, 2, 3, 1).is_contiguous():
+            w.grad = torch.zeros_like(w).contiguous(memory_format=torch.channels_last)
+    return w.grad
+
+
+def conv_wgrad(conv, a, dy, g):
+    """conv.weight.grad[:Co, :Ci] += dy^T * im2col(a)  (in place, KRSC fp32)."""
+    if not conv.weight.requires_grad:
+        return
+    st = _stream()
+    gw = _weight_grad(conv)
+    g.y_ld = act_ld(dy)
+    fn = 'gs_conv2d_wgrad' if CONV_IMPL == 'tc' else 'gs_conv2d_wgrad_simt'
+    if is_image_conv(conv):
+        Co_max = conv.out_channels
+        K = conv.kernel_size[0] * conv.kernel_size[1] * conv.in_channels
+        Kpad = image_kpad(conv)
+        tmp = torch.zeros((Co_max, Kpad), dtype=torch.float32, device=dy.device)
+        call(fn, ctypes.byref(g), a.data_ptr(), dy.data_ptr(), tmp.data_ptr(), st)
+        gw.permute(0, 2, 3, 1).reshape(Co_max, K).add_(tmp[:, :K])
+    else:
+        call(fn, ctypes.byref(g), a.data_ptr(), dy.data_ptr(), gw.data_ptr(), st)
+
+
+def conv_dgrad(conv, dy, g, x_shape, add=None):
+    """dx = conv_transpose(dy, W[:Co, :Ci]) (+ add)."""
+    krsc, crsk = conv_shadows(conv)
+    N, Ci, H, W = x_shape
+    dx = new_act(N, Ci, H, W, dy.device)
+    g.x_ld = Ci
+    g.y_ld = act_ld(dy)
+    add_ld = 0
+    if add is not None:
+        add = as_act(add)
+        add_ld = act_ld(add)
+    st = _stream()
+    if CONV_IMPL == 'tc':
+        ws = None
+        nbytes = _lib.load().gs_conv2d_dgrad_workspace_bytes(ctypes.byref(g))
+        if nbytes > 0:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dy.device)
+        call('gs_conv2d_dgrad', ctypes.byref(g), dy.data_ptr(), crsk.data_ptr(), dx.data_ptr(), _ptr(add), add_ld,
+             _ptr(ws), st)
+    else:
+        call('gs_conv2d_dgrad_simt', ctypes.byref(g), dy.data_ptr(), krsc.data_ptr(), dx.data_ptr(), _ptr(add),
+             add_ld, st)
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# batch norm pieces
+# ------------------------------------------------------------------------------------------------
+def bn_batch_mode(bn):
+    """True when the layer normalises with mini-batch statistics (train mode, or running stats dropped
+    by `caliberate_bn.use_minibatch_stats`, tools/test_supernet.py:190-198)."""
+    return bn.training or not bn.track_running_stats or bn.running_mean is None
+
+
+def _sync_group(bn):
+    """(process_group, world) when `bn` synchronises statistics across ranks, else (None, 1)."""
+    if not getattr(bn, 'sync', False) or not dist.is_available() or not dist.is_initialized():
+        return None, 1
+    pg = getattr(bn, 'process_group', None)
+    world = dist.get_world_size(pg)
+    return pg, world
+
+
+def bn_finalize(bn, stats, C, local_count):
+    """all-reduce the packed (sum, sumsq), then mean / invstd / scale / shift (+ running stats)."""
+    pg, world = _sync_group(bn)
+    if world > 1:
+        dist.all_reduce(stats, group=pg)
+    count = float(local_count) * world
+    aff = torch.empty((4, C), dtype=torch.float32, device=stats.device)
+    upd = bn.training and bn.track_running_stats and bn.running_mean is not None
+    if upd and bn.momentum is None:
+        raise GsError('DynamicBatchNorm2d: momentum=None (cumulative average) is not supported on the CUDA path')
+    call('gs_bn_finalize', stats.data_ptr(), count, C, _ptr(bn.weight), _ptr(bn.bias),
+         bn.running_mean.data_ptr() if upd else None, bn.running_var.data_ptr() if upd else None,
+         float(bn.momentum if bn.momentum is not None else 0.0), float(bn.eps), aff[0].data_ptr(), aff[1].data_ptr(),
+         aff[2].data_ptr(), aff[3].data_ptr(), _stream())
+    if upd:
+        bn._gs_nbt_pending = getattr(bn, '_gs_nbt_pending', 0) + 1
+    return aff, count
+
+
+def bn_eval_affine(bn, C):
+    aff = torch.empty((2, C), dtype=torch.float32, device=bn.running_mean.device)
+    call('gs_bn_eval_affine', C, _ptr(bn.weight), _ptr(bn.bias), bn.running_mean.data_ptr(),
+         bn.running_var.data_ptr(), float(bn.eps), aff[0].data_ptr(), aff[1].data_ptr(), _stream())
+    return aff
+
+
+def bn_stats(x):
+    x = as_act(x)
+    C = x.shape[1]
+    stats = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
+    call('gs_bn_stats', x.data_ptr(), _pixels(x), C, act_ld(x), stats.data_ptr(), _stream())
+    return stats
+
+
+def bn_apply(y, scale, shift, residual=None, relu=False):
+    N, C, H, W = y.shape
+    z = new_act(N, C, H, W, y.device)
+    res_ld = 0
+    if residual is not None:
+        residual = as_act(residual)
+        res_ld = act_ld(residual)
+    call('gs_bn_apply', y.data_ptr(), act_ld(y), _ptr(scale), _ptr(shift), _ptr(residual), res_ld, 1 if relu else 0,
+         z.data_ptr(), C, _pixels(y), C, _stream())
+    return z
+
+
+def _param_grad(p):
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
+
+
+# ------------------------------------------------------------------------------------------------
+# fused conv -> (dynamic BN) -> (ReLU) (+ residual): forward record + hand-written backward
+# ------------------------------------------------------------------------------------------------
+class LayerRec:
+    __slots__ = ('conv', 'bn', 'mode', 'a', 'x_shape', 'geom', 'y', 'z', 'aff', 'count', 'relu', 'has_res', 'Co')
+
+
+def cba_forward(x, conv, bn=None, relu=False, residual=None, Co=None, save=True):
+    """z = relu?( BN( conv(x) ) + residual ).  Returns (z, rec); rec drives cba_backward."""
+    Co = conv.width_state if Co is None else Co
+    rec = LayerRec() if save else None
+    if bn is not None and bn_batch_mode(bn):
+        y, stats, a, g = conv_forward(x, conv, Co, shift=_bias(conv, Co), want_stats=True)
+        aff, count = bn_finalize(bn, stats, Co, _pixels(y))
+        z = bn_apply(y, aff[2], aff[3], residual, relu)
+        mode = 'bn_batch'
+    else:
+        y = None
+        if bn is not None:
+            aff = bn_eval_affine(bn, Co)
+            scale, shift = aff[0], aff[1]
+            if conv.bias is not None:
+                raise GsError('conv bias followed by eval-mode BN is not supported')
+            mode = 'affine'
+        else:
+            aff, scale, shift = None, None, _bias(conv, Co)
+            mode = 'plain'
+        z, _, a, g = conv_forward(x, conv, Co, scale=scale, shift=shift, residual=residual, relu=relu)
+        count = 0.0
+    if save:
+        rec.conv, rec.bn, rec.mode, rec.a, rec.x_shape, rec.geom = conv, bn, mode, a, tuple(x.shape), g
+        rec.y, rec.z, rec.aff, rec.count, rec.relu, rec.has_res, rec.Co = y, z, aff, count, relu, residual is not None, Co
+    return z, rec
+
+
+def _bias(conv, Co):
+    return None if conv.bias is None else conv.bias[:Co]
+
+
+def cba_backward(rec, dz, need_dx=True, dx_add=None):
+    """Returns (dx, dres): gradient w.r.t. the conv input (None unless need_dx) and w.r.t. the residual."""
+    dz = as_act(dz)
+    conv, bn, C = rec.conv, rec.bn, rec.Co
+    N, _, Ho, Wo = dz.shape
+    P = N * Ho * Wo
+    dev = dz.device
+    st = _stream()
+    zmask = rec.z if rec.relu else None
+    dres = new_act(N, C, Ho, Wo, dev) if rec.has_res else None
+    if rec.mode == 'bn_batch':
+        mean, invstd = rec.aff[0], rec.aff[1]
+        sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
+        call('gs_bn_bwd_reduce', dz.data_ptr(), act_ld(dz), rec.y.data_ptr(), act_ld(rec.y), _ptr(zmask),
+             act_ld(zmask) if zmask is not None else 0, mean.data_ptr(), invstd.data_ptr(), P, C, sums.data_ptr(), st)
+        gw = bn.weight is not None and bn.weight.requires_grad
+        gb = bn.bias is not None and bn.bias.requires_grad
+        if gw or gb:
+            call('gs_bn_bwd_param', sums.data_ptr(), C, _param_grad(bn.weight).data_ptr() if gw else None,
+                 _param_grad(bn.bias).data_ptr() if gb else None, 1, st)
+        pg, world = _sync_group(bn)
+        if world > 1:
+            dist.all_reduce(sums, group=pg)
+        dy = new_act(N, C, Ho, Wo, dev)
+        call('gs_bn_bwd_apply', dz.data_ptr(), act_ld(dz), rec.y.data_ptr(), act_ld(rec.y), _ptr(zmask),
+             act_ld(zmask) if zmask is not None else 0, mean.data_ptr(), invstd.data_ptr(), _ptr(bn.weight),
+             sums.data_ptr(), float(rec.count), P, C, dy.data_ptr(), C, _ptr(dres), C, st)
+    else:
+        scale = rec.aff[0] if rec.mode == 'affine' else None
+        if scale is None and zmask is None and dres is None:
+            dy = dz
+        else:
+            dy = new_act(N, C, Ho, Wo, dev)
+            call('gs_affine_bwd', dz.data_ptr(), act_ld(dz), _ptr(zmask), act_ld(zmask) if zmask is not None else 0,
+                 _ptr(scale), P, C, dy.data_ptr(), C, _ptr(dres), C, st)
+        if conv.bias is not None and conv.bias.requires_grad:
+            s = bn_stats(dy)
+            call('gs_bn_bwd_param', s.data_ptr(), C, None, _param_grad(conv.bias).data_ptr(), 1, st)
+    conv_wgrad(conv, rec.a, dy, rec.geom)
+    dx = None
+    if need_dx:
+        if is_image_conv(conv):
+            raise GsError('gradient w.r.t. the input image is not provided by the hot path')
+        dx = conv_dgrad(conv, dy, rec.geom, rec.x_shape, add=dx_add)
+    return dx, dres
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd wrappers
+# ------------------------------------------------------------------------------------------------
+class ConvBnActFn(torch.autograd.Function):
+    """One fused layer.  Parameter gradients are accumulated IN PLACE into `.grad` (KRSC fp32 for the
+    conv weight) by the kernels; autograd only routes activation gradients."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, conv, bn, relu, Co):
+        save = torch.is_grad_enabled() or ctx.needs_input_grad[0] or weight.requires_grad
+        z, rec = cba_forward(x, conv, bn, relu, residual, Co, save=save)
+        ctx.rec = rec
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        dx, dres = cba_backward(ctx.rec, dz, need_dx=ctx.needs_input_grad[0])
+        ctx.rec = None
+        return dx, dres, None, None, None, None, None
+
+
+def conv_bn_act(x, conv, bn=None, relu=False, residual=None, Co=None):
+    return ConvBnActFn.apply(x, residual, conv.weight, conv, bn, relu, Co)
+
+
+class BottleneckFn(torch.autograd.Function):
+    """DynamicBottleneck as ONE autograd node: 3 (4 with downsample) fused conv/BN layers; the residual
+    gradient is folded into conv1's dgrad epilogue, so no separate add pass exists in either direction."""
+
+    @staticmethod
+    def forward(ctx, x, weight, block):
+        save = torch.is_grad_enabled()
+        z1, r1 = cba_forward(x, block.conv1, block.norm1, True, save=save)
+        z2, r2 = cba_forward(z1, block.conv2, block.norm2, True, save=save)
+        rd = None
+        identity = x
+        if block.downsample is not None:
+            identity, rd = cba_forward(x, block.downsample[0], block.downsample[1], False, save=save)
+        z3, r3 = cba_forward(z2, block.conv3, block.norm3, True, residual=identity, save=save)
+        ctx.recs = (r1, r2, r3, rd)
+        return z3
+
+    @staticmethod
+    def backward(ctx, dout):
+        r1, r2, r3, rd = ctx.recs
+        ctx.recs = None
+        d2, dres = cba_backward(r3, dout)
+        d1, _ = cba_backward(r2, d2)
+        if rd is not None:
+            add, _ = cba_backward(rd, dres)
+        else:
+            add = dres
+        if ctx.needs_input_grad[0]:
+            dx, _ = cba_backward(r1, d1, dx_add=add)
+        else:
+            cba_backward(r1, d1, need_dx=False)
+            dx = None
+        return dx, None, None
+
+
+def bottleneck(x, block):
+    return BottleneckFn.apply(x, block.conv1.weight, block)
+
+
+class MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _lib.require_device()
+        x = as_act(x)
+        N, C, H, W = x.shape
+        Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+        y = new_act(N, C, Ho, Wo, x.device)
+        idx = None
+        if torch.is_grad_enabled() or ctx.needs_input_grad[0]:
+            idx = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=x.device)
+        call('gs_maxpool3x3s2_fwd', x.data_ptr(), N, H, W, C, act_ld(x), y.data_ptr(), Ho, Wo, C, _ptr(idx), _stream())
+        ctx.idx, ctx.xs = idx, (N, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = as_act(dy)
+        N, C, H, W = ctx.xs
+        dx = new_act(N, C, H, W, dy.device)
+        call('gs_maxpool3x3s2_bwd', dy.data_ptr(), act_ld(dy), ctx.idx.data_ptr(), N, H, W, C, dy.shape[2], dy.shape[3],
+             dx.data_ptr(), C, _stream())
+        ctx.idx = None
+        return dx
+
+
+def maxpool3x3s2(x):
+    return MaxPoolFn.apply(x)
+
+
+class CatFn(torch.autograd.Function):
+    """torch.cat([a, b], dim=1) of NHWC activations as two pitched copies; the backward is two channel-slice
+    VIEWS of the incoming gradient (the kernels take pitches), i.e. free."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        xs = [as_act(x) for x in xs]
+        N, _, H, W = xs[0].shape
+        Cs = [x.shape[1] for x in xs]
+        out = new_act(N, sum(Cs), H, W, xs[0].device)
+        P, off, st = N * H * W, 0, _stream()
+        for x, C in zip(xs, Cs):
+            call('gs_copy_channels', x.data_ptr(), act_ld(x), out[:, off:off + C].data_ptr(), sum(Cs), P, C, st)
+            off += C
+        ctx.Cs = Cs
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        d = as_act(d)
+        outs, off = [], 0
+        for C in ctx.Cs:
+            outs.append(d[:, off:off + C])
+            off += C
+        return tuple(outs)
+
+
+def cat_channels(xs):
+    return CatFn.apply(*xs)
+
+
+class Dropout2dFn(torch.autograd.Function):
+    """nn.Dropout2d (fcn_head.py:248-253): the per-(n, c) Bernoulli mask comes from torch's generator (a
+    [N, C] tensor -- control-plane sized); applying it to the feature map is the kernel."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        x = as_act(x)
+        N, C, H, W = x.shape
+        keep = 1.0 - p
+        mask = torch.bernoulli(torch.full((N, C), keep, dtype=torch.float32, device=x.device)).div_(keep)
+        y = new_act(N, C, H, W, x.device)
+        call('gs_scale_nc', x.data_ptr(), act_ld(x), mask.data_ptr(), y.data_ptr(), C, N, H * W, C, _stream())
+        ctx.mask = mask
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = as_act(dy)
+        N, C, H, W = dy.shape
+        dx = new_act(N, C, H, W, dy.device)
+        call('gs_scale_nc', dy.data_ptr(), act_ld(dy), ctx.mask.data_ptr(), dx.data_ptr(), C, N, H * W, C, _stream())
+        return dx, None
+
+
+def dropout2d(x, p, training):
+    if not training or p <= 0:
+        return x
+    return Dropout2dFn.apply(x, p)
+
+
+class ConvSegFn(torch.autograd.Function):
+    """conv_seg: 1x1 DynamicConv2d + bias producing fp32 logits (the head's `@force_fp32` boundary)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, conv, Co):
+        y, _, a, g = conv_forward(x, conv, Co, shift=_bias(conv, Co), out_f32=True)
+        ctx.conv, ctx.a, ctx.g, ctx.xs, ctx.Co = conv, a, g, tuple(x.shape), Co
+        return y
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        conv, Co = ctx.conv, ctx.Co
+        dl = as_act(dlogits, torch.float32) if act_ld(dlogits) is None or dlogits.dtype != torch.float32 else dlogits
+        N, K, h, w = dl.shape
+        P, st = N * h * w, _stream()
+        if conv.bias is not None and conv.bias.requires_grad:
+            call('gs_colsum_f32', dl.data_ptr(), act_ld(dl), P, K, _param_grad(conv.bias).data_ptr(), st)
+        Kp = round_up(K, 8)
+        dy = new_act(N, K, h, w, dl.device, BF16, ld=Kp)
+        call('gs_cast_f32_bf16', dl.data_ptr(), act_ld(dl), dy.data_ptr(), Kp, P, K, st)
+        conv_wgrad(conv, ctx.a, dy, ctx.g)
+        dx = conv_dgrad(conv, dy, ctx.g, ctx.xs) if ctx.needs_input_grad[0] else None
+        ctx.a = None
+        return dx, None, None, None, None
+
+
+def conv_seg(x, conv, Co=None):
+    return ConvSegFn.apply(x, conv.weight, conv.bias, conv, conv.width_state if Co is None else Co)
+
+
+class UpsampleCEFn(torch.autograd.Function):
+    """losses(): bilinear resize to the label size -> CE(ignore_index) mean over ALL pixels * loss_weight,
+    plus top-1 accuracy (dynamic_fcn_head.py:137-159).  Returns (loss, acc_seg, n_ignored, n_correct)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index, loss_weight):
+        _lib.require_device()
+        lg = logits if (logits.dtype == torch.float32 and act_ld(logits) is not None) else as_act(logits, torch.float32)
+        N, K, h, w = lg.shape
+        lab = labels.reshape(N, labels.shape[-2], labels.shape[-1])
+        if lab.dtype != torch.int64 or not lab.is_contiguous():
+            lab = lab.long().contiguous()
+        H, W = lab.shape[-2:]
+        dev = lg.device
+        out_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        counts = torch.zeros(2, dtype=torch.int64, device=dev)
+        rec = None
+        if torch.is_grad_enabled() or ctx.needs_input_grad[0]:
+            rec = torch.empty(_lib.load().gs_upsample_ce_record_bytes(N, H, W), dtype=torch.uint8, device=dev)
+        call('gs_upsample_ce_fwd', lg.data_ptr(), N, h, w, K, act_ld(lg), lab.data_ptr(), H, W, int(ignore_index),
+             out_sum.data_ptr(), counts.data_ptr(), _ptr(rec), _stream())
+        numel = float(N * H * W)
+        loss = (out_sum * (loss_weight / numel)).float().squeeze(0)
+        acc = (counts[1].double() * (100.0 / numel)).float()
+        ctx.lg, ctx.rec, ctx.dims, ctx.gscale = lg, rec, (N, K, h, w, H, W), loss_weight / numel
+        ctx.mark_non_differentiable(acc, counts)
+        return loss, acc, counts
+
+    @staticmethod
+    def backward(ctx, dloss, dacc, dcounts):
+        N, K, h, w, H, W = ctx.dims
+        lg = ctx.lg
+        dl = new_act(N, K, h, w, lg.device, torch.float32)
+        ds = dloss.reshape(1).float().contiguous()
+        call('gs_upsample_ce_bwd', lg.data_ptr(), N, h, w, K, act_ld(lg), ctx.rec.data_ptr(), H, W, float(ctx.gscale),
+             ds.data_ptr(), dl.data_ptr(), K, _stream())
+        ctx.rec = None
+        return dl, None, None, None
+
+
+def upsample_ce(logits, labels, ignore_index=255, loss_weight=1.0):
+    return UpsampleCEFn.apply(logits, labels, ignore_index, loss_weight)
+
+
+def upsample_argmax(logits, size):
+    """Fused bilinear resize -> argmax over classes -> int64 [N, H, W] label map (inference)."""
+    _lib.require_device()
+    lg = logits if (logits.dtype == torch.float32 and act_ld(logits) is not None) else as_act(logits, torch.float32)
+    N, K, h, w = lg.shape
+    H, W = size
+    out = torch.empty((N, H, W), dtype=torch.int64, device=lg.device)
+    call('gs_upsample_argmax', lg.data_ptr(), N, h, w, K, act_ld(lg), H, W, out.data_ptr(), _stream())
+    return out
+
+
+def upsample_bilinear_f32(logits, size):
+    lg = logits if (logits.dtype == torch.float32 and act_ld(logits) is not None) else as_act(logits, torch.float32)
+    N, K, h, w = lg.shape
+    H, W = size
+    out = new_act(N, K, H, W, lg.device, torch.float32)
+    call('gs_upsample_bilinear_f32', lg.data_ptr(), N, h, w, K, act_ld(lg), out.data_ptr(), H, W, K, _stream())
+    return out
+
+
+def to_nchw_f32(x):
+    """bf16 NHWC activation -> fp32 NCHW contiguous tensor (what the reference's modules return)."""
+    x = as_act(x)
+    N, C, H, W = x.shape
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    call('gs_nhwc_bf16_to_nchw_f32', x.data_ptr(), act_ld(x), N, C, H, W, out.data_ptr(), _stream())
+    return out
+
+
+def from_nchw_f32(x, Cpad=None):
+    """fp32 NCHW tensor -> bf16 NHWC activation (channels padded with zeros to Cpad)."""
+    _lib.require_device()
+    x = x.float().contiguous()
+    N, C, H, W = x.shape
+    Cpad = round_up(C, 8) if Cpad is None else Cpad
+    out = new_act(N, Cpad, H, W, x.device)
+    call('gs_nchw_f32_to_nhwc_bf16', x.data_ptr(), N, C, H, W, out.data_ptr(), Cpad, Cpad, _stream())
+    return out

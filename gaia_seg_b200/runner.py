@@ -1,0 +1,498 @@
+"""Training plumbing around the hot path: config loading, the data-parallel wrapper, the fused SGD optimizer,
+an iteration-based runner with the hooks the reference registers (gaiaseg/apis/train.py:118-186: poly LR,
+optimizer, checkpoint, text logger, ManipulateArchHook, eval hooks) and checkpoint IO in the reference's
+format (max-width OIHW fp32 state_dict + meta).
+
+B200-first choices:
+  * all parameters live in ONE flat fp32 master buffer (+ one flat gradient buffer, one flat momentum buffer,
+    one flat bf16 forward-shadow buffer at the same offsets) -> the optimizer is ONE kernel launch, the
+    gradient exchange is ONE bucketed NCCL all-reduce over NVLink of the flat buffer instead of DDP's
+    reducer hooks + `find_unused_parameters` graph walk (gaiaseg/apis/train.py:88-95);
+  * SyncBN statistics are packed (sum, sumsq) all-reduces issued by the layers themselves.
+"""
+import importlib.util
+import math
+import os
+import os.path as osp
+import time
+from collections import OrderedDict
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import functional as F_gs
+from ._lib import call
+from .core import DynamicConv2d
+
+
+# ------------------------------------------------------------------------------------------------
+# Config (mmcv.Config subset: python files, `_base_` inheritance, attribute access, dotted overrides)
+# ------------------------------------------------------------------------------------------------
+class ConfigDict(dict):
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        self[name] = value
+
+
+def _to_cfgdict(obj):
+    if isinstance(obj, dict):
+        return ConfigDict({k: _to_cfgdict(v) for k, v in obj.items()})
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_to_cfgdict(v) for v in obj)
+    return obj
+
+
+def _merge(base, new):
+    out = dict(base)
+    for k, v in new.items():
+        if isinstance(v, dict) and isinstance(out.get(k), dict) and not v.get('_delete_', False):
+            out[k] = _merge(out[k], v)
+        else:
+            if isinstance(v, dict):
+                v = {kk: vv for kk, vv in v.items() if kk != '_delete_'}
+            out[k] = v
+    return out
+
+
+class Config:
+    def __init__(self, cfg_dict=None, filename=None):
+        object.__setattr__(self, '_cfg_dict', _to_cfgdict(cfg_dict or {}))
+        object.__setattr__(self, 'filename', filename)
+
+    @staticmethod
+    def _file2dict(filename):
+        filename = osp.abspath(osp.expanduser(filename))
+        if not osp.isfile(filename):
+            raise FileNotFoundError(filename)
+        spec = importlib.util.spec_from_file_location('_gs_cfg_' + str(abs(hash(filename))), filename)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        cfg = {k: v for k, v in vars(mod).items()
+               if not k.startswith('__') and not isinstance(v, type(os)) and not callable(v)}
+        base = cfg.pop('_base_', None)
+        if base is not None:
+            merged = {}
+            for b in (base if isinstance(base, (list, tuple)) else [base]):
+                merged = _merge(merged, Config._file2dict(osp.join(osp.dirname(filename), b)))
+            cfg = _merge(merged, cfg)
+        return cfg
+
+    @staticmethod
+    def fromfile(filename):
+        return Config(Config._file2dict(filename), filename)
+
+    def merge_from_dict(self, options):
+        for key, val in options.items():
+            d = self._cfg_dict
+            parts = key.split('.')
+            for p in parts[:-1]:
+                d = d.setdefault(p, ConfigDict())
+            d[parts[-1]] = _to_cfgdict(val)
+
+    def get(self, key, default=None):
+        return self._cfg_dict.get(key, default)
+
+    def __getattr__(self, name):
+        return getattr(self._cfg_dict, name)
+
+    def __setattr__(self, name, value):
+        self._cfg_dict[name] = _to_cfgdict(value)
+
+    def __getitem__(self, name):
+        return self._cfg_dict[name]
+
+    def __contains__(self, name):
+        return name in self._cfg_dict
+
+    def to_dict(self):
+        return dict(self._cfg_dict)
+
+
+# ------------------------------------------------------------------------------------------------
+# distributed helpers
+# ------------------------------------------------------------------------------------------------
+def get_dist_info():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def init_dist(launcher='pytorch', backend='nccl', **kwargs):
+    """mmcv.runner.init_dist for the pytorch launcher (tools/train_supernet.py:138): env:// rendezvous."""
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', rank % max(torch.cuda.device_count(), 1)))
+    if backend == 'nccl':
+        torch.cuda.set_device(local_rank)
+        kwargs.setdefault('device_id', torch.device('cuda', local_rank))
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', '29500')
+    dist.init_process_group(backend=backend, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------------
+# flat parameter storage + fused optimizer
+# ------------------------------------------------------------------------------------------------
+_ALIGN = 64  # elements; keeps every tensor 256-byte (fp32) / 128-byte (bf16 shadow) aligned
+
+
+class FlatParams:
+    """Moves every trainable parameter of `model` into one flat fp32 buffer (views keep the logical shapes and
+    the KRSC memory order of conv weights), with matching flat gradient and bf16 shadow buffers."""
+
+    def __init__(self, model):
+        params = [p for p in model.parameters() if p.requires_grad]
+        if not params:
+            raise ValueError('model has no trainable parameters')
+        dev = params[0].device
+        if dev.type != 'cuda':
+            raise F_gs.GsError('FlatParams: the model must be on a CUDA device (call model.cuda() first)')
+        for m in model.modules():
+            if isinstance(m, DynamicConv2d):
+                F_gs.ensure_krsc(m)
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.total = total
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_shadow = torch.empty(total, dtype=torch.bfloat16, device=dev)
+        self.params, self.offsets = params, offs
+        for p, o in zip(params, offs):
+            n = p.numel()
+            if p.dim() == 4:  # conv weight: memory order [Co][kh][kw][Ci]
+                Co, Ci, kh, kw = p.shape
+                vp = self.flat_p[o:o + n].view(Co, kh, kw, Ci).permute(0, 3, 1, 2)
+                vg = self.flat_g[o:o + n].view(Co, kh, kw, Ci).permute(0, 3, 1, 2)
+            else:
+                vp = self.flat_p[o:o + n].view(p.shape)
+                vg = self.flat_g[o:o + n].view(p.shape)
+            vp.copy_(p.data)
+            p.data = vp
+            p.grad = vg
+        self.convs = []
+        off_of = {id(p): o for p, o in zip(params, offs)}
+        for m in model.modules():
+            if isinstance(m, DynamicConv2d) and id(m.weight) in off_of:
+                self.convs.append(m)
+                o, n = off_of[id(m.weight)], m.weight.numel()
+                if not F_gs.is_image_conv(m):
+                    m._gs_w_krsc = self.flat_shadow[o:o + n]   # forward shadow lives in the flat buffer
+                m._gs_key = None
+        for m in self.convs:
+            F_gs.conv_shadows(m)
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+    def all_reduce_grads(self, group=None, bucket_bytes=64 << 20):
+        """Sum the flat gradient over the data-parallel group in NCCL buckets (the mean is folded into the
+        optimizer's grad_scale).  One call per bucket over NVLink; no per-parameter hooks."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return 1
+        n = bucket_bytes // 4
+        for s in range(0, self.total, n):
+            dist.all_reduce(self.flat_g[s:s + n], group=group)
+        return dist.get_world_size(group)
+
+
+class GsSGD(torch.optim.Optimizer):
+    """SGD(momentum, weight_decay) as one fused kernel over the flat master buffer; the same launch rewrites
+    the bf16 forward shadow, then one transpose-cast per conv refreshes the dgrad shadow.
+    Semantics of torch.optim.SGD with dampening 0 / nesterov False
+    (configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:175).  Every trainable parameter is updated every
+    step (zero gradient for channels / blocks outside the sampled sub-net, like the reference after
+    `optimizer.zero_grad()` once each block has been visited by the MAX sub-net)."""
+
+    def __init__(self, model_or_flat, lr=0.01, momentum=0.9, weight_decay=0.0, grad_scale=1.0):
+        self.flat = model_or_flat if isinstance(model_or_flat, FlatParams) else FlatParams(model_or_flat)
+        defaults = dict(lr=lr, momentum=momentum, weight_decay=weight_decay, initial_lr=lr)
+        super().__init__(self.flat.params, defaults)
+        self.momentum_buf = torch.zeros_like(self.flat.flat_p)
+        self.grad_scale = grad_scale
+        self._steps = 0
+
+    def zero_grad(self, set_to_none=False):
+        self.flat.zero_grad()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        g = self.param_groups[0]
+        f = self.flat
+        call('gs_sgd_flat', f.flat_p.data_ptr(), f.flat_g.data_ptr(), self.momentum_buf.data_ptr(), f.total,
+             float(g['lr']), float(g['momentum']), float(g['weight_decay']), float(self.grad_scale),
+             1 if self._steps == 0 else 0, f.flat_shadow.data_ptr(), F_gs._stream())
+        for m in f.convs:
+            F_gs.refresh_crsk(m)
+        self._steps += 1
+
+    def state_dict(self):
+        return dict(momentum_buf=self.momentum_buf, steps=self._steps,
+                    param_groups=[{k: v for k, v in g.items() if k != 'params'} for g in self.param_groups])
+
+    def load_state_dict(self, sd):
+        self.momentum_buf.copy_(sd['momentum_buf'])
+        self._steps = sd['steps']
+        for g, s in zip(self.param_groups, sd['param_groups']):
+            g.update(s)
+
+
+def build_optimizer(model, cfg):
+    cfg = dict(cfg)
+    typ = cfg.pop('type', 'SGD')
+    if typ != 'SGD':
+        raise NotImplementedError(f'optimizer {typ}: the GAIA-seg recipe is SGD')
+    if cfg.pop('nesterov', False) or cfg.pop('dampening', 0):
+        raise NotImplementedError('nesterov / dampening are not used by the GAIA-seg recipe')
+    module = model.module if hasattr(model, 'module') else model
+    return GsSGD(module, **cfg)
+
+
+class GsDataParallel(nn.Module):
+    """Stand-in for MMDistributedDataParallel(model.cuda(), broadcast_buffers=False,
+    find_unused_parameters=True) (gaiaseg/apis/train.py:88-95): one process per GPU, `.module` access,
+    `train_step` / `val_step` forwarding.  Gradient exchange is `FlatParams.all_reduce_grads` called by the
+    optimizer hook after backward."""
+
+    def __init__(self, module, device_ids=None, broadcast_buffers=False, find_unused_parameters=True, **kw):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def train_step(self, *args, **kwargs):
+        return self.module.train_step(*args, **kwargs)
+
+    def val_step(self, *args, **kwargs):
+        return self.module.val_step(*args, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------------
+# checkpoint IO
+# ------------------------------------------------------------------------------------------------
+# the stem norm's attribute name is whatever gaiavision's build_norm_layer returned -- unverifiable, so
+# accept the common spellings when loading
+_KEY_REMAP = (('backbone.norm1.', 'backbone.bn1.'), ('norm1.', 'bn1.'))
+
+
+def _unwrap(model):
+    return model.module if hasattr(model, 'module') and isinstance(model.module, nn.Module) else model
+
+
+def save_checkpoint(model, filename, optimizer=None, meta=None):
+    model = _unwrap(model)
+    sd = OrderedDict((k, v.detach().cpu().contiguous()) for k, v in model.state_dict().items())
+    ckpt = dict(meta=dict(meta or {}, time=time.asctime()), state_dict=sd)
+    if optimizer is not None:
+        ckpt['optimizer'] = {k: (v.detach().cpu() if torch.is_tensor(v) else v)
+                             for k, v in optimizer.state_dict().items()}
+    os.makedirs(osp.dirname(osp.abspath(filename)), exist_ok=True)
+    torch.save(ckpt, filename)
+
+
+def load_checkpoint(model, filename, map_location='cpu', strict=False, logger=None):
+    ckpt = torch.load(filename, map_location=map_location, weights_only=False)
+    sd = ckpt.get('state_dict', ckpt) if isinstance(ckpt, dict) else ckpt
+    sd = OrderedDict((k[7:] if k.startswith('module.') else k, v) for k, v in sd.items())
+    model = _unwrap(model)
+    own = model.state_dict()
+    fixed = OrderedDict()
+    for k, v in sd.items():
+        if k not in own:
+            for a, b in _KEY_REMAP:
+                if k.startswith(a) and (b + k[len(a):]) in own:
+                    k = b + k[len(a):]
+                    break
+        fixed[k] = v
+    with torch.no_grad():
+        missing, unexpected = [], [k for k in fixed if k not in own]
+        for k, dst in own.items():
+            if k not in fixed:
+                missing.append(k)
+                continue
+            src = fixed[k]
+            if tuple(src.shape) != tuple(dst.shape):
+                raise RuntimeError(f'size mismatch for {k}: checkpoint {tuple(src.shape)} vs model {tuple(dst.shape)}')
+            dst.copy_(src)   # in place: keeps the flat-buffer views and bumps _version (shadows refresh)
+    if strict and (missing or unexpected):
+        raise RuntimeError(f'missing keys {missing}, unexpected keys {unexpected}')
+    return ckpt
+
+
+# ------------------------------------------------------------------------------------------------
+# hooks + runner
+# ------------------------------------------------------------------------------------------------
+class Hook:
+    def before_run(self, runner): pass
+    def after_run(self, runner): pass
+    def before_train_iter(self, runner): pass
+    def after_train_iter(self, runner): pass
+
+    @staticmethod
+    def every_n_iters(runner, n):
+        return (runner.iter + 1) % n == 0 if n > 0 else False
+
+
+class PolyLrUpdaterHook(Hook):
+    """lr = (base - min_lr) * (1 - iter/max_iters)^power + min_lr   (mmcv PolyLrUpdaterHook, by_epoch=False)."""
+
+    def __init__(self, power=1.0, min_lr=0.0, by_epoch=False, **kw):
+        self.power, self.min_lr = power, min_lr
+
+    def before_run(self, runner):
+        self.base_lr = [g.setdefault('initial_lr', g['lr']) for g in runner.optimizer.param_groups]
+
+    def before_train_iter(self, runner):
+        coeff = (1 - runner.iter / runner.max_iters) ** self.power
+        for g, base in zip(runner.optimizer.param_groups, self.base_lr):
+            g['lr'] = (base - self.min_lr) * coeff + self.min_lr
+
+
+class OptimizerHook(Hook):
+    """zero_grad -> backward -> (gradient all-reduce) -> step  (mmcv OptimizerHook.after_train_iter)."""
+
+    def __init__(self, grad_clip=None, **kw):
+        if grad_clip is not None:
+            raise NotImplementedError('grad_clip is not used by the GAIA-seg recipe')
+
+    def after_train_iter(self, runner):
+        opt = runner.optimizer
+        opt.zero_grad()
+        runner.outputs['loss'].backward()
+        if isinstance(opt, GsSGD):
+            world = opt.flat.all_reduce_grads()
+            opt.grad_scale = 1.0 / world
+        opt.step()
+
+
+class CheckpointHook(Hook):
+    def __init__(self, interval=-1, by_epoch=False, out_dir=None, **kw):
+        self.interval, self.out_dir = interval, out_dir
+
+    def after_train_iter(self, runner):
+        if self.every_n_iters(runner, self.interval) and runner.rank == 0:
+            out = self.out_dir or runner.work_dir
+            path = osp.join(out, f'iter_{runner.iter + 1}.pth')
+            save_checkpoint(runner.model, path, optimizer=runner.optimizer, meta=dict(runner.meta or {}, iter=runner.iter + 1))
+            latest = osp.join(out, 'latest.pth')
+            if osp.lexists(latest):
+                os.remove(latest)
+            os.symlink(osp.basename(path), latest)
+
+
+class TextLoggerHook(Hook):
+    def __init__(self, interval=50, by_epoch=False, **kw):
+        self.interval = interval
+        self._t = None
+
+    def before_run(self, runner):
+        self._t = time.time()
+
+    def after_train_iter(self, runner):
+        if self.every_n_iters(runner, self.interval):
+            lv = runner.outputs['log_vars']
+            now = time.time()
+            dt = (now - self._t) / self.interval
+            self._t = now
+            if runner.rank == 0:
+                msg = ', '.join(f'{k}: {v:.4f}' for k, v in lv.items())
+                lr = runner.optimizer.param_groups[0]['lr']
+                print(f'Iter [{runner.iter + 1}/{runner.max_iters}] lr: {lr:.3e}, time: {dt:.3f}, {msg}', flush=True)
+
+
+class IterBasedRunner:
+    """mmcv IterBasedRunner for the single ('train', 1) workflow of the reference config."""
+
+    def __init__(self, model, optimizer=None, work_dir=None, logger=None, meta=None, max_iters=None, **kw):
+        self.model, self.optimizer, self.work_dir, self.logger, self.meta = model, optimizer, work_dir, logger, meta
+        self.max_iters = max_iters
+        self.iter = 0
+        self.hooks = []
+        self.outputs = None
+        self.rank, self.world_size = get_dist_info()
+        self.timestamp = None
+
+    def register_hook(self, hook, priority='NORMAL'):
+        self.hooks.append(hook)
+
+    def register_training_hooks(self, lr_config, optimizer_config=None, checkpoint_config=None, log_config=None,
+                                momentum_config=None):
+        if lr_config is not None:
+            cfg = dict(lr_config)
+            policy = cfg.pop('policy', 'poly')
+            if policy != 'poly':
+                raise NotImplementedError(f'lr policy {policy}: the GAIA-seg recipe is poly')
+            self.register_hook(PolyLrUpdaterHook(**cfg))
+        self.register_hook(OptimizerHook(**dict(optimizer_config or {})))
+        if checkpoint_config is not None:
+            self.register_hook(CheckpointHook(**dict(checkpoint_config)))
+        if log_config is not None:
+            for h in log_config.get('hooks', []):
+                if h.get('type') == 'TextLoggerHook':
+                    self.register_hook(TextLoggerHook(interval=log_config.get('interval', 50)))
+
+    def call_hook(self, name):
+        # LR and arch hooks run before the iteration in registration order; the optimizer hook first after it
+        for h in self.hooks:
+            getattr(h, name, lambda r: None)(self)
+
+    def load_checkpoint(self, filename, map_location='cpu', strict=False):
+        return load_checkpoint(self.model, filename, map_location, strict)
+
+    def resume(self, checkpoint):
+        ckpt = self.load_checkpoint(checkpoint)
+        self.iter = ckpt.get('meta', {}).get('iter', 0)
+        if 'optimizer' in ckpt and self.optimizer is not None:
+            self.optimizer.load_state_dict(ckpt['optimizer'])
+
+    def run(self, data_loaders, workflow=None, max_iters=None, **kw):
+        if max_iters is not None:
+            self.max_iters = max_iters
+        loader = data_loaders[0] if isinstance(data_loaders, (list, tuple)) else data_loaders
+        self.model.train()
+        self.call_hook('before_run')
+        it = iter(loader)
+        while self.iter < self.max_iters:
+            try:
+                data_batch = next(it)
+            except StopIteration:
+                it = iter(loader)
+                data_batch = next(it)
+            self.call_hook('before_train_iter')
+            data_batch = scatter_batch(data_batch)
+            self.outputs = self.model.train_step(data_batch, self.optimizer)
+            self.call_hook('after_train_iter')
+            self.iter += 1
+        self.call_hook('after_run')
+
+
+def scatter_batch(batch, device=None):
+    """host -> device copy of one batch (MMDDP.scatter): img fp32, gt_semantic_seg int64, metas untouched."""
+    device = device or torch.device('cuda', torch.cuda.current_device())
+    out = {}
+    for k, v in batch.items():
+        if torch.is_tensor(v):
+            out[k] = v.to(device, non_blocking=True)
+        elif isinstance(v, list) and v and torch.is_tensor(v[0]):
+            out[k] = [t.to(device, non_blocking=True) for t in v]
+        else:
+            out[k] = v
+    return out
+
+
+def build_runner(cfg, default_args=None):
+    cfg = dict(cfg)
+    typ = cfg.pop('type', 'IterBasedRunner')
+    if typ != 'IterBasedRunner':
+        raise NotImplementedError(f'runner {typ}: the GAIA-seg recipe uses IterBasedRunner')
+    args = dict(default_args or {})
+    args.update(cfg)
+    args.pop('batch_processor', None)
+    return IterBasedRunner(**args)

@@ -18,7 +18,7 @@
  *   - conv weights are the MAX-WIDTH supernet tensors; kernels address the active
  *     channel-prefix slice [0:Co, 0:Ci] in place through TMA descriptors (no slice copy):
  *       w_krsc : bf16 [Co_max][kh][kw][Ci_max]   (forward  B operand)
- *       w_crsk : bf16 [Ci_max][kh][kw][Co_max]   (dgrad    B operand)
+ *       w_crsk : bf16 [Ci_max][kh][kw][Co_pad]   (dgrad    B operand; Co_pad = Co_max rounded up to 8)
  *       dw_krsc: fp32 [Co_max][kh][kw][Ci_max]   (wgrad accumulator; == channels_last OIHW)
  *   - statistics buffers are fp64 [2*C]: sum[0:C], sum of squares [C:2C].
  */
@@ -187,14 +187,15 @@ int gs_colsum_f32(const float* src, int32_t ld, int64_t P, int32_t C, float* out
  *   pix_rec : gs_upsample_ce_record_bytes(N,H,W) bytes of scratch the backward pass re-reads (may be NULL
  *             for forward-only);  loss = loss_weight * out_sum / (N*H*W)   (mean over ALL pixels).
  *   labels outside [0,K) other than ignore_index count as ignored (the reference would raise).
- * backward: dlogits[n,i,j,k] = grad_scale * d(sum CE)/dlogit  (written, not accumulated; gather form). */
+ * backward: dlogits[n,i,j,k] = grad_scale * (*grad_scale_dev, if non-NULL: the upstream dloss scalar, read on
+ *   the device so the host never synchronises) * d(sum CE)/dlogit  (written, not accumulated; gather form). */
 int64_t gs_upsample_ce_record_bytes(int32_t N, int32_t H, int32_t W);
 int gs_upsample_ce_fwd(const float* logits, int32_t N, int32_t h, int32_t w, int32_t K, int32_t ld,
                        const int64_t* labels, int32_t H, int32_t W, int32_t ignore_index, double* out_sum,
                        int64_t* out_counts, void* pix_rec, void* stream);
 int gs_upsample_ce_bwd(const float* logits, int32_t N, int32_t h, int32_t w, int32_t K, int32_t ld,
-                       const void* pix_rec, int32_t H, int32_t W, float grad_scale, float* dlogits, int32_t dl_ld,
-                       void* stream);
+                       const void* pix_rec, int32_t H, int32_t W, float grad_scale, const float* grad_scale_dev,
+                       float* dlogits, int32_t dl_ld, void* stream);
 
 /* Fused bilinear upsample -> argmax (softmax is monotone, skipped).  Ties -> lowest class index.
  * replaces: whole_inference + softmax + argmax, restated at
@@ -216,7 +217,8 @@ int gs_upsample_bilinear_f32(const float* src, int32_t N, int32_t h, int32_t w, 
  * replaces torch.optim.SGD.step (configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:175-178) */
 int gs_sgd_flat(float* p, const float* g, float* momentum_buf, int64_t n, float lr, float momentum,
                 float weight_decay, float grad_scale, int32_t first_step, void* shadow_bf16, void* stream);
-/* dgrad shadow of one conv weight: fp32 [Co][R][Ci] (R = kh*kw) -> bf16 [Ci][R][Co] */
+/* dgrad shadow of one conv weight: fp32 [Co][R][Ci] (R = kh*kw) -> bf16 [Ci][R][Co_pad], Co_pad = Co rounded
+ * up to a multiple of 8 (TMA pitch alignment; the padding columns are never read). */
 int gs_transpose_cast(const float* w_krsc_f32, void* w_crsk_bf16, int32_t Co, int32_t R, int32_t Ci, void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,501 @@
+"""Parity checks CUDA path vs the CPU oracle (oracle/ref_model.py), shared by the `-m gpu` tests and by
+tools/gpu_diag.py (which runs ALL of them without stopping at the first failure and dumps a JSON report).
+
+Every check returns a dict(name=..., ok=bool, err=..., tol=..., **details).  Inputs are bf16-representable so
+the only differences are fp32 accumulation order and the bf16 rounding of the OUTPUT:
+    tolerance for a bf16 output tensor  : |got - ref| <= 2^-8 * |ref| + 2^-8 * rms(ref)   (one bf16 ulp, relative
+                                          to the element or to the tensor scale, whichever is larger)
+    tolerance for an fp32 output tensor : |got - ref| <= 1e-3 * max(|ref|, rms(ref))       (north-star 1e-3 relative)
+"""
+import math
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import ref_model as O  # noqa: E402
+
+BF16_EPS = 2.0 ** -8
+
+
+def bf16r(t):
+    """Round an fp32 tensor to bf16-representable values (kept in fp32)."""
+    return t.to(torch.bfloat16).float()
+
+
+def rel_err(got, ref, eps_rel, name):
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    if got.shape != ref.shape:
+        return dict(name=name, ok=False, err=float('inf'), tol=eps_rel, why=f'shape {tuple(got.shape)} vs {tuple(ref.shape)}')
+    if not torch.isfinite(got).all():
+        return dict(name=name, ok=False, err=float('inf'), tol=eps_rel, why='non-finite values in CUDA result')
+    rms = float(ref.pow(2).mean().sqrt()) if ref.numel() else 0.0
+    denom = torch.maximum(ref.abs(), torch.full_like(ref, rms)) + 1e-30
+    e = ((got - ref).abs() / denom)
+    err = float(e.max()) if e.numel() else 0.0
+    return dict(name=name, ok=err <= eps_rel, err=err, tol=eps_rel, rms=rms)
+
+
+def check_bf16(got, ref, name, ulps=2.0):
+    return rel_err(got, ref, ulps * BF16_EPS, name)
+
+
+def check_f32(got, ref, name, tol=1e-3):
+    return rel_err(got, ref, tol, name)
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # name,            N, H,  W,  Ci, Co, k, s, p, d, Ci_max, Co_max
+    ('1x1_basic',      2, 16, 16, 64, 64, 1, 1, 0, 1, 64, 64),
+    ('1x1_k320_n80',   2, 32, 32, 320, 80, 1, 1, 0, 1, 320, 80),
+    ('1x1_c48',        1, 16, 32, 48, 48, 1, 1, 0, 1, 80, 80),
+    ('3x3_basic',      2, 16, 16, 64, 64, 3, 1, 1, 1, 64, 64),
+    ('3x3_dil2',       1, 24, 24, 96, 96, 3, 1, 2, 2, 160, 160),
+    ('3x3_dil4',       1, 24, 32, 64, 128, 3, 1, 4, 4, 64, 128),
+    ('3x3_s2',         2, 32, 32, 96, 96, 3, 2, 1, 1, 160, 160),
+    ('1x1_s2',         2, 32, 32, 192, 384, 1, 2, 0, 1, 320, 640),
+    ('1x1_n640',       1, 16, 16, 128, 640, 1, 1, 0, 1, 128, 640),
+    ('3x3_prefix',     1, 16, 16, 96, 192, 3, 1, 1, 1, 160, 320),
+    ('3x3_ragged',     1, 17, 23, 64, 80, 3, 1, 1, 1, 64, 80),
+    ('3x3_s2_ragged',  1, 19, 27, 64, 64, 3, 2, 1, 1, 64, 64),
+    ('3x3_bigk',       1, 8, 16, 640, 512, 3, 1, 1, 1, 640, 512),
+]
+
+
+def _mk_conv(case, dev, gs, bias=False):
+    name, N, H, W, Ci, Co, k, s, p, d, Ci_max, Co_max = case
+    g = torch.Generator().manual_seed(hash(name) % (2 ** 31))
+    conv = gs.DynamicConv2d(Ci_max, Co_max, k, stride=s, padding=p, dilation=d, bias=bias)
+    with torch.no_grad():
+        conv.weight.copy_(bf16r(torch.randn(Co_max, Ci_max, k, k, generator=g) / math.sqrt(Ci * k * k)))
+        if bias:
+            conv.bias.copy_(torch.randn(Co_max, generator=g) * 0.1)
+    conv = conv.to(dev)
+    conv.manipulate_width(Co)
+    x = bf16r(torch.randn(N, Ci, H, W, generator=g))
+    return conv, x, g
+
+
+def conv_case_checks(case, gs, impl=None):
+    """fwd / dgrad / wgrad of one geometry against F.conv2d on the CPU (fp64)."""
+    Fg = gs.functional
+    if impl is not None:
+        old = Fg.CONV_IMPL
+        Fg.CONV_IMPL = impl
+    try:
+        name, N, H, W, Ci, Co, k, s, p, d, Ci_max, Co_max = case
+        tag = f'conv[{name}]' + (f'[{impl}]' if impl else '')
+        dev = torch.device('cuda')
+        conv, x, g = _mk_conv(case, dev, gs)
+        out = []
+        xd = x.double().requires_grad_(True)
+        wd = conv.weight.detach().cpu().double()[:Co, :Ci].clone().requires_grad_(True)
+        ref = F.conv2d(xd, wd, None, s, p, d)
+        dy = bf16r(torch.randn(ref.shape, generator=g))
+        ref.backward(dy.double())
+        xa = Fg.as_act(x.to(dev))
+        y, stats, a, geom = Fg.conv_forward(xa, conv, Co, want_stats=True)
+        torch.cuda.synchronize()
+        out.append(check_bf16(y.float(), ref, tag + '.fwd'))
+        yr = y.float().double().cpu()
+        st_ref = torch.cat([yr.sum((0, 2, 3)), (yr * yr).sum((0, 2, 3))])
+        out.append(check_f32(stats, st_ref, tag + '.stats', 1e-4))
+        dya = Fg.as_act(dy.to(dev))
+        dx = Fg.conv_dgrad(conv, dya, geom, tuple(x.shape))
+        torch.cuda.synchronize()
+        out.append(check_bf16(dx.float(), xd.grad, tag + '.dgrad'))
+        conv.weight.grad = None
+        Fg.conv_wgrad(conv, a, dya, geom)
+        torch.cuda.synchronize()
+        gw = conv.weight.grad.detach().cpu()
+        out.append(check_f32(gw[:Co, :Ci], wd.grad, tag + '.wgrad', 2e-3))
+        rest = gw.clone()
+        rest[:Co, :Ci] = 0
+        out.append(dict(name=tag + '.wgrad_outside_slice_zero', ok=bool((rest == 0).all()), err=float(rest.abs().max()), tol=0))
+        return out
+    finally:
+        if impl is not None:
+            Fg.CONV_IMPL = old
+
+
+def conv_epilogue_checks(gs):
+    """scale / shift / residual / relu epilogue, fp32 logits output (Co = 19 + bias)."""
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    out = []
+    case = ('epi', 2, 16, 24, 96, 80, 3, 1, 1, 1, 160, 160)
+    conv, x, g = _mk_conv(case, dev, gs)
+    Co = 80
+    scale = (torch.rand(Co, generator=g) + 0.5)
+    shift = torch.randn(Co, generator=g)
+    res = bf16r(torch.randn(2, Co, 16, 24, generator=g))
+    ref = F.conv2d(x.double(), conv.weight.detach().cpu().double()[:Co, :96], None, 1, 1, 1)
+    ref = torch.relu(ref * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1) + res.double())
+    z, _, _, _ = Fg.conv_forward(Fg.as_act(x.to(dev)), conv, Co, scale=scale.to(dev), shift=shift.to(dev),
+                                 residual=Fg.as_act(res.to(dev)), relu=True)
+    torch.cuda.synchronize()
+    out.append(check_bf16(z.float(), ref, 'conv.epilogue_scale_shift_res_relu'))
+    case = ('seg', 2, 16, 24, 512, 19, 1, 1, 0, 1, 512, 19)
+    conv, x, g = _mk_conv(case, dev, gs, bias=True)
+    ref = F.conv2d(x.double(), conv.weight.detach().cpu().double(), conv.bias.detach().cpu().double())
+    y, _, _, _ = Fg.conv_forward(Fg.as_act(x.to(dev)), conv, 19, shift=conv.bias[:19], out_f32=True)
+    torch.cuda.synchronize()
+    out.append(check_f32(y, ref, 'conv.logits_f32_co19_bias'))
+    return out
+
+
+def image_conv_checks(gs):
+    """first conv: im2col of the fp32 image + GEMM, fwd and wgrad (7x7 s2 p3 and 3x3 s2 p1)."""
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    out = []
+    for k, s, p, Co, Co_max in ((7, 2, 3, 32, 64), (3, 2, 1, 32, 32)):
+        g = torch.Generator().manual_seed(k)
+        conv = gs.DynamicConv2d(3, Co_max, k, stride=s, padding=p, bias=False)
+        with torch.no_grad():
+            conv.weight.copy_(bf16r(torch.randn(Co_max, 3, k, k, generator=g) / math.sqrt(3 * k * k)))
+        conv = conv.to(dev)
+        conv.manipulate_width(Co)
+        x = bf16r(torch.randn(2, 3, 34, 50, generator=g))
+        xd = x.double()
+        wd = conv.weight.detach().cpu().double()[:Co].clone().requires_grad_(True)
+        ref = F.conv2d(xd, wd, None, s, p)
+        dy = bf16r(torch.randn(ref.shape, generator=g))
+        ref.backward(dy.double())
+        y, _, a, geom = Fg.conv_forward(x.to(dev), conv, Co)
+        torch.cuda.synchronize()
+        out.append(check_bf16(y.float(), ref, f'image_conv{k}x{k}.fwd'))
+        conv.weight.grad = None
+        Fg.conv_wgrad(conv, a, Fg.as_act(dy.to(dev)), geom)
+        torch.cuda.synchronize()
+        out.append(check_f32(conv.weight.grad[:Co].cpu(), wd.grad, f'image_conv{k}x{k}.wgrad', 2e-3))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# batch norm, pooling, loss
+# ------------------------------------------------------------------------------------------------
+def bn_checks(gs):
+    """conv -> DynBN(train) -> ReLU (+ residual) forward and backward against the oracle modules, including
+    the running-stat update of the channel prefix."""
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    out = []
+    for relu, with_res, C, Cmax in ((True, False, 64, 64), (True, True, 48, 80), (False, False, 96, 160)):
+        g = torch.Generator().manual_seed(C + relu * 7 + with_res * 13)
+        tag = f'cba[C{C}/{Cmax},relu={int(relu)},res={int(with_res)}]'
+        oc = O.DynamicConv2d(32, Cmax, 3, padding=1, bias=False)
+        ob = O.DynamicBatchNorm2d(Cmax)
+        with torch.no_grad():
+            oc.weight.copy_(bf16r(torch.randn(oc.weight.shape, generator=g) * 0.1))
+            ob.weight.copy_(torch.rand(Cmax, generator=g) + 0.5)
+            ob.bias.copy_(torch.randn(Cmax, generator=g) * 0.1)
+        oc.manipulate_width(C)
+        conv = gs.DynamicConv2d(32, Cmax, 3, padding=1, bias=False)
+        bn = gs.DynamicBatchNorm2d(Cmax)
+        conv.load_state_dict(oc.state_dict())
+        bn.load_state_dict(ob.state_dict())
+        conv, bn = conv.to(dev), bn.to(dev)
+        conv.manipulate_width(C)
+        x = bf16r(torch.randn(2, 32, 12, 20, generator=g))
+        res = bf16r(torch.randn(2, C, 12, 20, generator=g)) if with_res else None
+        dz = bf16r(torch.randn(2, C, 12, 20, generator=g))
+        # oracle (fp32 CPU)
+        xo = x.clone().requires_grad_(True)
+        ro = res.clone().requires_grad_(True) if with_res else None
+        oc.train(); ob.train()
+        yo = ob(oc(xo))
+        if with_res:
+            yo = yo + ro
+        zo = torch.relu(yo) if relu else yo
+        zo.backward(dz)
+        # CUDA
+        xg = Fg.as_act(x.to(dev)).requires_grad_(True)
+        rg = Fg.as_act(res.to(dev)).requires_grad_(True) if with_res else None
+        conv.train(); bn.train()
+        zg = Fg.conv_bn_act(xg, conv, bn, relu=relu, residual=rg)
+        zg.backward(Fg.as_act(dz.to(dev)))
+        torch.cuda.synchronize()
+        out.append(check_bf16(zg.float(), zo, tag + '.fwd', 4.0))
+        out.append(check_bf16(xg.grad.float(), xo.grad, tag + '.dx', 6.0))
+        if with_res:
+            out.append(check_bf16(rg.grad.float(), ro.grad, tag + '.dres', 2.0))
+        out.append(check_f32(conv.weight.grad[:C].cpu(), oc.weight.grad[:C], tag + '.dw', 2e-2))
+        out.append(check_f32(bn.weight.grad[:C].cpu(), ob.weight.grad[:C], tag + '.dgamma', 2e-2))
+        out.append(check_f32(bn.bias.grad[:C].cpu(), ob.bias.grad[:C], tag + '.dbeta', 2e-2))
+        out.append(check_f32(bn.running_mean.cpu(), ob.running_mean, tag + '.running_mean', 5e-3))
+        out.append(check_f32(bn.running_var.cpu(), ob.running_var, tag + '.running_var', 5e-3))
+        untouched = bool((bn.running_mean[C:] == 0).all() and (bn.running_var[C:] == 1).all())
+        out.append(dict(name=tag + '.running_stats_outside_slice_untouched', ok=untouched, err=0.0, tol=0))
+        # eval mode (running stats, fused epilogue)
+        oc.eval(); ob.eval(); conv.eval(); bn.eval()
+        with torch.no_grad():
+            ze = ob(oc(x))
+            if with_res:
+                ze = ze + res
+            ze = torch.relu(ze) if relu else ze
+            zge = Fg.conv_bn_act(Fg.as_act(x.to(dev)), conv, bn, relu=relu,
+                                 residual=Fg.as_act(res.to(dev)) if with_res else None)
+        torch.cuda.synchronize()
+        out.append(check_bf16(zge.float(), ze, tag + '.eval_fwd', 4.0))
+    return out
+
+
+def standalone_bn_checks(gs):
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(5)
+    C, Cmax = 40, 64
+    ob = O.DynamicBatchNorm2d(Cmax)
+    with torch.no_grad():
+        ob.weight.copy_(torch.rand(Cmax, generator=g) + 0.5)
+        ob.bias.copy_(torch.randn(Cmax, generator=g) * 0.1)
+    bn = gs.DynamicBatchNorm2d(Cmax)
+    bn.load_state_dict(ob.state_dict())
+    bn = bn.to(dev)
+    x = bf16r(torch.randn(3, C, 9, 14, generator=g) * 2 + 1)
+    dz = bf16r(torch.randn(3, C, 9, 14, generator=g))
+    xo = x.clone().requires_grad_(True)
+    zo = ob(xo)
+    zo.backward(dz)
+    xg = Fg.as_act(x.to(dev)).requires_grad_(True)
+    zg = bn(xg)
+    zg.backward(Fg.as_act(dz.to(dev)))
+    torch.cuda.synchronize()
+    return [check_bf16(zg.float(), zo, 'dynbn_standalone.fwd', 3.0), check_bf16(xg.grad.float(), xo.grad, 'dynbn_standalone.dx', 4.0),
+            check_f32(bn.weight.grad[:C].cpu(), ob.weight.grad[:C], 'dynbn_standalone.dgamma', 1e-2)]
+
+
+def maxpool_checks(gs):
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    out = []
+    for (N, C, H, W) in ((2, 32, 16, 24), (1, 64, 17, 31)):
+        g = torch.Generator().manual_seed(H)
+        x = bf16r(torch.relu(torch.randn(N, C, H, W, generator=g)))
+        xo = x.clone().requires_grad_(True)
+        yo = F.max_pool2d(xo, 3, 2, 1)
+        dy = bf16r(torch.randn(yo.shape, generator=g))
+        yo.backward(dy)
+        xg = Fg.as_act(x.to(dev)).requires_grad_(True)
+        yg = Fg.maxpool3x3s2(xg)
+        yg.backward(Fg.as_act(dy.to(dev)))
+        torch.cuda.synchronize()
+        out.append(dict(name=f'maxpool[{H}x{W}].fwd_exact', ok=bool((yg.float().cpu() == yo).all()), err=float((yg.float().cpu() - yo).abs().max()), tol=0))
+        out.append(check_bf16(xg.grad.float(), xo.grad, f'maxpool[{H}x{W}].bwd', 2.0))
+    return out
+
+
+def _labels(g, N, K, H, W, ignore_ratio=0.1):
+    lab = torch.randint(0, K, (N, 1, H, W), generator=g)
+    lab[torch.rand(N, 1, H, W, generator=g) < ignore_ratio] = 255
+    return lab
+
+
+def loss_checks(gs, cases=((2, 19, 16, 32, 128, 256), (1, 150, 8, 8, 64, 64), (2, 19, 7, 9, 33, 50), (1, 19, 16, 16, 16, 16))):
+    """fused upsample + CE(ignore) + accuracy and its gradient vs the oracle (F.interpolate -> cross_entropy)."""
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    out = []
+    for (N, K, h, w, H, W) in cases:
+        g = torch.Generator().manual_seed(K * 1000 + h)
+        tag = f'upsample_ce[N{N},K{K},{h}x{w}->{H}x{W}]'
+        logits = torch.randn(N, K, h, w, generator=g) * 3
+        lab = _labels(g, N, K, H, W)
+        lo = logits.clone().requires_grad_(True)
+        up = F.interpolate(lo, size=(H, W), mode='bilinear', align_corners=False)
+        loss_o = 0.4 * O.cross_entropy(up, lab.squeeze(1), 255)
+        acc_o = O.accuracy(up, lab.squeeze(1))
+        loss_o.backward()
+        lg = logits.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        loss_g, acc_g, counts = Fg.upsample_ce(lg, lab.to(dev), 255, 0.4)
+        loss_g.backward()
+        torch.cuda.synchronize()
+        out.append(check_f32(loss_g.reshape(1), loss_o.reshape(1), tag + '.loss', 1e-4))
+        n_ign = int((lab == 255).sum())
+        out.append(dict(name=tag + '.ignored_count_exact', ok=int(counts[0]) == n_ign, err=abs(int(counts[0]) - n_ign), tol=0))
+        hits_o = int(round(float(acc_o) * lab.numel() / 100.0))
+        # arg-max hits are bit-exact except where the oracle's top-2 margin is within fp32 rounding of the lerp
+        top2 = up.detach().topk(2, dim=1).values
+        fragile = int(((top2[:, 0] - top2[:, 1]).abs() < 1e-5).sum())
+        d = abs(int(counts[1]) - hits_o)
+        out.append(dict(name=tag + '.correct_count', ok=d <= fragile, err=d, tol=fragile))
+        out.append(check_f32(lg.grad, lo.grad, tag + '.dlogits', 2e-3))
+    return out
+
+
+def argmax_checks(gs):
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    out = []
+    for (N, K, h, w, H, W) in ((1, 19, 16, 32, 128, 256), (2, 150, 9, 7, 40, 33)):
+        g = torch.Generator().manual_seed(h * 31 + K)
+        logits = torch.randn(N, K, h, w, generator=g)
+        up = F.interpolate(logits, size=(H, W), mode='bilinear', align_corners=False)
+        ref = F.softmax(up, dim=1).argmax(dim=1)
+        got = Fg.upsample_argmax(logits.to(dev).contiguous(memory_format=torch.channels_last), (H, W)).cpu()
+        top2 = up.topk(2, dim=1).values
+        fragile = (top2[:, 0] - top2[:, 1]).abs() < 1e-5
+        bad = (got != ref) & ~fragile
+        out.append(dict(name=f'upsample_argmax[K{K},{h}x{w}->{H}x{W}]', ok=int(bad.sum()) == 0, err=int(bad.sum()),
+                        tol=0, mismatches_at_ties=int(((got != ref) & fragile).sum())))
+    # exactly representable case: integer logits, x2 upsample (weights 0.25 / 0.75) -> bit-exact incl. ties
+    g = torch.Generator().manual_seed(9)
+    logits = torch.randint(-3, 4, (1, 8, 12, 12), generator=g).float()
+    up = F.interpolate(logits, size=(24, 24), mode='bilinear', align_corners=False)
+    ref = up.argmax(dim=1)
+    got = Fg.upsample_argmax(logits.to(dev).contiguous(memory_format=torch.channels_last), (24, 24)).cpu()
+    out.append(dict(name='upsample_argmax[integer logits, ties -> lowest index] exact', ok=bool((got == ref).all()),
+                    err=int((got != ref).sum()), tol=0))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# model level
+# ------------------------------------------------------------------------------------------------
+def small_cfg(num_classes=19, deep_stem=False, os8=False, aux=False, dropout=0.0, sync=True):
+    norm = dict(type='DynSyncBN' if sync else 'DynBN', requires_grad=True)
+    if sync:
+        norm['group_size'] = 1
+    bb = dict(type='DynamicResNet', in_channels=3, stem_width=[16, 16, 32] if deep_stem else 32,
+              body_depth=[2, 2, 3, 2], body_width=[32, 48, 64, 80], num_stages=4, out_indices=(0, 1, 2, 3),
+              conv_cfg=dict(type='DynConv2d'), norm_cfg=norm, style='pytorch', deep_stem=deep_stem)
+    if os8:
+        bb.update(strides=(1, 2, 1, 1), dilations=(1, 1, 2, 4), contract_dilation=True)
+    cfg = dict(type='DynamicEncoderDecoder', backbone=bb,
+               decode_head=dict(type='DynamicFCNHead', conv_cfg=dict(type='DynConv2d'), in_channels=320, in_index=3,
+                                channels=64, num_convs=2, concat_input=True, dropout_ratio=dropout,
+                                num_classes=num_classes, norm_cfg=dict(type='SyncBN', requires_grad=True),
+                                align_corners=False,
+                                loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0)))
+    if aux:
+        cfg['auxiliary_head'] = dict(type='DynamicFCNHead', conv_cfg=dict(type='DynConv2d'), in_channels=256, in_index=2,
+                                     channels=32, num_convs=1, concat_input=False, dropout_ratio=dropout,
+                                     num_classes=num_classes, norm_cfg=dict(type='SyncBN', requires_grad=True),
+                                     align_corners=False,
+                                     loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=0.4))
+    return cfg
+
+
+SMALL_ARCHS = {
+    'max': {'backbone': {'stem': {'width': 32}, 'body': {'width': [32, 48, 64, 80], 'depth': [2, 2, 3, 2]}}},
+    'min': {'backbone': {'stem': {'width': 16}, 'body': {'width': [16, 32, 48, 64], 'depth': [1, 1, 2, 1]}}},
+    'mid': {'backbone': {'stem': {'width': 32}, 'body': {'width': [16, 48, 48, 80], 'depth': [2, 1, 3, 1]}}},
+}
+
+
+def randomize(model, seed=0):
+    """Non-trivial parameters (SURVEY 8c hazard 3: zero-init norm3 makes every block an identity); all values
+    bf16-representable for conv weights so both sides start from identical numbers."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 4:
+                fan = p.shape[1] * p.shape[2] * p.shape[3]
+                p.copy_(bf16r(torch.randn(p.shape, generator=g) * math.sqrt(2.0 / fan)))
+            elif n.endswith('conv_seg.bias'):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.01)
+            elif n.endswith('.weight'):
+                p.copy_(torch.rand(p.shape, generator=g) + 0.5)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+
+
+def build_pair(gs, cfg, seed=0):
+    om = O.build_segmentor(cfg)
+    randomize(om, seed)
+    gm = gs.build_segmentor(cfg, train_cfg=dict(), test_cfg=dict(mode='whole'))
+    missing = gm.load_state_dict(om.state_dict(), strict=True)
+    return om, gm.cuda(), missing
+
+
+def model_checks(gs, variants=(('os32', {}), ('os8_deepstem_aux', dict(deep_stem=True, os8=True, aux=True)))):
+    """Whole segmentor: train-mode loss / accuracy / parameter gradients and eval-mode label maps for the same
+    sampled sub-net.  Stated bf16 tolerances (activations are stored in bf16 between layers):
+       loss 2e-2 relative; per-parameter gradient: cosine >= 0.99 and norm ratio within 5 %; label maps >= 97 %
+       pixel agreement (disagreements sit at small soft-max margins)."""
+    out = []
+    for vname, kw in variants:
+        cfg = small_cfg(**kw)
+        om, gm, _ = build_pair(gs, cfg)
+        for aname in ('max', 'min', 'mid'):
+            arch = {'backbone': dict(SMALL_ARCHS[aname]['backbone'])}
+            if kw.get('deep_stem'):
+                w = arch['backbone']['stem']['width']
+                arch['backbone'] = dict(arch['backbone'], stem={'width': [w // 2, w // 2, w]})
+            om.manipulate_arch(arch)
+            gm.manipulate_arch(arch)
+            g = torch.Generator().manual_seed(7)
+            img = bf16r(torch.randn(2, 3, 64, 96, generator=g))
+            lab = _labels(g, 2, 19, 64, 96)
+            tag = f'model[{vname},{aname}]'
+            om.train(); gm.train()
+            om.zero_grad()
+            for p in gm.parameters():
+                p.grad = None
+            lo = om.forward_train(img, None, lab)
+            loss_o = om.parse_losses(lo)
+            loss_o.backward()
+            res = gm.train_step(dict(img=img.cuda(), img_metas=[{}, {}], gt_semantic_seg=lab.cuda()), None)
+            res['loss'].backward()
+            torch.cuda.synchronize()
+            out.append(check_f32(res['loss'].reshape(1), loss_o.reshape(1), tag + '.loss', 2e-2))
+            acc_g, acc_o = res['log_vars']['decode.acc_seg'], float(lo['decode.acc_seg'])
+            out.append(dict(name=tag + '.acc_seg', ok=abs(acc_g - acc_o) < 1.0, err=abs(acc_g - acc_o), tol=1.0))
+            worst_cos, worst_ratio, worst_name, unused_ok = 1.0, 0.0, '', True
+            gp = dict(gm.named_parameters())
+            for n, po in om.named_parameters():
+                pg = gp[n]
+                if po.grad is None or float(po.grad.abs().max()) == 0.0:
+                    if pg.grad is not None and float(pg.grad.abs().max()) != 0.0:
+                        unused_ok = False
+                    continue
+                a, b = pg.grad.detach().double().cpu().flatten(), po.grad.detach().double().flatten()
+                cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+                ratio = abs(float(a.norm() / (b.norm() + 1e-30)) - 1.0)
+                if cos < worst_cos:
+                    worst_cos, worst_name = cos, n
+                worst_ratio = max(worst_ratio, ratio)
+            out.append(dict(name=tag + '.param_grads', ok=worst_cos >= 0.99 and worst_ratio <= 0.05, err=1 - worst_cos,
+                            tol=0.01, worst_param=worst_name, worst_norm_ratio_dev=worst_ratio))
+            out.append(dict(name=tag + '.inactive_params_zero_grad', ok=unused_ok, err=0.0, tol=0))
+            om.eval(); gm.eval()
+            with torch.no_grad():
+                pred_o = om.simple_test(img)
+                pred_g = gm(return_loss=False, img=[img.cuda()],
+                            img_metas=[[dict(ori_shape=(64, 96, 3), flip=False)] * 2])
+            agree = float((torch.from_numpy(__import__('numpy').stack(pred_g)) == pred_o).float().mean())
+            out.append(dict(name=tag + '.labelmap_agreement', ok=agree >= 0.97, err=1 - agree, tol=0.03))
+    return out
+
+
+def all_checks(gs, with_simt=True):
+    res = []
+    groups = [('conv_tc', lambda: sum((conv_case_checks(c, gs, 'tc') for c in CONV_CASES), []))]
+    if with_simt:
+        groups.append(('conv_simt', lambda: sum((conv_case_checks(c, gs, 'simt') for c in CONV_CASES[:8]), [])))
+    groups += [('conv_epilogue', lambda: conv_epilogue_checks(gs)), ('image_conv', lambda: image_conv_checks(gs)),
+               ('bn', lambda: bn_checks(gs)), ('dynbn', lambda: standalone_bn_checks(gs)),
+               ('maxpool', lambda: maxpool_checks(gs)), ('loss', lambda: loss_checks(gs)),
+               ('argmax', lambda: argmax_checks(gs)), ('model', lambda: model_checks(gs))]
+    for gname, fn in groups:
+        try:
+            res += fn()
+        except Exception as e:  # keep going: the report must show every group
+            import traceback
+            res.append(dict(name=gname + '.EXCEPTION', ok=False, err=float('inf'), tol=0,
+                            why=f'{type(e).__name__}: {e}', tb=traceback.format_exc()[-1500:]))
+            try:
+                torch.cuda.synchronize()
+            except Exception as e2:
+                res.append(dict(name=gname + '.CUDA_CONTEXT_DEAD', ok=False, err=float('inf'), tol=0, why=str(e2)))
+                break
+    return res
