@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- supernet sandwich-training throughput (BASELINE.json metric: "supernet train imgs/s @512x1024").
+
+One STEP = one sandwich cycle of the reference recipe (tools/train_supernet.py:180-187): four training iterations
+[MAX, MIN, random, random] of the Dynamic ResNet supernet + FCN head, each iteration = sample sub-net ->
+manipulate_arch -> forward -> fused upsample+CE loss -> backward -> (gradient all-reduce) -> fused SGD step, on a
+batch of 2 synthetic Cityscapes-shaped images (3x512x1024, 19 classes, 10 % ignore) per GPU.  8 images per GPU per
+step.  Weak scaling: per-GPU work is fixed as N grows; SyncBN statistics and gradients cross NVLink via NCCL.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--variant os8|os32] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = the same loop fed from
+pinned host memory through the public API (`model.train_step` + optimizer), H2D copy of every batch and D2H read
+of the loss inside the timed region.  `--impl reference` times the CPU oracle (oracle/ref_model.py -- the
+reference's own mmseg/gaiavision stack is not installable here) on the host cores.
+"""
+import argparse
+import json
+import os
+import random
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMG_H, IMG_W, NUM_CLASSES, BATCH = 512, 1024, 19, 2
+CYCLE = 4  # MAX, MIN, rand, rand
+
+
+def supernet_cfg(variant):
+    bb = dict(type='DynamicResNet', in_channels=3, stem_width=64, body_depth=[4, 6, 29, 4],
+              body_width=[80, 160, 320, 640], num_stages=4, out_indices=(0, 1, 2, 3), conv_cfg=dict(type='DynConv2d'),
+              norm_cfg=dict(type='DynSyncBN', requires_grad=True, group_size=1), style='pytorch')
+    if variant == 'os8':   # configs/local_examples/extract_subnet/psp_ar50to101_v1c_extract.py:6-14
+        bb.update(deep_stem=True, stem_width=[32, 32, 64], strides=(1, 2, 1, 1), dilations=(1, 1, 2, 4),
+                  contract_dilation=True)
+    return dict(type='DynamicEncoderDecoder', backbone=bb,
+                decode_head=dict(type='DynamicFCNHead', conv_cfg=dict(type='DynConv2d'), in_channels=2560, in_index=3,
+                                 channels=512, num_convs=2, concat_input=True, dropout_ratio=0.1,
+                                 num_classes=NUM_CLASSES, norm_cfg=dict(type='SyncBN', requires_grad=True),
+                                 align_corners=False,
+                                 loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0)))
+
+
+def sampler_cfg(variant, seed=0):
+    """sandwich = concat[MAX, MIN, random x2] over the search space of configs/_dynamic_/model_samplers/ar50to101v2.py."""
+    deep = variant == 'os8'
+    stem_max, stem_min = ([32, 32, 64], [16, 16, 32]) if deep else (64, 32)
+    stem_range = (dict(type='range', key='arch.backbone.stem.width', start=[16, 16, 32], end=[32, 32, 64],
+                       step=[8, 8, 16], ascending=True) if deep else
+                  dict(type='range', key='arch.backbone.stem.width', start=32, end=64, step=16))
+    width = dict(type='range', key='arch.backbone.body.width', start=[48, 96, 192, 384], end=[80, 160, 320, 640],
+                 step=[16, 32, 64, 128], ascending=True)
+    depth = dict(type='range', key='arch.backbone.body.depth', start=[2, 2, 5, 2], end=[4, 6, 29, 4], step=[1, 2, 2, 1])
+    MAX = {'name': 'MAX', 'arch.backbone.stem.width': stem_max, 'arch.backbone.body.width': [80, 160, 320, 640],
+           'arch.backbone.body.depth': [4, 6, 29, 4]}
+    MIN = {'name': 'MIN', 'arch.backbone.stem.width': stem_min, 'arch.backbone.body.width': [48, 96, 192, 384],
+           'arch.backbone.body.depth': [2, 2, 5, 2]}
+    return MAX, MIN, dict(type='composite', model_samplers=[stem_range, width, depth])
+
+
+def synth_batch(rank, idx, device=None, pin=False):
+    import torch
+    g = torch.Generator().manual_seed(1234 + rank * 7919 + idx)
+    img = torch.randn(BATCH, 3, IMG_H, IMG_W, generator=g)
+    lab = torch.randint(0, NUM_CLASSES, (BATCH, 1, IMG_H, IMG_W), generator=g)
+    lab[torch.rand(BATCH, 1, IMG_H, IMG_W, generator=g) < 0.1] = 255
+    if pin:
+        img, lab = img.pin_memory(), lab.pin_memory()
+    if device is not None:
+        img, lab = img.to(device), lab.to(device)
+    return img, lab
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([time.time()] + [c.strip() for c in line.split(',')])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r[1:] for r in self.rows if self.t0 is None or (self.t0 <= r[0] <= self.t1 + 0.25)]
+        self.rows = rows or [r[1:] for r in self.rows]
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
+        return dict(sm_mhz=statistics.median(busy) if busy else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def run_reference(args):
+    """--impl reference: the CPU oracle (restatement of the reference's mmseg/gaiavision path) on the host cores.
+    One step = a BOUNDED sample of the workload: one training iteration (forward + loss + backward + SGD) of the
+    MIN sub-net on ONE 3x512x1024 image (the cheapest quarter of a sandwich cycle, 1/8 of its images)."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    import torch
+    from oracle import ref_model as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = supernet_cfg(args.variant)
+    cfg['decode_head']['dropout_ratio'] = 0.1
+    model = O.build_segmentor(cfg)
+    _, MIN, _ = sampler_cfg(args.variant)
+    from gaia_seg_b200.model_space import fold_dict
+    model.manipulate_arch(fold_dict(MIN)['arch'])
+    model.train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+    img, lab = synth_batch(0, 0)
+    img, lab = img[:1], lab[:1]
+
+    def step():
+        opt.zero_grad()
+        loss = model.parse_losses(model.forward_train(img, None, lab))
+        loss.backward()
+        opt.step()
+        return float(loss)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = args.steps * 1 / dt
+    sample = 'one fwd+loss+bwd+SGD iteration of the MIN sub-net on 1x3x512x1024 per step (torch CPU fp32 oracle)'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'supernet train imgs/s @512x1024', 'value': v, 'unit': 'imgs/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args.variant), 'variant': args.variant},
+        'cpu_baseline': {'value': v, 'unit': 'imgs/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'imgs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def workload_name(variant):
+    return (f'BASELINE configs[1]: supernet sandwich training [MAX, MIN, rand, rand], DynamicResNet({variant}) + FCN head, '
+            f'SyncBN, synthetic Cityscapes {IMG_H}x{IMG_W} crops, batch {BATCH}/GPU, one step = one 4-iteration cycle')
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--variant', default='os8', choices=['os8', 'os32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--ncu-cycle', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import gaia_seg_b200 as gs
+    from gaia_seg_b200 import functional as Fg
+    from gaia_seg_b200.model_space import build_model_sampler, fold_dict, sandwich_sampler_cfg
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node N'
+    gs._lib.require_device()
+    gs.set_random_seed(0)
+
+    model = gs.build_segmentor(supernet_cfg(args.variant), train_cfg=dict(), test_cfg=dict(mode='whole')).to(dev)
+    model.train()
+    opt = gs.GsSGD(model, lr=0.01, momentum=0.9, weight_decay=5e-4)
+    MAX, MIN, rnd = sampler_cfg(args.variant)
+    sampler = build_model_sampler(sandwich_sampler_cfg(MAX, MIN, rnd, num_random=2, seed=0))  # shared seed: all ranks agree
+    n_dev_batches = 4
+    dev_batches = [synth_batch(rank, i, device=dev) for i in range(n_dev_batches)]
+    host_batches = [synth_batch(rank, 100 + i, pin=True) for i in range(n_dev_batches)]
+    metas = [dict(ori_shape=(IMG_H, IMG_W, 3), flip=False)] * BATCH
+    it_count = [0]
+
+    def iteration(img, lab):
+        meta = fold_dict(sampler.sample())
+        model.manipulate_arch(meta['arch'])
+        out = model.train_step(dict(img=img, img_metas=metas, gt_semantic_seg=lab), opt)
+        opt.zero_grad()
+        out['loss'].backward()
+        w = opt.flat.all_reduce_grads()
+        opt.grad_scale = 1.0 / w
+        opt.step()
+        it_count[0] += 1
+        return out
+
+    def step_resident():
+        for _ in range(CYCLE):
+            img, lab = dev_batches[it_count[0] % n_dev_batches]
+            out = iteration(img, lab)
+        return out
+
+    def step_e2e():
+        loss = None
+        for _ in range(CYCLE):
+            himg, hlab = host_batches[it_count[0] % n_dev_batches]
+            img = himg.to(dev, non_blocking=True)
+            lab = hlab.to(dev, non_blocking=True)
+            out = iteration(img, lab)
+            loss = out['loss'].item()          # device -> host read of the step result
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    if args.ncu_cycle:   # profiling aid: exactly one sandwich cycle between cudaProfilerStart/Stop, no timing
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({'ncu_cycle': 'done', 'launches_per_cycle': None}))
+        return
+    gs._lib.reset_launch_count()
+    t_w0 = time.time()
+    ms = timed(step_resident, args.steps)
+    clocks.window(t_w0, time.time())
+    launches = gs._lib.launch_count()
+    clk = clocks.stop() if rank == 0 else {}
+    imgs_per_step = CYCLE * BATCH * world
+    value = imgs_per_step * args.steps / (ms / 1e3)
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = imgs_per_step * args.steps / (ms_e2e / 1e3)
+    h2d = CYCLE * (BATCH * 3 * IMG_H * IMG_W * 4 + BATCH * IMG_H * IMG_W * 8)
+    d2h = CYCLE * 4
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), CUDA events around every launch ----
+    roof, breakdown = None, None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback (B200_PROFILING.md sustained 1.4 PF)'
+    if not args.no_profile:
+        Fg.PROFILE = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        step_resident()
+        e1.record()
+        torch.cuda.synchronize()
+        prof, Fg.PROFILE = Fg.PROFILE, None
+        cyc_ms = e0.elapsed_time(e1)
+        agg = {}
+        for kind, flops, a, b in prof:
+            d = agg.setdefault(kind, [0.0, 0.0, 0])
+            d[0] += flops
+            d[1] += a.elapsed_time(b)
+            d[2] += 1
+        ig_f = agg.get('fwd', [0, 0, 0])[0] + agg.get('dgrad', [0, 0, 0])[0]
+        ig_ms = agg.get('fwd', [0, 0, 0])[1] + agg.get('dgrad', [0, 0, 0])[1]
+        ig_n = agg.get('fwd', [0, 0, 0])[2] + agg.get('dgrad', [0, 0, 0])[2]
+        ach = ig_f / (ig_ms * 1e-3) / 1e12 if ig_ms > 0 else 0.0
+        roof = {'bound': 'tensor', 'kernel': 'gs::igemm_kernel (conv fwd + dgrad)', 'achieved': ach, 'peak': peak_tf,
+                'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                'launches': ig_n, 'avg_launch_ms': ig_ms / max(ig_n, 1), 'flops_per_launch': ig_f / max(ig_n, 1)}
+        breakdown = {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0, 'ms': v[1], 'launches': v[2],
+                         'share_of_step': v[1] / cyc_ms} for k, v in agg.items()}
+        breakdown['profiled_step_ms'] = cyc_ms
+        tot_flops = sum(v[0] for v in agg.values())
+        breakdown['conv_flops_per_step'] = tot_flops
+        breakdown['whole_step_tflops'] = tot_flops / (ms / args.steps * 1e-3) / 1e12
+
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline(args.variant)
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {
+            'metric': 'supernet train imgs/s @512x1024', 'value': value, 'unit': 'imgs/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': workload_name(args.variant), 'variant': args.variant, 'global_batch': BATCH * world,
+                       'images_per_step': imgs_per_step, 'parallelism': f'dp{world}',
+                       'l2': 'inputs + activations of every iteration (>1 GB) exceed the 126 MB L2; 4 rotating input batches',
+                       'timing': 'CUDA events on the launching stream, barrier+sync both sides, max over ranks'},
+            'clocks': clk, 'gpu_launches': launches,
+            'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / args.steps},
+            'roofline': roof, 'cpu_baseline': cpu_base, 'breakdown': breakdown}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(variant):
+    """The CPU oracle on the GPU box's host cores, bounded sample (about 10-30 s): one training iteration of the MIN
+    sub-net on one 3x512x1024 image, best of 2 after one warm-up."""
+    import torch
+    from oracle import ref_model as O
+    from gaia_seg_b200.model_space import fold_dict
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = supernet_cfg(variant)
+    model = O.build_segmentor(cfg)
+    _, MIN, _ = sampler_cfg(variant)
+    model.manipulate_arch(fold_dict(MIN)['arch'])
+    model.train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+    img, lab = synth_batch(0, 0)
+    img, lab = img[:1], lab[:1]
+    best = None
+    for i in range(3):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = model.parse_losses(model.forward_train(img, None, lab))
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i > 0:
+            best = dt if best is None else min(best, dt)
+    return {'value': 1.0 / best, 'unit': 'imgs/s', 'cores': cores, 'kind': 'port',
+            'sample': 'one fwd+loss+bwd+SGD iteration of the MIN sub-net (cheapest of the sandwich cycle) on 1x3x512x1024, '
+                      'torch CPU fp32 oracle, best of 2 after 1 warm-up', 'seconds_per_iteration': best}
+
+
+if __name__ == '__main__':
+    main()

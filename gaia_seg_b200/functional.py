@@ -24,6 +24,22 @@ BF16 = torch.bfloat16
 # 'tc' = tcgen05 implicit GEMM (product path); 'simt' = CUDA-core triage kernels (debug only)
 CONV_IMPL = os.environ.get('GS_CONV_IMPL', 'tc')
 
+# bench.py sets this to a list to time every convolution launch with CUDA events on the launching stream:
+# entries are (kind, algorithmic_flops, start_event, end_event)
+PROFILE = None
+
+
+def _timed_call(kind, g, fn, *args):
+    if PROFILE is None:
+        call(fn, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(fn, *args)
+    e1.record()
+    flops = 2.0 * g.N * g.Ho * g.Wo * g.Co * g.Ci * g.kh * g.kw
+    PROFILE.append((kind, flops, e0, e1))
+
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
@@ -231,8 +247,8 @@ def conv_forward(x, conv, Co, scale=None, shift=None, residual=None, relu=False,
         residual = as_act(residual)
         res_ld = act_ld(residual)
     fn = 'gs_conv2d_fwd' if CONV_IMPL == 'tc' else 'gs_conv2d_fwd_simt'
-    call(fn, ctypes.byref(g), a.data_ptr(), krsc.data_ptr(), y.data_ptr(), _ptr(scale), _ptr(shift), _ptr(residual),
-         res_ld, flags, _ptr(stats), st)
+    _timed_call('fwd', g, fn, ctypes.byref(g), a.data_ptr(), krsc.data_ptr(), y.data_ptr(), _ptr(scale), _ptr(shift),
+                _ptr(residual), res_ld, flags, _ptr(stats), st)
     return y, stats, a, g
 
 
@@ -258,10 +274,10 @@ def conv_wgrad(conv, a, dy, g):
         K = conv.kernel_size[0] * conv.kernel_size[1] * conv.in_channels
         Kpad = image_kpad(conv)
         tmp = torch.zeros((Co_max, Kpad), dtype=torch.float32, device=dy.device)
-        call(fn, ctypes.byref(g), a.data_ptr(), dy.data_ptr(), tmp.data_ptr(), st)
+        _timed_call('wgrad', g, fn, ctypes.byref(g), a.data_ptr(), dy.data_ptr(), tmp.data_ptr(), st)
         gw.permute(0, 2, 3, 1).reshape(Co_max, K).add_(tmp[:, :K])
     else:
-        call(fn, ctypes.byref(g), a.data_ptr(), dy.data_ptr(), gw.data_ptr(), st)
+        _timed_call('wgrad', g, fn, ctypes.byref(g), a.data_ptr(), dy.data_ptr(), gw.data_ptr(), st)
 
 
 def conv_dgrad(conv, dy, g, x_shape, add=None):
@@ -281,11 +297,11 @@ def conv_dgrad(conv, dy, g, x_shape, add=None):
         nbytes = _lib.load().gs_conv2d_dgrad_workspace_bytes(ctypes.byref(g))
         if nbytes > 0:
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dy.device)
-        call('gs_conv2d_dgrad', ctypes.byref(g), dy.data_ptr(), crsk.data_ptr(), dx.data_ptr(), _ptr(add), add_ld,
-             _ptr(ws), st)
+        _timed_call('dgrad', g, 'gs_conv2d_dgrad', ctypes.byref(g), dy.data_ptr(), crsk.data_ptr(), dx.data_ptr(),
+                    _ptr(add), add_ld, _ptr(ws), st)
     else:
-        call('gs_conv2d_dgrad_simt', ctypes.byref(g), dy.data_ptr(), krsc.data_ptr(), dx.data_ptr(), _ptr(add),
-             add_ld, st)
+        _timed_call('dgrad', g, 'gs_conv2d_dgrad_simt', ctypes.byref(g), dy.data_ptr(), krsc.data_ptr(), dx.data_ptr(),
+                    _ptr(add), add_ld, st)
     return dx
 
 
@@ -454,7 +470,7 @@ class ConvBnActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, residual, weight, conv, bn, relu, Co):
-        save = torch.is_grad_enabled() or ctx.needs_input_grad[0] or weight.requires_grad
+        save = any(ctx.needs_input_grad)
         z, rec = cba_forward(x, conv, bn, relu, residual, Co, save=save)
         ctx.rec = rec
         return z
@@ -476,7 +492,7 @@ class BottleneckFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, block):
-        save = torch.is_grad_enabled()
+        save = any(ctx.needs_input_grad)
         z1, r1 = cba_forward(x, block.conv1, block.norm1, True, save=save)
         z2, r2 = cba_forward(z1, block.conv2, block.norm2, True, save=save)
         rd = None
@@ -518,7 +534,7 @@ class MaxPoolFn(torch.autograd.Function):
         Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
         y = new_act(N, C, Ho, Wo, x.device)
         idx = None
-        if torch.is_grad_enabled() or ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0]:
             idx = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=x.device)
         call('gs_maxpool3x3s2_fwd', x.data_ptr(), N, H, W, C, act_ld(x), y.data_ptr(), Ho, Wo, C, _ptr(idx), _stream())
         ctx.idx, ctx.xs = idx, (N, C, H, W)
@@ -647,7 +663,7 @@ class UpsampleCEFn(torch.autograd.Function):
         out_sum = torch.zeros(1, dtype=torch.float64, device=dev)
         counts = torch.zeros(2, dtype=torch.int64, device=dev)
         rec = None
-        if torch.is_grad_enabled() or ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0]:
             rec = torch.empty(_lib.load().gs_upsample_ce_record_bytes(N, H, W), dtype=torch.uint8, device=dev)
         call('gs_upsample_ce_fwd', lg.data_ptr(), N, h, w, K, act_ld(lg), lab.data_ptr(), H, W, int(ignore_index),
              out_sum.data_ptr(), counts.data_ptr(), _ptr(rec), _stream())

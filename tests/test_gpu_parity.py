@@ -44,6 +44,10 @@ def test_standalone_dynbn(gs):
     _assert_all(C.standalone_bn_checks(gs))
 
 
+def test_res_stage_fwd_bwd(gs):
+    _assert_all(C.stage_checks(gs))
+
+
 def test_maxpool(gs):
     _assert_all(C.maxpool_checks(gs))
 

@@ -19,6 +19,7 @@ GROUPS = {
     'tc_s2': ({}, "sum((C.conv_case_checks(c, gs, 'tc') for c in C.CONV_CASES if 's2' in c[0]), [])"),
     'tc_epilogue': ({}, "C.conv_epilogue_checks(gs) + C.image_conv_checks(gs)"),
     'tc_bn': ({}, "C.bn_checks(gs)"),
+    'stage_tc': ({}, "C.stage_checks(gs)"),
     'model_tc': ({}, "C.model_checks(gs)"),
 }
 
