@@ -117,48 +117,66 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def run_reference(args):
-    """--impl reference: the CPU oracle (restatement of the reference's mmseg/gaiavision path) on the host cores.
-    One step = a BOUNDED sample of the workload: one training iteration (forward + loss + backward + SGD) of the
-    MIN sub-net on ONE 3x512x1024 image (the cheapest quarter of a sandwich cycle, 1/8 of its images)."""
-    rank = int(os.environ.get('RANK', 0))
-    if rank != 0:
-        return
-    import torch
-    from oracle import ref_model as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = supernet_cfg(args.variant)
-    cfg['decode_head']['dropout_ratio'] = 0.1
-    model = O.build_segmentor(cfg)
-    _, MIN, _ = sampler_cfg(args.variant)
-    from gaia_seg_b200.model_space import fold_dict
-    model.manipulate_arch(fold_dict(MIN)['arch'])
-    model.train()
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
-    img, lab = synth_batch(0, 0)
-    img, lab = img[:1], lab[:1]
+class CpuArm:
+    """The CPU oracle (restatement of the reference's mmseg/gaiavision path, oracle/ref_model.py) on the host cores.
+    One CPU step = one sandwich cycle [MAX, MIN, rand, rand] (forward + loss + backward + SGD each) at batch ONE
+    3x512x1024 image per iteration: the same sub-net mix as a GPU step on half its batch -- a bounded sample
+    (about 5-20 s of CPU work).  4 images per CPU step."""
+    IMGS_PER_STEP = CYCLE
 
-    def step():
-        opt.zero_grad()
-        loss = model.parse_losses(model.forward_train(img, None, lab))
+    def __init__(self, variant):
+        import torch
+        from oracle import ref_model as O
+        from gaia_seg_b200.model_space import build_model_sampler, fold_dict, sandwich_sampler_cfg
+        self.torch, self.fold = torch, fold_dict
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.model = O.build_segmentor(supernet_cfg(variant))
+        self.model.train()
+        MAX, MIN, rnd = sampler_cfg(variant)
+        self.sampler = build_model_sampler(sandwich_sampler_cfg(MAX, MIN, rnd, num_random=2, seed=0))
+        self.opt = torch.optim.SGD(self.model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+        img, lab = synth_batch(0, 0)
+        self.img, self.lab = img[:1], lab[:1]
+        self.sample = ('one sandwich cycle [MAX, MIN, rand, rand] of fwd+loss+bwd+SGD iterations at batch 1x3x512x1024 '
+                       '(4 images; same sub-net mix as a GPU step, half its batch), torch CPU fp32 oracle')
+
+    def iteration(self):
+        self.model.manipulate_arch(self.fold(self.sampler.sample())['arch'])
+        self.opt.zero_grad()
+        loss = self.model.parse_losses(self.model.forward_train(self.img, None, self.lab))
         loss.backward()
-        opt.step()
-        return float(loss)
-    for _ in range(args.warmup):
-        step()
+        self.opt.step()
+        return float(loss.detach())
+
+    def step(self):
+        for _ in range(CYCLE):
+            self.iteration()
+
+
+def run_reference(args):
+    """--impl reference: times CpuArm steps with all host threads.  Rank 0 only."""
+    if int(os.environ.get('RANK', 0)) != 0:
+        return
+    arm = CpuArm(args.variant)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
+    for _ in range(args.warmup):
+        arm.step()
+    per = (time.perf_counter() - t0) / max(args.warmup, 1)
+    steps = args.steps
+    if args.warmup and per * steps > 300:      # keep the whole run within a few minutes
+        steps = max(1, int(300 / per))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        arm.step()
     dt = time.perf_counter() - t0
-    v = args.steps * 1 / dt
-    sample = 'one fwd+loss+bwd+SGD iteration of the MIN sub-net on 1x3x512x1024 per step (torch CPU fp32 oracle)'
+    v = steps * arm.IMGS_PER_STEP / dt
     print(json.dumps({
         'impl': 'reference', 'metric': 'supernet train imgs/s @512x1024', 'value': v, 'unit': 'imgs/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'steps': steps, 'steps_requested': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name(args.variant), 'variant': args.variant},
-        'cpu_baseline': {'value': v, 'unit': 'imgs/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': v, 'unit': 'imgs/s', 'cores': arm.cores, 'kind': 'port', 'sample': arm.sample},
         'e2e': {'value': v, 'unit': 'imgs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
@@ -177,6 +195,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--ncu-cycle', action='store_true')
+    ap.add_argument('--host-profile', action='store_true', help='cProfile one cycle -> gpurun_out/hostprof.txt')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -269,6 +288,25 @@ def main():
         torch.cuda.profiler.stop()
         print(json.dumps({'ncu_cycle': 'done', 'launches_per_cycle': None}))
         return
+    if args.host_profile and rank == 0:
+        import cProfile
+        import pstats
+        torch.cuda.synchronize()
+        pr = cProfile.Profile()
+        pr.enable()
+        step_resident()
+        pr.disable()
+        torch.cuda.synchronize()
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', 'hostprof.txt'), 'w') as f:
+            pstats.Stats(pr, stream=f).sort_stats('cumulative').print_stats(70)
+            pstats.Stats(pr, stream=f).sort_stats('tottime').print_stats(45)
+    # host-side enqueue time of one step (no sync inside): if it is close to ms_per_step the loop is CPU-bound
+    torch.cuda.synchronize()
+    t_h0 = time.perf_counter()
+    step_resident()
+    host_enqueue_ms = (time.perf_counter() - t_h0) * 1e3
+    torch.cuda.synchronize()
     gs._lib.reset_launch_count()
     t_w0 = time.time()
     ms = timed(step_resident, args.steps)
@@ -324,7 +362,7 @@ def main():
         breakdown['whole_step_tflops'] = tot_flops / (ms / args.steps * 1e-3) / 1e12
 
     cpu_base = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline(args.variant)
 
     if world > 1:
@@ -338,7 +376,7 @@ def main():
                        'images_per_step': imgs_per_step, 'parallelism': f'dp{world}',
                        'l2': 'inputs + activations of every iteration (>1 GB) exceed the 126 MB L2; 4 rotating input batches',
                        'timing': 'CUDA events on the launching stream, barrier+sync both sides, max over ranks'},
-            'clocks': clk, 'gpu_launches': launches,
+            'clocks': clk, 'gpu_launches': launches, 'host_enqueue_ms_per_step': host_enqueue_ms,
             'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps},
             'roofline': roof, 'cpu_baseline': cpu_base, 'breakdown': breakdown}
@@ -348,34 +386,16 @@ def main():
 
 
 def cpu_baseline(variant):
-    """The CPU oracle on the GPU box's host cores, bounded sample (about 10-30 s): one training iteration of the MIN
-    sub-net on one 3x512x1024 image, best of 2 after one warm-up."""
-    import torch
-    from oracle import ref_model as O
-    from gaia_seg_b200.model_space import fold_dict
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = supernet_cfg(variant)
-    model = O.build_segmentor(cfg)
-    _, MIN, _ = sampler_cfg(variant)
-    model.manipulate_arch(fold_dict(MIN)['arch'])
-    model.train()
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
-    img, lab = synth_batch(0, 0)
-    img, lab = img[:1], lab[:1]
-    best = None
-    for i in range(3):
-        t0 = time.perf_counter()
-        opt.zero_grad()
-        loss = model.parse_losses(model.forward_train(img, None, lab))
-        loss.backward()
-        opt.step()
-        dt = time.perf_counter() - t0
-        if i > 0:
-            best = dt if best is None else min(best, dt)
-    return {'value': 1.0 / best, 'unit': 'imgs/s', 'cores': cores, 'kind': 'port',
-            'sample': 'one fwd+loss+bwd+SGD iteration of the MIN sub-net (cheapest of the sandwich cycle) on 1x3x512x1024, '
-                      'torch CPU fp32 oracle, best of 2 after 1 warm-up', 'seconds_per_iteration': best}
+    """cpu_baseline leg of the B200 arm: one CpuArm step (after one warm-up iteration), rank 0, N=1 only."""
+    arm = CpuArm(variant)
+    arm.iteration()                      # warm-up (MAX sub-net: touches every weight once)
+    for _ in range(CYCLE - 1):           # finish the warm-up cycle so the timed step starts at MAX again
+        arm.iteration()
+    t0 = time.perf_counter()
+    arm.step()
+    dt = time.perf_counter() - t0
+    return {'value': arm.IMGS_PER_STEP / dt, 'unit': 'imgs/s', 'cores': arm.cores, 'kind': 'port', 'sample': arm.sample,
+            'seconds_per_step': dt}
 
 
 if __name__ == '__main__':

@@ -47,8 +47,9 @@ PROTOTYPES = {
     'gs_bn_finalize': (_I, [_P, _D, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
     'gs_bn_eval_affine': (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P]),
     'gs_bn_apply': (_I, [_P, _I, _P, _P, _P, _I, _I, _P, _I, _L, _I, _P]),
-    'gs_bn_bwd_reduce': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _L, _I, _P, _P]),
-    'gs_bn_bwd_apply': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _D, _L, _I, _P, _I, _P, _I, _P]),
+    'gs_bn_apply_train': (_I, [_P, _I, _P, _D, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _P, _I, _L, _I, _P]),
+    'gs_bn_bwd_reduce': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _L, _I, _P, _P]),
+    'gs_bn_bwd_apply': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _D, _L, _I, _P, _I, _P, _I, _P, _P, _P]),
     'gs_affine_bwd': (_I, [_P, _I, _P, _I, _P, _L, _I, _P, _I, _P, _I, _P]),
     'gs_bn_bwd_param': (_I, [_P, _I, _P, _P, _I, _P]),
     'gs_maxpool3x3s2_fwd': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
@@ -68,7 +69,6 @@ PROTOTYPES = {
     'gs_upsample_argmax': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'gs_upsample_bilinear_f32': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
     'gs_sgd_flat': (_I, [_P, _P, _P, _L, _F, _F, _F, _F, _I, _P, _P]),
-    'gs_transpose_cast': (_I, [_P, _P, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -275,8 +275,7 @@ class DynBNFn(torch.autograd.Function):
         C = x.shape[1]
         if F_gs.bn_batch_mode(bn):
             stats = F_gs.bn_stats(x)
-            aff, count = F_gs.bn_finalize(bn, stats, C, F_gs._pixels(x))
-            z = F_gs.bn_apply(x, aff[2], aff[3])
+            z, aff, count = F_gs.bn_train_apply(bn, x, stats, C)
             ctx.mode = 'batch'
         else:
             aff = F_gs.bn_eval_affine(bn, C)
@@ -288,31 +287,16 @@ class DynBNFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dz):
-        import torch.distributed as dist
         from ._lib import call
         dz = F_gs.as_act(dz)
         x, aff, bn = ctx.x, ctx.aff, ctx.bn
         N, C, H, W = x.shape
-        P, st = N * H * W, F_gs._stream()
-        dx = F_gs.new_act(N, C, H, W, x.device)
         if ctx.mode == 'batch':
-            sums = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
-            call('gs_bn_bwd_reduce', dz.data_ptr(), F_gs.act_ld(dz), x.data_ptr(), F_gs.act_ld(x), None, 0,
-                 aff[0].data_ptr(), aff[1].data_ptr(), P, C, sums.data_ptr(), st)
-            gw = bn.weight is not None and bn.weight.requires_grad
-            gb = bn.bias is not None and bn.bias.requires_grad
-            if gw or gb:
-                call('gs_bn_bwd_param', sums.data_ptr(), C, F_gs._param_grad(bn.weight).data_ptr() if gw else None,
-                     F_gs._param_grad(bn.bias).data_ptr() if gb else None, 1, st)
-            pg, world = F_gs._sync_group(bn)
-            if world > 1:
-                dist.all_reduce(sums, group=pg)
-            call('gs_bn_bwd_apply', dz.data_ptr(), F_gs.act_ld(dz), x.data_ptr(), F_gs.act_ld(x), None, 0,
-                 aff[0].data_ptr(), aff[1].data_ptr(), F_gs._ptr(bn.weight), sums.data_ptr(), float(ctx.count), P, C,
-                 dx.data_ptr(), C, None, 0, st)
+            dx, _ = F_gs.bn_backward(bn, dz, x, aff, ctx.count, None, False, False)
         else:
-            call('gs_affine_bwd', dz.data_ptr(), F_gs.act_ld(dz), None, 0, aff[0].data_ptr(), P, C, dx.data_ptr(), C,
-                 None, 0, st)
+            dx = F_gs.new_act(N, C, H, W, x.device)
+            call('gs_affine_bwd', dz.data_ptr(), F_gs.act_ld(dz), None, 0, aff[0].data_ptr(), N * H * W, C,
+                 dx.data_ptr(), C, None, 0, F_gs._stream())
         ctx.x = None
         return dx, None, None
 

@@ -47,7 +47,8 @@ struct IgemmParams {
     int kchunks;          // ceil(Kc / 64)
     int taps_h, taps_w;
     int in_mul, base, step;  // input coord of tap t for output o:  o*in_mul + base + t*step
-    int b_box_rows;       // rows of the weight box (<= 256)
+    int b_box_rows;       // rows of the weight box (<= 256)            (K-major B, forward)
+    int b_mn;             // 1: B is MN-major (dgrad reads W[co][r][s][ci] in place: K = co rows, N = ci contiguous)
     // epilogue
     int direct;           // 1: per-thread global stores (fp32 out or unaligned), 0: TMA store
     int out_f32;
@@ -106,7 +107,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = kIgABytes + p.b_box_rows * 128;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
                 const int mt = tile / p.n_tiles;
@@ -115,6 +115,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const int h0 = (rem / p.tiles_w) * p.TH;
                 const int w0 = (rem % p.tiles_w) * p.TW;
                 const int n0 = nt * 256;
+                int n_valid = p.Cout - n0;
+                if (n_valid > 256) n_valid = 256;
+                const int b_boxes = (n_valid + 63) >> 6;   // MN-major B: [64 k-rows][64 n] boxes
+                const uint32_t tx_bytes = kIgABytes + (p.b_mn ? b_boxes * 8192 : p.b_box_rows * 128);
                 for (int r = 0; r < p.taps_h; ++r) {
                     const int ih = h0 * p.in_mul + p.base + r * p.step;
                     for (int s = 0; s < p.taps_w; ++s) {
@@ -125,7 +129,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             uint8_t* b_dst = a_dst + kIgABytes;
                             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                             tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * 64, iw, ih, img);
-                            tma_load_4d(b_dst, &tmB, &full_bar[stage], kc * 64, s, r, n0);
+                            if (p.b_mn) {
+                                for (int j = 0; j < b_boxes; ++j)
+                                    tma_load_4d(b_dst + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, s, r, kc * 64);
+                            } else {
+                                tma_load_4d(b_dst, &tmB, &full_bar[stage], kc * 64, s, r, n0);
+                            }
                             if (++stage == kIgStages) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -145,7 +154,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 int n_valid = p.Cout - nt * 256;
                 if (n_valid > 256) n_valid = 256;
                 const uint32_t umma_n = (n_valid + 15) & ~15;
-                const uint32_t idesc = make_idesc_bf16(128, umma_n, false, false);
+                const uint32_t idesc = make_idesc_bf16(128, umma_n, false, p.b_mn != 0);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + acc * 256;
@@ -161,7 +170,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll 1
                     for (int k = 0; k < ksteps; ++k) {
                         const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-                        const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                        const uint64_t bdesc = p.b_mn ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                                      : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
                         umma_bf16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
                         accumulate = 1;
                     }
@@ -337,6 +347,7 @@ struct IgemmLaunch {
     int a_estride;         // element stride of the spatial traversal (fwd conv stride), 1 or 2
     // weights: 4-D [rows_max][kh][kw][cols_max] with active extents rows (=Cout) x cols (=Kc)
     const void* b_ptr; int b_rows_max, b_cols_max;
+    int b_mn;              // 1: b_ptr is W[K rows = Kc][kh][kw][N cols = Cout] with pitch b_cols_max (dgrad in place)
     int N, Ho, Wo, Cout, Kc, kh, kw;
     int in_mul, base, step;
     void* out; long long out_ld; int out_f32;
@@ -360,6 +371,7 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     p.taps_h = L.kh; p.taps_w = L.kw;
     p.in_mul = L.in_mul; p.base = L.base; p.step = L.step;
     p.b_box_rows = L.Cout >= 256 ? 256 : gs_round_up(L.Cout, 16);
+    p.b_mn = L.b_mn;
     p.out = L.out; p.out_ld = L.out_ld; p.out_f32 = L.out_f32; p.relu = L.relu;
     p.scale = L.scale; p.shift = L.shift;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(L.residual); p.res_ld = L.res_ld;
@@ -382,7 +394,15 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
         if (encode_tmap_4d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.a_ptr, dims, str, box, es,
                            CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
     }
-    {
+    if (L.b_mn) {
+        const uint64_t dims[4] = {(uint64_t)L.Cout, (uint64_t)L.kw, (uint64_t)L.kh, (uint64_t)L.Kc};
+        const uint64_t str[3] = {(uint64_t)L.b_cols_max * 2, (uint64_t)L.b_cols_max * 2 * L.kw,
+                                 (uint64_t)L.b_cols_max * 2 * L.kw * L.kh};
+        const uint32_t box[4] = {64, 1, 1, 64};
+        const uint32_t es[4] = {1, 1, 1, 1};
+        if (encode_tmap_4d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.b_ptr, dims, str, box, es,
+                           CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    } else {
         const uint64_t dims[4] = {(uint64_t)L.Kc, (uint64_t)L.kw, (uint64_t)L.kh, (uint64_t)L.Cout};
         const uint64_t str[3] = {(uint64_t)L.b_cols_max * 2, (uint64_t)L.b_cols_max * 2 * L.kw,
                                  (uint64_t)L.b_cols_max * 2 * L.kw * L.kh};
@@ -684,7 +704,7 @@ extern "C" int64_t gs_conv2d_dgrad_workspace_bytes(const gs_conv_geom* g) {
     return (int64_t)g->N * Hu * Wu * gs_round_up(g->Co, 8) * 2;
 }
 
-extern "C" int gs_conv2d_dgrad(const gs_conv_geom* g, const void* dy, const void* w_crsk, void* dx,
+extern "C" int gs_conv2d_dgrad(const gs_conv_geom* g, const void* dy, const void* w_krsc, void* dx,
                                const void* residual, int32_t res_ld, void* workspace, void* stream_) {
     if (check_geom(g)) return -1;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -705,7 +725,8 @@ extern "C" int gs_conv2d_dgrad(const gs_conv_geom* g, const void* dy, const void
         L.a_ptr = workspace; L.a_C = g->Co; L.a_ld = g->Co; L.a_H = Hu; L.a_W = Wu;
     }
     L.a_estride = 1;
-    L.b_ptr = w_crsk; L.b_rows_max = g->Ci_max; L.b_cols_max = gs_round_up(g->Co_max, 8);
+    // B operand = the forward weight W[co][r][s][ci] read IN PLACE as an MN-major operand (K = co rows)
+    L.b_ptr = w_krsc; L.b_rows_max = g->Co_max; L.b_cols_max = g->Ci_max; L.b_mn = 1;
     L.N = g->N; L.Ho = g->H; L.Wo = g->W; L.Cout = g->Ci; L.Kc = g->Co; L.kh = g->kh; L.kw = g->kw;
     // dx[h] = sum_r dy_up[h + pad - r*dil] * w[:, r]
     L.in_mul = 1; L.base = g->pad; L.step = -g->dil;

@@ -119,26 +119,66 @@ __global__ void bn_eval_affine_kernel(int C, const float* __restrict__ gamma, co
 
 // ------------------------------------------------------------------------------------------------
 // apply: z = relu?( y*scale + shift (+ res) )
+// FROM_STATS: scale / shift are derived in the kernel prologue from the (all-reduced) fp64 sums -- the
+// "finalize" step costs no launch; block 0 also stores mean / invstd / scale / shift for the backward pass and
+// updates the running statistics of the channel prefix.
 // ------------------------------------------------------------------------------------------------
-template <bool HAS_RES>
+struct BnTrainArgs {
+    const double* stats;   // [2C] sum, sumsq
+    double inv_count;      // 1 / elements per channel (over the SyncBN group)
+    double unbias;         // count / (count - 1)
+    const float* gamma;    // may be NULL
+    const float* beta;     // may be NULL
+    float* rm;             // running mean / var prefix, may be NULL
+    float* rv;
+    float momentum, eps;
+    float* aff;            // [4][C]: mean, invstd, scale, shift
+    int C;
+};
+
+template <bool HAS_RES, bool FROM_STATS>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, long long y_ld8,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                        const uint4* __restrict__ res, long long res_ld8, int relu,
                                                        uint4* __restrict__ z, long long z_ld8, long long P, int C8,
-                                                       int Vc, int R) {
+                                                       int Vc, int R, BnTrainArgs t) {
     const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
     const long long S = (long long)gridDim.x * R;
     for (int cv = cx; cv < C8; cv += Vc) {
         float sc[8], sh[8];
-        if (scale) load8f(scale + cv * 8, sc);
-        else {
+        if (FROM_STATS) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sc[i] = 1.f;
-        }
-        if (shift) load8f(shift + cv * 8, sh);
-        else {
+            for (int i = 0; i < 8; ++i) {
+                const int c = cv * 8 + i;
+                const double m = t.stats[c] * t.inv_count;
+                double var = t.stats[t.C + c] * t.inv_count - m * m;
+                if (var < 0.0) var = 0.0;
+                const float mf = static_cast<float>(m);
+                const float istd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(t.eps)));
+                const float g = t.gamma ? __ldg(t.gamma + c) : 1.f;
+                const float b = t.beta ? __ldg(t.beta + c) : 0.f;
+                sc[i] = g * istd;
+                sh[i] = b - mf * sc[i];
+                if (blockIdx.x == 0 && ry == 0) {
+                    t.aff[c] = mf;
+                    t.aff[t.C + c] = istd;
+                    t.aff[2 * t.C + c] = sc[i];
+                    t.aff[3 * t.C + c] = sh[i];
+                    if (t.rm) t.rm[c] = (1.f - t.momentum) * t.rm[c] + t.momentum * mf;
+                    if (t.rv) t.rv[c] = (1.f - t.momentum) * t.rv[c] + t.momentum * static_cast<float>(var * t.unbias);
+                }
+            }
+        } else {
+            if (scale) load8f(scale + cv * 8, sc);
+            else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sh[i] = 0.f;
+                for (int i = 0; i < 8; ++i) sc[i] = 1.f;
+            }
+            if (shift) load8f(shift + cv * 8, sh);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sh[i] = 0.f;
+            }
         }
         long long p = (long long)blockIdx.x * R + ry;
         for (; p + 3 * S < P; p += 4 * S) {
@@ -155,9 +195,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
                 if (HAS_RES) unpack8(rr[u], g);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    float t = fmaf(f[i], sc[i], sh[i]);
-                    if (HAS_RES) t += g[i];
-                    f[i] = relu ? fmaxf(t, 0.f) : t;
+                    float tt = fmaf(f[i], sc[i], sh[i]);
+                    if (HAS_RES) tt += g[i];
+                    f[i] = relu ? fmaxf(tt, 0.f) : tt;
                 }
                 stg_stream(z + (p + u * S) * z_ld8 + cv, pack8(f));
             }
@@ -168,9 +208,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
             if (HAS_RES) unpack8(ldg_stream(res + p * res_ld8 + cv), g);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                float t = fmaf(f[i], sc[i], sh[i]);
-                if (HAS_RES) t += g[i];
-                f[i] = relu ? fmaxf(t, 0.f) : t;
+                float tt = fmaf(f[i], sc[i], sh[i]);
+                if (HAS_RES) tt += g[i];
+                f[i] = relu ? fmaxf(tt, 0.f) : tt;
             }
             stg_stream(z + p * z_ld8 + cv, pack8(f));
         }
@@ -180,13 +220,19 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
 // ------------------------------------------------------------------------------------------------
 // backward pass 1: per-channel sums of g and g*xhat, g = dz * [z > 0]
 // ------------------------------------------------------------------------------------------------
-template <bool HAS_Z>
+// MASK: 0 = no activation, 1 = ReLU mask from the stored output z (needed when a residual was added),
+//       2 = ReLU mask recomputed from y: [fma(y, scale, shift) > 0] -- bit-identical to the forward's test and one
+//           tensor read cheaper.
+template <int MASK>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restrict__ dz, long long dz_ld8,
                                                             const uint4* __restrict__ y, long long y_ld8,
                                                             const uint4* __restrict__ z, long long z_ld8,
                                                             const float* __restrict__ mean,
-                                                            const float* __restrict__ invstd, long long P, int C,
+                                                            const float* __restrict__ invstd,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, long long P, int C,
                                                             int C8, int Vc, int R, double* __restrict__ sums) {
+    constexpr bool HAS_Z = (MASK == 1);
     __shared__ float red[256 * 16];
     const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
     const long long S = (long long)gridDim.x * R;
@@ -196,9 +242,10 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
 #pragma unroll
         for (int i = 0; i < 8; ++i) { sg[i] = 0.f; sx[i] = 0.f; }
         if (cv < C8) {
-            float mu[8], is[8];
+            float mu[8], is[8], sc[8], sh[8];
             load8f(mean + cv * 8, mu);
             load8f(invstd + cv * 8, is);
+            if (MASK == 2) { load8f(scale + cv * 8, sc); load8f(shift + cv * 8, sh); }
             long long p = (long long)blockIdx.x * R + ry;
             for (; p + S < P; p += 2 * S) {
                 uint4 a[2], b[2], c[2];
@@ -216,7 +263,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
                     if (HAS_Z) unpack8(c[u], zz);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float gi = (HAS_Z && !(zz[i] > 0.f)) ? 0.f : g[i];
+                        bool dead = HAS_Z && !(zz[i] > 0.f);
+                        if (MASK == 2) dead = !(fmaf(yy[i], sc[i], sh[i]) > 0.f);
+                        const float gi = dead ? 0.f : g[i];
                         sg[i] += gi;
                         sx[i] = fmaf(gi, (yy[i] - mu[i]) * is[i], sx[i]);
                     }
@@ -229,7 +278,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
                 if (HAS_Z) unpack8(ldg_stream(z + p * z_ld8 + cv), zz);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float gi = (HAS_Z && !(zz[i] > 0.f)) ? 0.f : g[i];
+                    bool dead = HAS_Z && !(zz[i] > 0.f);
+                    if (MASK == 2) dead = !(fmaf(yy[i], sc[i], sh[i]) > 0.f);
+                    const float gi = dead ? 0.f : g[i];
                     sg[i] += gi;
                     sx[i] = fmaf(gi, (yy[i] - mu[i]) * is[i], sx[i]);
                 }
@@ -242,23 +293,28 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
 // ------------------------------------------------------------------------------------------------
 // backward pass 2: dy = gamma*invstd*( g - sum_g/count - xhat*sum_gx/count ); dres = g
 // ------------------------------------------------------------------------------------------------
-template <bool HAS_Z, bool HAS_DRES>
+template <int MASK, bool HAS_DRES>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ dz, long long dz_ld8,
                                                            const uint4* __restrict__ y, long long y_ld8,
                                                            const uint4* __restrict__ z, long long z_ld8,
                                                            const float* __restrict__ mean,
                                                            const float* __restrict__ invstd,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
                                                            const float* __restrict__ gamma,
                                                            const double* __restrict__ sums, double inv_count,
                                                            long long P, int C, int C8, int Vc, int R,
                                                            uint4* __restrict__ dy, long long dy_ld8,
-                                                           uint4* __restrict__ dres, long long dres_ld8) {
+                                                           uint4* __restrict__ dres, long long dres_ld8,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    constexpr bool HAS_Z = (MASK == 1);
     const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
     const long long S = (long long)gridDim.x * R;
     for (int cv = cx; cv < C8; cv += Vc) {
-        float mu[8], is[8], k0[8], k1[8], k2[8];
+        float mu[8], is[8], k0[8], k1[8], k2[8], sc[8], sh[8];
         load8f(mean + cv * 8, mu);
         load8f(invstd + cv * 8, is);
+        if (MASK == 2) { load8f(scale + cv * 8, sc); load8f(shift + cv * 8, sh); }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int c = cv * 8 + i;
@@ -266,6 +322,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
             k0[i] = g * is[i];                                               // gamma * invstd
             k1[i] = static_cast<float>(sums[c] * inv_count);                 // mean of g
             k2[i] = static_cast<float>(sums[C + c] * inv_count);             // mean of g*xhat
+            if (blockIdx.x == 0 && ry == 0) {   // parameter gradients (single-rank case: local sums == group sums)
+                if (dgamma) dgamma[c] += static_cast<float>(sums[C + c]);
+                if (dbeta) dbeta[c] += static_cast<float>(sums[c]);
+            }
         }
         for (long long p = (long long)blockIdx.x * R + ry; p < P; p += S) {
             float g[8], yy[8], zz[8], o[8];
@@ -274,7 +334,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
             if (HAS_Z) unpack8(ldg_stream(z + p * z_ld8 + cv), zz);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float gi = (HAS_Z && !(zz[i] > 0.f)) ? 0.f : g[i];
+                bool dead = HAS_Z && !(zz[i] > 0.f);
+                if (MASK == 2) dead = !(fmaf(yy[i], sc[i], sh[i]) > 0.f);
+                const float gi = dead ? 0.f : g[i];
                 g[i] = gi;
                 const float xh = (yy[i] - mu[i]) * is[i];
                 o[i] = k0[i] * (gi - k1[i] - xh * k2[i]);
@@ -339,12 +401,21 @@ static int check_act(const void* p, long long ld, int C, const char* what) {
 
 using namespace gs;
 
+static inline int reduce_grid(const ColMap& m, long long P) {
+    // enough blocks for >= 4 per SM when the tensor allows it, at least 4 pixels per thread row
+    long long ppt = P / ((long long)m.R * 148 * 4);
+    if (ppt < 4) ppt = 4;
+    if (ppt > 64) ppt = 64;
+    return colmap_grid(m, P, (int)ppt, 148 * 8);
+}
+
+
 extern "C" int gs_bn_stats(const void* x, int64_t P, int32_t C, int32_t ld, double* stats, void* stream) {
     if (check_act(x, ld, C, "bn_stats x")) return -1;
     GS_REQUIRE(stats != nullptr, "bn_stats: null stats");
     if (P <= 0) return 0;
     const ColMap m = make_colmap(C);
-    const int grid = colmap_grid(m, P, 32, 148 * 4);
+    const int grid = reduce_grid(m, P);
     bn_stats_kernel<<<grid, m.threads, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const uint4*>(x), ld / 8, P, C, m.C8, m.Vc, m.R, stats);
     GS_LAUNCHED();
@@ -378,66 +449,104 @@ extern "C" int gs_bn_apply(const void* y, int32_t y_ld, const float* scale, cons
     if (residual && check_act(residual, res_ld, C, "bn_apply residual")) return -1;
     if (P <= 0) return 0;
     const ColMap m = make_colmap(C);
-    const int grid = colmap_grid(m, P, 8, 148 * 8);
+    const int grid = reduce_grid(m, P);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    BnTrainArgs t{};
     if (residual)
-        bn_apply_kernel<true><<<grid, m.threads, 0, st>>>(reinterpret_cast<const uint4*>(y), y_ld / 8, scale, shift,
-                                                          reinterpret_cast<const uint4*>(residual), res_ld / 8, relu,
-                                                          reinterpret_cast<uint4*>(z), z_ld / 8, P, m.C8, m.Vc, m.R);
+        bn_apply_kernel<true, false><<<grid, m.threads, 0, st>>>(
+            reinterpret_cast<const uint4*>(y), y_ld / 8, scale, shift, reinterpret_cast<const uint4*>(residual),
+            res_ld / 8, relu, reinterpret_cast<uint4*>(z), z_ld / 8, P, m.C8, m.Vc, m.R, t);
     else
-        bn_apply_kernel<false><<<grid, m.threads, 0, st>>>(reinterpret_cast<const uint4*>(y), y_ld / 8, scale, shift,
-                                                           nullptr, 0, relu, reinterpret_cast<uint4*>(z), z_ld / 8, P,
-                                                           m.C8, m.Vc, m.R);
+        bn_apply_kernel<false, false><<<grid, m.threads, 0, st>>>(
+            reinterpret_cast<const uint4*>(y), y_ld / 8, scale, shift, nullptr, 0, relu, reinterpret_cast<uint4*>(z),
+            z_ld / 8, P, m.C8, m.Vc, m.R, t);
+    GS_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gs_bn_apply_train(const void* y, int32_t y_ld, const double* stats, double count, const float* gamma,
+                                 const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                                 float* aff, const void* residual, int32_t res_ld, int32_t relu, void* z, int32_t z_ld,
+                                 int64_t P, int32_t C, void* stream) {
+    if (check_act(y, y_ld, C, "bn_apply_train y") || check_act(z, z_ld, C, "bn_apply_train z")) return -1;
+    if (residual && check_act(residual, res_ld, C, "bn_apply_train residual")) return -1;
+    GS_REQUIRE(stats && aff && count > 0, "bn_apply_train: null stats / aff or empty count");
+    if (P <= 0) return 0;
+    const ColMap m = make_colmap(C);
+    const int grid = reduce_grid(m, P);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    BnTrainArgs t{};
+    t.stats = stats; t.inv_count = 1.0 / count; t.unbias = count > 1.0 ? count / (count - 1.0) : 1.0;
+    t.gamma = gamma; t.beta = beta; t.rm = running_mean; t.rv = running_var; t.momentum = momentum; t.eps = eps;
+    t.aff = aff; t.C = C;
+    if (residual)
+        bn_apply_kernel<true, true><<<grid, m.threads, 0, st>>>(
+            reinterpret_cast<const uint4*>(y), y_ld / 8, nullptr, nullptr, reinterpret_cast<const uint4*>(residual),
+            res_ld / 8, relu, reinterpret_cast<uint4*>(z), z_ld / 8, P, m.C8, m.Vc, m.R, t);
+    else
+        bn_apply_kernel<false, true><<<grid, m.threads, 0, st>>>(
+            reinterpret_cast<const uint4*>(y), y_ld / 8, nullptr, nullptr, nullptr, 0, relu,
+            reinterpret_cast<uint4*>(z), z_ld / 8, P, m.C8, m.Vc, m.R, t);
     GS_LAUNCHED();
     return 0;
 }
 
 extern "C" int gs_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z,
-                                int32_t z_ld, const float* mean, const float* invstd, int64_t P, int32_t C,
-                                double* sums, void* stream) {
+                                int32_t z_ld, const float* mean, const float* invstd, const float* scale,
+                                const float* shift, int32_t relu, int64_t P, int32_t C, double* sums, void* stream) {
     if (check_act(dz, dz_ld, C, "bn_bwd_reduce dz") || check_act(y, y_ld, C, "bn_bwd_reduce y")) return -1;
     if (z && check_act(z, z_ld, C, "bn_bwd_reduce z")) return -1;
     GS_REQUIRE(mean && invstd && sums, "bn_bwd_reduce: null pointer");
+    GS_REQUIRE(!relu || z || (scale && shift), "bn_bwd_reduce: ReLU mask needs z or (scale, shift)");
     if (P <= 0) return 0;
     const ColMap m = make_colmap(C);
-    const int grid = colmap_grid(m, P, 32, 148 * 4);
+    const int grid = reduce_grid(m, P);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (z)
-        bn_bwd_reduce_kernel<true><<<grid, m.threads, 0, st>>>(
-            reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8,
-            reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, P, C, m.C8, m.Vc, m.R, sums);
-    else
-        bn_bwd_reduce_kernel<false><<<grid, m.threads, 0, st>>>(
-            reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8, nullptr, 0,
-            mean, invstd, P, C, m.C8, m.Vc, m.R, sums);
+    const int mask = !relu ? 0 : (z ? 1 : 2);
+#define GS_BWD_REDUCE(MK)                                                                                            \
+    bn_bwd_reduce_kernel<MK><<<grid, m.threads, 0, st>>>(                                                            \
+        reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8,                  \
+        reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, scale, shift, P, C, m.C8, m.Vc, m.R, sums)
+    if (mask == 0) GS_BWD_REDUCE(0);
+    else if (mask == 1) GS_BWD_REDUCE(1);
+    else GS_BWD_REDUCE(2);
+#undef GS_BWD_REDUCE
     GS_LAUNCHED();
     return 0;
 }
 
 extern "C" int gs_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z, int32_t z_ld,
-                               const float* mean, const float* invstd, const float* gamma, const double* sums,
-                               double count, int64_t P, int32_t C, void* dy, int32_t dy_ld, void* dres,
-                               int32_t dres_ld, void* stream) {
+                               const float* mean, const float* invstd, const float* scale, const float* shift,
+                               int32_t relu, const float* gamma, const double* sums, double count, int64_t P, int32_t C,
+                               void* dy, int32_t dy_ld, void* dres, int32_t dres_ld, float* dgamma, float* dbeta,
+                               void* stream) {
     if (check_act(dz, dz_ld, C, "bn_bwd_apply dz") || check_act(y, y_ld, C, "bn_bwd_apply y") ||
         check_act(dy, dy_ld, C, "bn_bwd_apply dy"))
         return -1;
     if (z && check_act(z, z_ld, C, "bn_bwd_apply z")) return -1;
     if (dres && check_act(dres, dres_ld, C, "bn_bwd_apply dres")) return -1;
     GS_REQUIRE(mean && invstd && sums && count > 0, "bn_bwd_apply: null pointer / empty count");
+    GS_REQUIRE(!relu || z || (scale && shift), "bn_bwd_apply: ReLU mask needs z or (scale, shift)");
     if (P <= 0) return 0;
     const ColMap m = make_colmap(C);
-    const int grid = colmap_grid(m, P, 8, 148 * 8);
+    const int grid = reduce_grid(m, P);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const double inv_count = 1.0 / count;
-#define GS_BWD_APPLY(HZ, HD)                                                                                         \
-    bn_bwd_apply_kernel<HZ, HD><<<grid, m.threads, 0, st>>>(                                                         \
+    const int mask = !relu ? 0 : (z ? 1 : 2);
+#define GS_BWD_APPLY(MK, HD)                                                                                         \
+    bn_bwd_apply_kernel<MK, HD><<<grid, m.threads, 0, st>>>(                                                         \
         reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8,                  \
-        reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, gamma, sums, inv_count, P, C, m.C8, m.Vc, m.R,    \
-        reinterpret_cast<uint4*>(dy), dy_ld / 8, reinterpret_cast<uint4*>(dres), dres_ld / 8)
-    if (z && dres) GS_BWD_APPLY(true, true);
-    else if (z) GS_BWD_APPLY(true, false);
-    else if (dres) GS_BWD_APPLY(false, true);
-    else GS_BWD_APPLY(false, false);
+        reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, scale, shift, gamma, sums, inv_count, P, C, m.C8, \
+        m.Vc, m.R, reinterpret_cast<uint4*>(dy), dy_ld / 8, reinterpret_cast<uint4*>(dres), dres_ld / 8, dgamma, dbeta)
+    if (dres) {
+        if (mask == 0) GS_BWD_APPLY(0, true);
+        else if (mask == 1) GS_BWD_APPLY(1, true);
+        else GS_BWD_APPLY(2, true);
+    } else {
+        if (mask == 0) GS_BWD_APPLY(0, false);
+        else if (mask == 1) GS_BWD_APPLY(1, false);
+        else GS_BWD_APPLY(2, false);
+    }
 #undef GS_BWD_APPLY
     GS_LAUNCHED();
     return 0;
@@ -450,7 +559,7 @@ extern "C" int gs_affine_bwd(const void* dz, int32_t dz_ld, const void* z, int32
     if (dres && check_act(dres, dres_ld, C, "affine_bwd dres")) return -1;
     if (P <= 0) return 0;
     const ColMap m = make_colmap(C);
-    const int grid = colmap_grid(m, P, 8, 148 * 8);
+    const int grid = reduce_grid(m, P);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define GS_AFF_BWD(HZ, HD)                                                                                      \
     affine_bwd_kernel<HZ, HD><<<grid, m.threads, 0, st>>>(                                                      \

@@ -4,7 +4,7 @@
 //
 // Master conv weights are stored [Co_max][kh][kw][Ci_max] (channels_last memory of the OIHW
 // parameter), so the forward shadow `w_krsc` is an element-wise bf16 cast at the same flat index;
-// the dgrad shadow `w_crsk` [Ci_max][kh][kw][Co_max] is a tiled transpose-cast per tensor.
+// dgrad reads the same buffer as an MN-major tcgen05 operand, so no transposed copy exists.
 #include "../../include/gaiaseg_b200.h"
 #include "gs_host.h"
 
@@ -42,24 +42,6 @@ __global__ void __launch_bounds__(256) sgd_flat_kernel(float4* __restrict__ p, c
     }
 }
 
-// src fp32 [Co][R][Ci]  ->  dst bf16 [Ci][R][CoP], CoP = round_up(Co, 8)   (32x32 tiles over (co, ci) per r)
-__global__ void transpose_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Co, int R,
-                                      int Ci) {
-    __shared__ float tile[32][33];
-    const int r = blockIdx.z;
-    const int CoP = (Co + 7) & ~7;
-    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
-    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-        const int co = co0 + j, ci = ci0 + threadIdx.x;
-        tile[j][threadIdx.x] = (co < Co && ci < Ci) ? src[((long long)co * R + r) * Ci + ci] : 0.f;
-    }
-    __syncthreads();
-    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-        const int ci = ci0 + j, co = co0 + threadIdx.x;
-        if (ci < Ci && co < Co) dst[((long long)ci * R + r) * CoP + co] = __float2bfloat16_rn(tile[threadIdx.x][j]);
-    }
-}
-
 }  // namespace gs
 
 using namespace gs;
@@ -81,12 +63,3 @@ extern "C" int gs_sgd_flat(float* p, const float* g, float* momentum_buf, int64_
     return 0;
 }
 
-extern "C" int gs_transpose_cast(const float* w_krsc_f32, void* w_crsk_bf16, int32_t Co, int32_t R, int32_t Ci,
-                                 void* stream) {
-    GS_REQUIRE(w_krsc_f32 && w_crsk_bf16 && Co > 0 && R > 0 && Ci > 0, "transpose_cast: bad arguments");
-    dim3 grid((Ci + 31) / 32, (Co + 31) / 32, R);
-    transpose_cast_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-        w_krsc_f32, reinterpret_cast<__nv_bfloat16*>(w_crsk_bf16), Co, R, Ci);
-    GS_LAUNCHED();
-    return 0;
-}

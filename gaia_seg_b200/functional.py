@@ -109,6 +109,40 @@ def _pixels(t):
     return t.shape[0] * t.shape[2] * t.shape[3]
 
 
+class _ZeroPool:
+    """Zero-initialised fp64 scratch for the per-layer statistic accumulators (the kernels add into them with
+    atomics).  One big buffer per device, handed out in slices and re-zeroed with ONE memset when it wraps, instead
+    of a torch.zeros launch per layer.  Safe because every slice is consumed in stream order right after it is
+    produced (stats -> apply, sums -> bwd_apply) and the memset is enqueued on the same stream."""
+    SIZE = 1 << 22   # doubles (32 MB)
+
+    def __init__(self):
+        self.bufs = {}
+
+    def take(self, n, device):
+        n = (n + 15) // 16 * 16
+        st = self.bufs.get(device)
+        if st is None:
+            st = self.bufs[device] = [torch.zeros(self.SIZE, dtype=torch.float64, device=device), 0]
+        if n > self.SIZE:
+            return torch.zeros(n, dtype=torch.float64, device=device)
+        if st[1] + n > self.SIZE:
+            st[0].zero_()
+            st[1] = 0
+        out = st[0][st[1]:st[1] + n]
+        st[1] += n
+        return out
+
+
+_zero_pool = _ZeroPool()
+
+
+def zeros_f64(n, device):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return torch.zeros(n, dtype=torch.float64, device=device)   # all-reduced buffers: keep them private
+    return _zero_pool.take(n, device)[:n]
+
+
 # ------------------------------------------------------------------------------------------------
 # convolution
 # ------------------------------------------------------------------------------------------------
@@ -149,50 +183,40 @@ def ensure_krsc(conv):
 
 
 def conv_shadows(conv):
-    """bf16 shadows of the max-width weight (forward KRSC, dgrad CRSK); rebuilt when the fp32 master
-    was modified by anything other than the fused optimizer (tracked through tensor._version)."""
+    """bf16 shadow of the max-width weight, [Co_max][kh][kw][Ci_max] (the forward B operand; dgrad reads the same
+    buffer as an MN-major operand).  Rebuilt when the fp32 master was modified by anything other than the fused
+    optimizer (tracked through tensor._version)."""
     w = ensure_krsc(conv)
     if w.dtype != torch.float32 or not w.is_cuda:
         raise GsError('DynamicConv2d: master weight must be fp32 on a CUDA device')
     key = (w.data_ptr(), w._version)
     if getattr(conv, '_gs_key', None) == key:
-        return conv._gs_w_krsc, conv._gs_w_crsk
+        return conv._gs_w_krsc
     Co, Ci, kh, kw = w.shape
     R = kh * kw
     st = _stream()
+    krsc = getattr(conv, '_gs_w_krsc', None)
     if is_image_conv(conv):
         K, Kpad = R * Ci, image_kpad(conv)
-        krsc = getattr(conv, '_gs_w_krsc', None)
         if krsc is None or krsc.numel() != Co * Kpad or krsc.device != w.device:
             krsc = torch.empty(Co * Kpad, dtype=BF16, device=w.device)
         call('gs_cast_f32_bf16', w.data_ptr(), K, krsc.data_ptr(), Kpad, Co, K, st)
-        crsk = None
     else:
         n = w.numel()
-        krsc = getattr(conv, '_gs_w_krsc', None)
         if krsc is None or krsc.numel() != n or krsc.device != w.device:
             krsc = torch.empty(n, dtype=BF16, device=w.device)
         call('gs_cast_f32_bf16', w.data_ptr(), n, krsc.data_ptr(), n, 1, n, st)
-        crsk = getattr(conv, '_gs_w_crsk', None)
-        cop = round_up(Co, 8)
-        if crsk is None or crsk.numel() != Ci * R * cop or crsk.device != w.device:
-            crsk = torch.empty(Ci * R * cop, dtype=BF16, device=w.device)
-        call('gs_transpose_cast', w.data_ptr(), crsk.data_ptr(), Co, R, Ci, st)
-    conv._gs_w_krsc, conv._gs_w_crsk, conv._gs_key = krsc, crsk, key
-    return krsc, crsk
+    conv._gs_w_krsc, conv._gs_key = krsc, key
+    return krsc
 
 
-def refresh_crsk(conv):
-    """Called by the fused optimizer after it rewrote master + KRSC shadow through raw pointers."""
-    if is_image_conv(conv):
-        w = conv.weight
-        Co, Ci, kh, kw = w.shape
-        K, Kpad = kh * kw * Ci, image_kpad(conv)
-        call('gs_cast_f32_bf16', w.data_ptr(), K, conv._gs_w_krsc.data_ptr(), Kpad, Co, K, _stream())
-        return
+def refresh_image_shadow(conv):
+    """Called by the fused optimizer for the (zero-padded, im2col-ordered) shadow of the first conv; every other
+    shadow lives inside the flat bf16 buffer the optimizer kernel rewrites itself."""
     w = conv.weight
     Co, Ci, kh, kw = w.shape
-    call('gs_transpose_cast', w.data_ptr(), conv._gs_w_crsk.data_ptr(), Co, kh * kw, Ci, _stream())
+    K, Kpad = kh * kw * Ci, image_kpad(conv)
+    call('gs_cast_f32_bf16', w.data_ptr(), K, conv._gs_w_krsc.data_ptr(), Kpad, Co, K, _stream())
 
 
 def _geom(N, H, W, Ci, Co, Ci_max, Co_max, kh, kw, stride, pad, dil, x_ld, y_ld):
@@ -207,7 +231,7 @@ def conv_forward(x, conv, Co, scale=None, shift=None, residual=None, relu=False,
     """y = epi(conv(x, W[:Co, :Ci])).  Returns (y, stats, a_operand, geom): `a_operand` is the tensor the
     weight gradient must be taken against (x itself, or the im2col matrix of the image conv)."""
     _lib.require_device()
-    krsc, _ = conv_shadows(conv)
+    krsc = conv_shadows(conv)
     kh, kw, stride, pad, dil = _conv_attrs(conv)
     Co_max, Ci_max = conv.out_channels, conv.in_channels
     if not (0 < Co <= Co_max):
@@ -235,12 +259,13 @@ def conv_forward(x, conv, Co, scale=None, shift=None, residual=None, relu=False,
         if Ci > Ci_max:
             raise GsError(f'DynamicConv2d: input has {Ci} channels, max-width weight only {Ci_max}')
         g = _geom(N, H, W, Ci, Co, Ci_max, Co_max, kh, kw, stride, pad, dil, act_ld(a), 0)
+    conv._gs_last_ci = Ci
     y_ld = Co if not out_f32 else Co
     y = new_act(N, Co, g.Ho, g.Wo, dev, torch.float32 if out_f32 else BF16, ld=y_ld)
     g.y_ld = y_ld
     stats = None
     if want_stats:
-        stats = torch.zeros(2 * Co, dtype=torch.float64, device=dev)
+        stats = zeros_f64(2 * Co, dev)
     flags = (1 if relu else 0) | (2 if out_f32 else 0)
     res_ld = 0
     if residual is not None:
@@ -282,7 +307,7 @@ def conv_wgrad(conv, a, dy, g):
 
 def conv_dgrad(conv, dy, g, x_shape, add=None):
     """dx = conv_transpose(dy, W[:Co, :Ci]) (+ add)."""
-    krsc, crsk = conv_shadows(conv)
+    krsc = conv_shadows(conv)
     N, Ci, H, W = x_shape
     dx = new_act(N, Ci, H, W, dy.device)
     g.x_ld = Ci
@@ -297,7 +322,7 @@ def conv_dgrad(conv, dy, g, x_shape, add=None):
         nbytes = _lib.load().gs_conv2d_dgrad_workspace_bytes(ctypes.byref(g))
         if nbytes > 0:
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dy.device)
-        _timed_call('dgrad', g, 'gs_conv2d_dgrad', ctypes.byref(g), dy.data_ptr(), crsk.data_ptr(), dx.data_ptr(),
+        _timed_call('dgrad', g, 'gs_conv2d_dgrad', ctypes.byref(g), dy.data_ptr(), krsc.data_ptr(), dx.data_ptr(),
                     _ptr(add), add_ld, _ptr(ws), st)
     else:
         _timed_call('dgrad', g, 'gs_conv2d_dgrad_simt', ctypes.byref(g), dy.data_ptr(), krsc.data_ptr(), dx.data_ptr(),
@@ -323,23 +348,57 @@ def _sync_group(bn):
     return pg, world
 
 
-def bn_finalize(bn, stats, C, local_count):
-    """all-reduce the packed (sum, sumsq), then mean / invstd / scale / shift (+ running stats)."""
+def bn_train_apply(bn, y, stats, C, residual=None, relu=False):
+    """all-reduce the packed (sum, sumsq) over the SyncBN group, then ONE kernel: finalize (mean / invstd / scale /
+    shift, running-stat update of the channel prefix) + normalise + residual + ReLU.  Returns (z, aff, count)."""
     pg, world = _sync_group(bn)
     if world > 1:
         dist.all_reduce(stats, group=pg)
-    count = float(local_count) * world
-    aff = torch.empty((4, C), dtype=torch.float32, device=stats.device)
+    count = float(_pixels(y)) * world
+    aff = torch.empty((4, C), dtype=torch.float32, device=y.device)
     upd = bn.training and bn.track_running_stats and bn.running_mean is not None
     if upd and bn.momentum is None:
         raise GsError('DynamicBatchNorm2d: momentum=None (cumulative average) is not supported on the CUDA path')
-    call('gs_bn_finalize', stats.data_ptr(), count, C, _ptr(bn.weight), _ptr(bn.bias),
+    N, _, H, W = y.shape
+    z = new_act(N, C, H, W, y.device)
+    res_ld = 0
+    if residual is not None:
+        residual = as_act(residual)
+        res_ld = act_ld(residual)
+    call('gs_bn_apply_train', y.data_ptr(), act_ld(y), stats.data_ptr(), count, _ptr(bn.weight), _ptr(bn.bias),
          bn.running_mean.data_ptr() if upd else None, bn.running_var.data_ptr() if upd else None,
-         float(bn.momentum if bn.momentum is not None else 0.0), float(bn.eps), aff[0].data_ptr(), aff[1].data_ptr(),
-         aff[2].data_ptr(), aff[3].data_ptr(), _stream())
+         float(bn.momentum if bn.momentum is not None else 0.0), float(bn.eps), aff.data_ptr(), _ptr(residual), res_ld,
+         1 if relu else 0, z.data_ptr(), C, _pixels(y), C, _stream())
     if upd:
         bn._gs_nbt_pending = getattr(bn, '_gs_nbt_pending', 0) + 1
-    return aff, count
+    return z, aff, count
+
+
+def bn_backward(bn, dz, y, aff, count, zmask, relu, want_dres):
+    """Two kernels: per-channel sums (+ all-reduce over the SyncBN group), then dy (+ dres, + parameter grads)."""
+    N, C, H, W = dz.shape
+    P, dev, st = N * H * W, dz.device, _stream()
+    mean, invstd, scale, shift = aff[0], aff[1], aff[2], aff[3]
+    sums = zeros_f64(2 * C, dev)
+    zl = act_ld(zmask) if zmask is not None else 0
+    call('gs_bn_bwd_reduce', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),
+         invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, P, C, sums.data_ptr(), st)
+    gw = bn.weight is not None and bn.weight.requires_grad
+    gb = bn.bias is not None and bn.bias.requires_grad
+    dgam = _param_grad(bn.weight).data_ptr() if gw else None
+    dbet = _param_grad(bn.bias).data_ptr() if gb else None
+    pg, world = _sync_group(bn)
+    if world > 1:
+        if gw or gb:   # parameter gradients come from the LOCAL sums (the gradient all-reduce averages them later)
+            call('gs_bn_bwd_param', sums.data_ptr(), C, dgam, dbet, 1, st)
+        dgam = dbet = None
+        dist.all_reduce(sums, group=pg)
+    dy = new_act(N, C, H, W, dev)
+    dres = new_act(N, C, H, W, dev) if want_dres else None
+    call('gs_bn_bwd_apply', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),
+         invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, _ptr(bn.weight), sums.data_ptr(),
+         float(count), P, C, dy.data_ptr(), C, _ptr(dres), C, dgam, dbet, st)
+    return dy, dres
 
 
 def bn_eval_affine(bn, C):
@@ -352,7 +411,7 @@ def bn_eval_affine(bn, C):
 def bn_stats(x):
     x = as_act(x)
     C = x.shape[1]
-    stats = torch.zeros(2 * C, dtype=torch.float64, device=x.device)
+    stats = zeros_f64(2 * C, x.device)
     call('gs_bn_stats', x.data_ptr(), _pixels(x), C, act_ld(x), stats.data_ptr(), _stream())
     return stats
 
@@ -388,8 +447,7 @@ def cba_forward(x, conv, bn=None, relu=False, residual=None, Co=None, save=True)
     rec = LayerRec() if save else None
     if bn is not None and bn_batch_mode(bn):
         y, stats, a, g = conv_forward(x, conv, Co, shift=_bias(conv, Co), want_stats=True)
-        aff, count = bn_finalize(bn, stats, Co, _pixels(y))
-        z = bn_apply(y, aff[2], aff[3], residual, relu)
+        z, aff, count = bn_train_apply(bn, y, stats, Co, residual, relu)
         mode = 'bn_batch'
     else:
         y = None
@@ -423,25 +481,11 @@ def cba_backward(rec, dz, need_dx=True, dx_add=None):
     dev = dz.device
     st = _stream()
     zmask = rec.z if rec.relu else None
-    dres = new_act(N, C, Ho, Wo, dev) if rec.has_res else None
     if rec.mode == 'bn_batch':
-        mean, invstd = rec.aff[0], rec.aff[1]
-        sums = torch.zeros(2 * C, dtype=torch.float64, device=dev)
-        call('gs_bn_bwd_reduce', dz.data_ptr(), act_ld(dz), rec.y.data_ptr(), act_ld(rec.y), _ptr(zmask),
-             act_ld(zmask) if zmask is not None else 0, mean.data_ptr(), invstd.data_ptr(), P, C, sums.data_ptr(), st)
-        gw = bn.weight is not None and bn.weight.requires_grad
-        gb = bn.bias is not None and bn.bias.requires_grad
-        if gw or gb:
-            call('gs_bn_bwd_param', sums.data_ptr(), C, _param_grad(bn.weight).data_ptr() if gw else None,
-                 _param_grad(bn.bias).data_ptr() if gb else None, 1, st)
-        pg, world = _sync_group(bn)
-        if world > 1:
-            dist.all_reduce(sums, group=pg)
-        dy = new_act(N, C, Ho, Wo, dev)
-        call('gs_bn_bwd_apply', dz.data_ptr(), act_ld(dz), rec.y.data_ptr(), act_ld(rec.y), _ptr(zmask),
-             act_ld(zmask) if zmask is not None else 0, mean.data_ptr(), invstd.data_ptr(), _ptr(bn.weight),
-             sums.data_ptr(), float(rec.count), P, C, dy.data_ptr(), C, _ptr(dres), C, st)
+        # without a residual the ReLU mask is recomputed from y (one tensor read less than reading z)
+        dy, dres = bn_backward(bn, dz, rec.y, rec.aff, rec.count, zmask if rec.has_res else None, rec.relu, rec.has_res)
     else:
+        dres = new_act(N, C, Ho, Wo, dev) if rec.has_res else None
         scale = rec.aff[0] if rec.mode == 'affine' else None
         if scale is None and zmask is None and dres is None:
             dy = dz

@@ -187,6 +187,7 @@ class FlatParams:
                 m._gs_key = None
         for m in self.convs:
             F_gs.conv_shadows(m)
+        self.image_convs = [m for m in self.convs if F_gs.is_image_conv(m)]
 
     def zero_grad(self):
         self.flat_g.zero_()
@@ -204,7 +205,7 @@ class FlatParams:
 
 class GsSGD(torch.optim.Optimizer):
     """SGD(momentum, weight_decay) as one fused kernel over the flat master buffer; the same launch rewrites
-    the bf16 forward shadow, then one transpose-cast per conv refreshes the dgrad shadow.
+    the bf16 shadow weights (forward and dgrad read the same buffer).
     Semantics of torch.optim.SGD with dampening 0 / nesterov False
     (configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:175).  Every trainable parameter is updated every
     step (zero gradient for channels / blocks outside the sampled sub-net, like the reference after
@@ -228,8 +229,8 @@ class GsSGD(torch.optim.Optimizer):
         call('gs_sgd_flat', f.flat_p.data_ptr(), f.flat_g.data_ptr(), self.momentum_buf.data_ptr(), f.total,
              float(g['lr']), float(g['momentum']), float(g['weight_decay']), float(self.grad_scale),
              1 if self._steps == 0 else 0, f.flat_shadow.data_ptr(), F_gs._stream())
-        for m in f.convs:
-            F_gs.refresh_crsk(m)
+        for m in f.image_convs:
+            F_gs.refresh_image_shadow(m)
         self._steps += 1
 
     def state_dict(self):

@@ -17,8 +17,8 @@
  *     (concat without copy).  Pitches and base pointers of bf16 tensors are 16-byte aligned.
  *   - conv weights are the MAX-WIDTH supernet tensors; kernels address the active
  *     channel-prefix slice [0:Co, 0:Ci] in place through TMA descriptors (no slice copy):
- *       w_krsc : bf16 [Co_max][kh][kw][Ci_max]   (forward  B operand)
- *       w_crsk : bf16 [Ci_max][kh][kw][Co_pad]   (dgrad    B operand; Co_pad = Co_max rounded up to 8)
+ *       w_krsc : bf16 [Co_max][kh][kw][Ci_max]   (forward B operand, K-major; the SAME buffer is the dgrad B
+ *                                                 operand, read as an MN-major UMMA operand -- no transposed copy)
  *       dw_krsc: fp32 [Co_max][kh][kw][Ci_max]   (wgrad accumulator; == channels_last OIHW)
  *   - statistics buffers are fp64 [2*C]: sum[0:C], sum of squares [C:2C].
  */
@@ -75,7 +75,7 @@ int gs_conv2d_fwd(const gs_conv_geom* g, const void* x, const void* w_krsc, void
 /* dx = conv_transpose(dy, w[:Co,:Ci]) (+ residual).  replaces autograd of F.conv2d (cuDNN dgrad).
  * For stride > 1 `workspace` must hold gs_conv2d_dgrad_workspace_bytes(g) bytes. */
 int64_t gs_conv2d_dgrad_workspace_bytes(const gs_conv_geom* g);
-int gs_conv2d_dgrad(const gs_conv_geom* g, const void* dy, const void* w_crsk, void* dx, const void* residual,
+int gs_conv2d_dgrad(const gs_conv_geom* g, const void* dy, const void* w_krsc, void* dx, const void* residual,
                     int32_t res_ld, void* workspace, void* stream);
 
 /* dw_krsc[:Co, :, :, :Ci] += dy^T * im2col(x).  replaces autograd of F.conv2d (cuDNN wgrad);
@@ -122,17 +122,30 @@ int gs_bn_eval_affine(int32_t C, const float* gamma, const float* beta, const fl
 int gs_bn_apply(const void* y, int32_t y_ld, const float* scale, const float* shift, const void* residual,
                 int32_t res_ld, int32_t relu, void* z, int32_t z_ld, int64_t P, int32_t C, void* stream);
 
-/* Backward pass 1: g = dz * [z > 0] (z == NULL: no activation mask);
- * sums[0:C] += sum g ; sums[C:2C] += sum g * xhat, xhat = (y-mean)*invstd. */
+/* Training-mode apply with the finalize step folded into the kernel prologue (one launch instead of two):
+ * scale / shift are derived from the (all-reduced) sums, block 0 stores aff = [mean | invstd | scale | shift]
+ * ([4][C] fp32, needed by the backward pass) and updates running_mean / running_var (NULL to skip). */
+int gs_bn_apply_train(const void* y, int32_t y_ld, const double* stats, double count, const float* gamma,
+                      const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                      float* aff, const void* residual, int32_t res_ld, int32_t relu, void* z, int32_t z_ld, int64_t P,
+                      int32_t C, void* stream);
+
+/* Backward pass 1: g = dz * mask;  sums[0:C] += sum g ; sums[C:2C] += sum g * xhat, xhat = (y-mean)*invstd.
+ * mask: relu == 0 -> none; z != NULL -> [z > 0] (needed when a residual was added before the ReLU);
+ *       else [fma(y, scale, shift) > 0], bit-identical to the forward's test and one tensor read cheaper. */
 int gs_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z, int32_t z_ld,
-                     const float* mean, const float* invstd, int64_t P, int32_t C, double* sums, void* stream);
+                     const float* mean, const float* invstd, const float* scale, const float* shift, int32_t relu,
+                     int64_t P, int32_t C, double* sums, void* stream);
 
 /* Backward pass 2 (sums all-reduced over the SyncBN group, count = elements per channel in the group):
  *   dy = gamma*invstd*( g - sum_g/count - xhat*sum_gx/count )           -> dy (bf16)
- *   dres = g (bf16)                      if dres != NULL (gradient of the residual branch) */
+ *   dres = g (bf16)                      if dres != NULL (gradient of the residual branch)
+ *   dgamma[c] += sums[C+c], dbeta[c] += sums[c]   if non-NULL (single-rank case, where the local sums are the
+ *   group sums; with several ranks call gs_bn_bwd_param on the LOCAL sums before the all-reduce instead). */
 int gs_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z, int32_t z_ld,
-                    const float* mean, const float* invstd, const float* gamma, const double* sums, double count,
-                    int64_t P, int32_t C, void* dy, int32_t dy_ld, void* dres, int32_t dres_ld, void* stream);
+                    const float* mean, const float* invstd, const float* scale, const float* shift, int32_t relu,
+                    const float* gamma, const double* sums, double count, int64_t P, int32_t C, void* dy, int32_t dy_ld,
+                    void* dres, int32_t dres_ld, float* dgamma, float* dbeta, void* stream);
 
 /* Backward of a per-channel affine (+ReLU) with FIXED statistics (eval-mode / frozen BN, conv bias):
  *   g = dz * [z > 0];  dy = scale * g;  dres = g. */
@@ -217,10 +230,6 @@ int gs_upsample_bilinear_f32(const float* src, int32_t N, int32_t h, int32_t w, 
  * replaces torch.optim.SGD.step (configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:175-178) */
 int gs_sgd_flat(float* p, const float* g, float* momentum_buf, int64_t n, float lr, float momentum,
                 float weight_decay, float grad_scale, int32_t first_step, void* shadow_bf16, void* stream);
-/* dgrad shadow of one conv weight: fp32 [Co][R][Ci] (R = kh*kw) -> bf16 [Ci][R][Co_pad], Co_pad = Co rounded
- * up to a multiple of 8 (TMA pitch alignment; the padding columns are never read). */
-int gs_transpose_cast(const float* w_krsc_f32, void* w_crsk_bf16, int32_t Co, int32_t R, int32_t Ci, void* stream);
-
 #ifdef __cplusplus
 }
 #endif
