@@ -41,7 +41,14 @@ def _timed_call(kind, g, fn, *args):
     PROFILE.append((kind, flops, e0, e1))
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def _stream():
+    """cudaStream_t of torch's current stream on the current device (raw handle: torch.cuda.current_stream()
+    costs ~15 us of Python per call, this ~0.3 us)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
