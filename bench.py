@@ -342,7 +342,12 @@ def main():
         prof, Fg.PROFILE = Fg.PROFILE, None
         cyc_ms = e0.elapsed_time(e1)
         agg = {}
-        for kind, flops, a, b in prof:
+        shapes = {}
+        for kind, flops, a, b, shp in prof:
+            sd = shapes.setdefault((kind,) + shp, [0.0, 0.0, 0])
+            sd[0] += flops
+            sd[1] += a.elapsed_time(b)
+            sd[2] += 1
             d = agg.setdefault(kind, [0.0, 0.0, 0])
             d[0] += flops
             d[1] += a.elapsed_time(b)
@@ -357,6 +362,12 @@ def main():
         breakdown = {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0, 'ms': v[1], 'launches': v[2],
                          'share_of_step': v[1] / cyc_ms} for k, v in agg.items()}
         breakdown['profiled_step_ms'] = cyc_ms
+        if rank == 0:
+            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+            rows = [dict(kind=k[0], P=k[1], Ci=k[2], Co=k[3], k=k[4], stride=k[5], dil=k[6], launches=v[2], ms=v[1],
+                         tflops=v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0) for k, v in shapes.items()]
+            rows.sort(key=lambda r: -r['ms'])
+            json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'conv_shapes.json'), 'w'), indent=0)
         tot_flops = sum(v[0] for v in agg.values())
         breakdown['conv_flops_per_step'] = tot_flops
         breakdown['whole_step_tflops'] = tot_flops / (ms / args.steps * 1e-3) / 1e12

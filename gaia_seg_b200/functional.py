@@ -38,7 +38,7 @@ def _timed_call(kind, g, fn, *args):
     call(fn, *args)
     e1.record()
     flops = 2.0 * g.N * g.Ho * g.Wo * g.Co * g.Ci * g.kh * g.kw
-    PROFILE.append((kind, flops, e0, e1))
+    PROFILE.append((kind, flops, e0, e1, (g.N * g.Ho * g.Wo, g.Ci, g.Co, g.kh, g.stride, g.dil)))
 
 
 _raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
