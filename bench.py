@@ -332,6 +332,19 @@ def main():
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
     peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback (B200_PROFILING.md sustained 1.4 PF)'
     if not args.no_profile:
+        # (a) every C-ABI call timed -> share of each kernel family in one cycle
+        gs._lib.PROFILE_CALLS = []
+        torch.cuda.synchronize()
+        step_resident()
+        torch.cuda.synchronize()
+        calls, gs._lib.PROFILE_CALLS = gs._lib.PROFILE_CALLS, None
+        fam = {}
+        for name, a, b in calls:
+            d = fam.setdefault(name, [0.0, 0])
+            d[0] += a.elapsed_time(b)
+            d[1] += 1
+        kernel_ms = {k: {'ms': round(v[0], 3), 'launches': v[1]} for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])}
+        # (b) convolution launches with their algorithmic FLOPs
         Fg.PROFILE = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -362,6 +375,7 @@ def main():
         breakdown = {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0, 'ms': v[1], 'launches': v[2],
                          'share_of_step': v[1] / cyc_ms} for k, v in agg.items()}
         breakdown['profiled_step_ms'] = cyc_ms
+        breakdown['c_abi_calls_ms'] = kernel_ms
         if rank == 0:
             os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
             rows = [dict(kind=k[0], P=k[1], Ci=k[2], Co=k[3], k=k[4], stride=k[5], dil=k[6], launches=v[2], ms=v[1],

@@ -35,6 +35,7 @@ PROTOTYPES = {
     'gs_device_check': (_I, []),
     'gs_launch_count': (_L, []),
     'gs_reset_launch_count': (None, []),
+    'gs_debug_set_trace': (_I, [_P]),
     'gs_conv2d_fwd': (_I, [_G, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     'gs_conv2d_dgrad_workspace_bytes': (_L, [_G]),
     'gs_conv2d_dgrad': (_I, [_G, _P, _P, _P, _P, _I, _P, _P]),
@@ -116,9 +117,22 @@ def require_device():
     _device_ok = True
 
 
+# bench.py sets this to a list to time EVERY C-ABI call with CUDA events on the launching stream
+# (entries: (entry point name, start event, end event)); None in normal operation.
+PROFILE_CALLS = None
+
+
 def call(name, *args):
     """Call an int-returning entry point and raise on error."""
-    rc = getattr(load(), name)(*args)
+    if PROFILE_CALLS is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(_lib, name)(*args)
+        e1.record()
+        PROFILE_CALLS.append((name, e0, e1))
+    else:
+        rc = getattr(_lib, name)(*args)
     if rc != 0:
         raise GsError(f'{name} failed ({rc}): {last_error()}')
 

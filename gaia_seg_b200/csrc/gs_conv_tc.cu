@@ -35,7 +35,15 @@ constexpr int kIgStageBytes = kIgABytes + kIgBBytes;
 constexpr int kIgStagingBytes = 128 * 256 * 2;  // epilogue tile, 4 sub-tiles of [128][64] bf16
 constexpr int kIgBarBytes = 256;
 constexpr int kIgSmemBytes = 1024 + kIgStages * kIgStageBytes + kIgStagingBytes + kIgBarBytes;
-constexpr int kIgThreads = 192;
+constexpr int kIgThreads = 320;                // TMA warp, MMA warp, 8 epilogue warps
+
+// Optional in-kernel trace (gs_debug_set_trace): CTA 0 writes %globaltimer stamps of its pipeline events.
+//   [0] kernel start  [1] setup done  [16+i] producer issued stage i  [80+i] MMA saw stage i full
+//   [144+4t+{0,1,2,3}] epilogue tile t: accumulator ready / TMEM drained + staged / store issued / tile done
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ void trace(int slot) {
+    if (g_trace != nullptr && blockIdx.x == 0) g_trace[slot] = global_timer_ns();
+}
 
 struct IgemmParams {
     int N, Ho, Wo;        // output pixels
@@ -64,7 +72,8 @@ struct IgemmParams {
 
 __global__ void __launch_bounds__(kIgThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ IgemmParams p) {
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+             const __grid_constant__ IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
@@ -74,23 +83,27 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint64_t* empty_bar = bars + kIgStages;     // [kIgStages]
     uint64_t* tfull_bar = bars + 2 * kIgStages; // [2]
     uint64_t* tempty_bar = tfull_bar + 2;       // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* res_bar = tempty_bar + 2;          // [4] residual sub-tile landed in the staging ring
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) trace(0);
 
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (!p.direct) tma_prefetch_desc(&tmC);
+        if (!p.direct && p.residual != nullptr) tma_prefetch_desc(&tmR);
         for (int i = 0; i < kIgStages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
         }
+        for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -99,17 +112,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int groups = gridDim.x / p.n_tiles;   // m-tile stride of a CTA (host guarantees gridDim.x % n_tiles == 0)
     const int tiles_hw = p.tiles_h * p.tiles_w;
+    if (threadIdx.x == 0) trace(1);
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles;
-                const int mt = tile / p.n_tiles;
+            int tr_i = 0;
+            // CTA b owns ONE n-tile (b % n_tiles) for the whole kernel and walks m-tiles b / n_tiles + i * groups:
+            // the n_tiles CTAs that share an activation tile run side by side (L2 reuse), the weight tile of a CTA
+            // never changes, and the DynBN statistics of its output channels stay in registers until the end.
+            const int nt = blockIdx.x % p.n_tiles;
+            for (int mt = blockIdx.x / p.n_tiles; mt < p.m_tiles; mt += groups) {
                 const int img = mt / tiles_hw;
                 const int rem = mt - img * tiles_hw;
                 const int h0 = (rem / p.tiles_w) * p.TH;
@@ -125,6 +142,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         const int iw = w0 * p.in_mul + p.base + s * p.step;
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
+                            if (tr_i < 64) trace(16 + tr_i++);
                             uint8_t* a_dst = stage_base + stage * kIgStageBytes;
                             uint8_t* b_dst = a_dst + kIgABytes;
                             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -148,9 +166,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            int tr_i = 0;
             const int iters = p.taps_h * p.taps_w * p.kchunks;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles;
+            const int nt = blockIdx.x % p.n_tiles;
+            for (int mt = blockIdx.x / p.n_tiles; mt < p.m_tiles; mt += groups) {
                 int n_valid = p.Cout - nt * 256;
                 if (n_valid > 256) n_valid = 256;
                 const uint32_t umma_n = (n_valid + 15) & ~15;
@@ -163,6 +182,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after_sync();
+                    if (tr_i < 64) trace(80 + tr_i++);
                     const uint32_t a_addr = smem_u32(stage_base + stage * kIgStageBytes);
                     const uint32_t b_addr = a_addr + kIgABytes;
                     int krem = p.Kc - kc * 64;
@@ -185,17 +205,32 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
         }
     } else {
-        // =========================== epilogue (warps 2..5) ===========================
+        // =========================== epilogue (warps 2..9) ===========================
+        // Two warps per TMEM sub-partition: `half` 0 drains accumulator columns 0..127 (sub-tiles 0,1), half 1
+        // columns 128..255 (sub-tiles 2,3); each half is an independent 128-thread pipeline with its own named
+        // barrier, two staging slots and its own TMA-store thread.
+        // Per tile: four 64-column sub-tiles, each  TMEM -> registers -> affine / residual / ReLU -> bf16 -> swizzled
+        // staging buffer (ring of 4 x 16 KB) -> TMA store, software-pipelined so the store of sub-tile j overlaps
+        // the drain of j+1 (one named barrier per sub-tile).  DynBN statistics: every lane re-reads the 32 rows
+        // its own warp just staged (column pair = lane, conflict-free) and keeps sum / sum^2 in registers across
+        // ALL tiles of the current n-tile; fp64 atomics only when the n-tile changes or the kernel ends.
         const int q = warp & 3;            // TMEM sub-partition of this warp
         const int row = q * 32 + lane;     // accumulator row == pixel within the tile
-        const int ep_tid = threadIdx.x - 64;
+        const int half = (warp - 2) >> 2;
+        const int ep_tid = threadIdx.x - 64 - half * 128;   // thread index inside the half (0 = its TMA thread)
         const int th = row / p.TW;
         const int tw = row - th * p.TW;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int nt = tile % p.n_tiles;
-            const int mt = tile / p.n_tiles;
+        uint32_t res_phase = 0;
+        int tr_t = 0;
+        uint32_t ring = 0;                 // staging position of this half (2 slots, flattened over tiles)
+        uint8_t* const hstage = staging + half * 2 * (128 * 128);
+        float st_s[4], st_q[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
+        const int nt = blockIdx.x % p.n_tiles;
+        for (int mt = blockIdx.x / p.n_tiles; mt < p.m_tiles; mt += groups) {
             const int img = mt / tiles_hw;
             const int rem = mt - img * tiles_hw;
             const int h0 = (rem / p.tiles_w) * p.TH;
@@ -204,50 +239,61 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             int n_valid = p.Cout - n0;
             if (n_valid > 256) n_valid = 256;
             const int nchunks = (n_valid + 31) >> 5;
+            const int nsub = (n_valid + 63) >> 6;
+            const int j_lo = half * 2;
+            const int j_hi = nsub < j_lo + 2 ? nsub : j_lo + 2;   // this half's sub-tiles [j_lo, j_hi)
             const int h = h0 + th, w = w0 + tw;
             const bool valid = (h < p.Ho) && (w < p.Wo);
             const long long pix = (static_cast<long long>(img) * p.Ho + h) * p.Wo + w;
 
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after_sync();
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
-
-            for (int c = 0; c < nchunks; ++c) {
-                uint32_t raw[32];
-                tmem_ld_32x32b_x32(t_addr + c * 32, raw);
-                tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                const int col0 = n0 + c * 32;
-                if (p.scale != nullptr) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (col0 + i < p.Cout) v[i] *= __ldg(p.scale + col0 + i);
-                }
-                if (p.shift != nullptr) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (col0 + i < p.Cout) v[i] += __ldg(p.shift + col0 + i);
-                }
-                if (p.residual != nullptr && valid) {
-                    const __nv_bfloat16* rp = p.residual + pix * p.res_ld + col0;
-#pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8) {
-                        if (col0 + g8 * 8 < p.Cout) {
-                            const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + g8 * 8));
-                            v[g8 * 8 + 0] += bf16_lo(u.x); v[g8 * 8 + 1] += bf16_hi(u.x);
-                            v[g8 * 8 + 2] += bf16_lo(u.y); v[g8 * 8 + 3] += bf16_hi(u.y);
-                            v[g8 * 8 + 4] += bf16_lo(u.z); v[g8 * 8 + 5] += bf16_hi(u.z);
-                            v[g8 * 8 + 6] += bf16_lo(u.w); v[g8 * 8 + 7] += bf16_hi(u.w);
-                        }
+            const bool res_tma = (!p.direct) && (p.residual != nullptr);
+            if (res_tma) {
+                // residual tile -> staging IN PLACE (overlaps the MMA main loop of this tile); the epilogue adds it
+                // at the very positions it overwrites.  All earlier stores must have finished reading the ring.
+                if (ep_tid == 0) {
+                    tma_store_wait_read0();
+                    for (int j = j_lo; j < j_hi; ++j) {
+                        mbar_arrive_expect_tx(&res_bar[j], 128 * 128);
+                        tma_load_4d(hstage + ((ring + j - j_lo) & 1) * (128 * 128), &tmR, &res_bar[j], n0 + j * 64, w0,
+                                    h0, img);
                     }
                 }
-                if (p.relu) {
+            }
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after_sync();
+            if (ep_tid == 0 && half == 0 && tr_t < 16) trace(144 + 4 * tr_t);
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+
+            if (p.direct) {
+                for (int c = half * 4; c < nchunks && c < half * 4 + 4; ++c) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32b_x32(t_addr + c * 32, raw);
+                    tmem_ld_wait();
+                    float v[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                }
-                if (p.direct) {
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                    const int col0 = n0 + c * 32;
+                    if (p.scale != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.Cout) v[i] *= __ldg(p.scale + col0 + i);
+                    }
+                    if (p.shift != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.Cout) v[i] += __ldg(p.shift + col0 + i);
+                    }
+                    if (p.residual != nullptr && valid) {
+                        const __nv_bfloat16* rp = p.residual + pix * p.res_ld + col0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + i < p.Cout) v[i] += __bfloat162float(rp[i]);
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
                     if (valid) {
                         if (p.out_f32) {
                             float* op = reinterpret_cast<float*>(p.out) + pix * p.out_ld + col0;
@@ -261,71 +307,151 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                 if (col0 + i < p.Cout) op[i] = __float2bfloat16_rn(v[i]);
                         }
                     }
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            } else {
+                uint32_t raw0[32], raw1[32];                 // both 32-column chunks of the current sub-tile
+                if (j_lo < j_hi) {
+                    tmem_ld_32x32b_x32(t_addr + j_lo * 64, raw0);
+                    if (j_lo * 2 + 1 < nchunks) tmem_ld_32x32b_x32(t_addr + j_lo * 64 + 32, raw1);
                 } else {
-                    if (!valid) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = 0.f;  // keeps OOB pixels out of the statistics
-                    }
-                    // staging: sub-tile j = c/2 is [128 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
-                    uint8_t* sub = staging + (c >> 1) * (128 * 128) + row * 128;
-#pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8) {
-                        const int chunk = ((c & 1) * 4 + g8) ^ (row & 7);
-                        uint4 u;
-                        u.x = pack_bf16x2(v[g8 * 8 + 0], v[g8 * 8 + 1]);
-                        u.y = pack_bf16x2(v[g8 * 8 + 2], v[g8 * 8 + 3]);
-                        u.z = pack_bf16x2(v[g8 * 8 + 4], v[g8 * 8 + 5]);
-                        u.w = pack_bf16x2(v[g8 * 8 + 6], v[g8 * 8 + 7]);
-                        *reinterpret_cast<uint4*>(sub + chunk * 16) = u;
-                    }
+                    // nothing to drain for this half: still hand the accumulator back
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 }
-            }
-            // accumulator buffer drained -> hand it back to the MMA warp
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-
-            if (!p.direct) {
-                fence_proxy_async_smem();
-                named_bar_sync(1, 128);
-                if (ep_tid == 0) {
-                    const int nsub = (n_valid + 63) >> 6;
-                    for (int j = 0; j < nsub; ++j) tma_store_4d(&tmC, staging + j * (128 * 128), n0 + j * 64, w0, h0, img);
-                    tma_store_commit();
-                }
-                if (p.stats != nullptr) {
-                    // thread t owns columns 2t, 2t+1 of the tile
-                    const int cpair = ep_tid * 2;
-                    if (cpair < n_valid) {
-                        const uint8_t* sub = staging + (cpair >> 6) * (128 * 128);
-                        const int cin = cpair & 63;
-                        const int chunk = cin >> 3;
-                        const int word = (cin & 7) >> 1;
-                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                for (int j = j_lo; j < j_hi; ++j) {
+                    uint8_t* sub = hstage + (ring & 1) * (128 * 128);
+                    if (res_tma) mbar_wait(&res_bar[j], res_phase);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int c = j * 2 + cc;
+                        if (c < nchunks) {
+                            float v[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cc == 0 ? raw0[i] : raw1[i]);
+                            const int col0 = n0 + c * 32;
+                            if (p.scale != nullptr) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    if (col0 + i < p.Cout) v[i] *= __ldg(p.scale + col0 + i);
+                            }
+                            if (p.shift != nullptr) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    if (col0 + i < p.Cout) v[i] += __ldg(p.shift + col0 + i);
+                            }
+                            if (res_tma) {
+#pragma unroll
+                                for (int g8 = 0; g8 < 4; ++g8) {
+                                    const int chunk = (cc * 4 + g8) ^ (row & 7);
+                                    const uint4 u = *reinterpret_cast<const uint4*>(sub + row * 128 + chunk * 16);
+                                    v[g8 * 8 + 0] += bf16_lo(u.x); v[g8 * 8 + 1] += bf16_hi(u.x);
+                                    v[g8 * 8 + 2] += bf16_lo(u.y); v[g8 * 8 + 3] += bf16_hi(u.y);
+                                    v[g8 * 8 + 4] += bf16_lo(u.z); v[g8 * 8 + 5] += bf16_hi(u.z);
+                                    v[g8 * 8 + 6] += bf16_lo(u.w); v[g8 * 8 + 7] += bf16_hi(u.w);
+                                }
+                            }
+                            if (p.relu) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                            }
+                            if (!valid) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = 0.f;  // keeps OOB pixels out of the statistics
+                            }
+#pragma unroll
+                            for (int g8 = 0; g8 < 4; ++g8) {
+                                const int chunk = (cc * 4 + g8) ^ (row & 7);
+                                uint4 u;
+                                u.x = pack_bf16x2(v[g8 * 8 + 0], v[g8 * 8 + 1]);
+                                u.y = pack_bf16x2(v[g8 * 8 + 2], v[g8 * 8 + 3]);
+                                u.z = pack_bf16x2(v[g8 * 8 + 4], v[g8 * 8 + 5]);
+                                u.w = pack_bf16x2(v[g8 * 8 + 6], v[g8 * 8 + 7]);
+                                *reinterpret_cast<uint4*>(sub + row * 128 + chunk * 16) = u;
+                            }
+                        }
+                    }
+                    if (j == j_hi - 1) {
+                        // this warp's share of the accumulator is drained -> hand it back to the MMA warp
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        if (ep_tid == 0 && half == 0 && tr_t < 16) trace(145 + 4 * tr_t);
+                    } else {
+                        // prefetch the next sub-tile's accumulators: the TMEM latency hides behind statistics,
+                        // fence, barrier and the TMA-store issue below
+                        const int c2 = (j + 1) * 2;
+                        tmem_ld_32x32b_x32(t_addr + c2 * 32, raw0);
+                        if (c2 + 1 < nchunks) tmem_ld_32x32b_x32(t_addr + (c2 + 1) * 32, raw1);
+                    }
+                    __syncwarp();
+                    if (p.stats != nullptr) {
+                        // lane owns columns (2*lane, 2*lane+1) of this sub-tile, over the 32 rows its warp staged
+                        const int cin = lane * 2;
+                        if (j * 64 + cin < n_valid) {
+                            const int chunk = cin >> 3;
+                            const int word = (cin & 7) >> 1;
+                            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
-                        for (int r = 0; r < 128; ++r) {
-                            const uint32_t wv =
-                                *reinterpret_cast<const uint32_t*>(sub + r * 128 + ((chunk ^ (r & 7)) << 4) + word * 4);
-                            const float a = bf16_lo(wv), b = bf16_hi(wv);
-                            s0 += a; q0 = fmaf(a, a, q0);
-                            s1 += b; q1 = fmaf(b, b, q1);
-                        }
-                        const int gc = n0 + cpair;
-                        atomicAdd(p.stats + gc, static_cast<double>(s0));
-                        atomicAdd(p.stats + p.Cout + gc, static_cast<double>(q0));
-                        if (cpair + 1 < n_valid) {
-                            atomicAdd(p.stats + gc + 1, static_cast<double>(s1));
-                            atomicAdd(p.stats + p.Cout + gc + 1, static_cast<double>(q1));
+                            for (int r = 0; r < 32; ++r) {
+                                const int rr = q * 32 + r;
+                                const uint32_t wv = *reinterpret_cast<const uint32_t*>(
+                                    sub + rr * 128 + ((chunk ^ (rr & 7)) << 4) + word * 4);
+                                const float a = bf16_lo(wv), b = bf16_hi(wv);
+                                s0 += a; q0 = fmaf(a, a, q0);
+                                s1 += b; q1 = fmaf(b, b, q1);
+                            }
+                            st_s[(j - j_lo) * 2] += s0; st_q[(j - j_lo) * 2] += q0;
+                            st_s[(j - j_lo) * 2 + 1] += s1; st_q[(j - j_lo) * 2 + 1] += q1;
                         }
                     }
+                    fence_proxy_async_smem();
+                    // the OTHER slot of this half was stored one group ago: that store must have finished reading
+                    // shared memory before anybody passes the barrier and overwrites it with the next sub-tile
+                    if (ep_tid == 0) tma_store_wait_read0();
+                    named_bar_sync(1 + half, 128);
+                    if (ep_tid == 0) {
+                        tma_store_4d(&tmC, sub, n0 + j * 64, w0, h0, img);
+                        tma_store_commit();
+                        if (j == 0 && tr_t < 16) trace(146 + 4 * tr_t);
+                    }
+                    ++ring;
                 }
-                if (ep_tid == 0) tma_store_wait_read0();
-                named_bar_sync(1, 128);  // staging may be overwritten by the next tile
+                if (res_tma) res_phase ^= 1;
             }
+            if (ep_tid == 0 && half == 0 && tr_t < 16) trace(147 + 4 * tr_t);
+            ++tr_t;
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
         if (!p.direct && ep_tid == 0) tma_store_wait_all0();
+        if (p.stats != nullptr) {
+            // one flush per kernel: the 4 row-quarters are summed through the now idle staging buffer, then one column
+            // per thread goes out with two fp64 atomics
+            named_bar_sync(3, 256);
+            float* red = reinterpret_cast<float*>(staging);        // [4 quarters][512]: sums 0..255, squares 256..511
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    red[q * 512 + (half * 2 + jj) * 64 + lane * 2 + e] = st_s[jj * 2 + e];
+                    red[q * 512 + 256 + (half * 2 + jj) * 64 + lane * 2 + e] = st_q[jj * 2 + e];
+                }
+            named_bar_sync(3, 256);
+            for (int c = ep_tid + half * 128; c < 256; c += 256) {
+                const int col = nt * 256 + c;
+                if (col < p.Cout) {
+                    const float su = red[c] + red[512 + c] + red[1024 + c] + red[1536 + c];
+                    const float sq = red[256 + c] + red[768 + c] + red[1280 + c] + red[1792 + c];
+                    atomicAdd(p.stats + col, static_cast<double>(su));
+                    atomicAdd(p.stats + p.Cout + col, static_cast<double>(sq));
+                }
+            }
+        }
     }
 
     tc_fence_before_sync();
@@ -422,14 +548,26 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     } else {
         tmC = tmA;  // unused
     }
+    CUtensorMap tmR = tmC;
+    if (!p.direct && L.residual != nullptr) {
+        const uint64_t dims[4] = {(uint64_t)L.Cout, (uint64_t)L.Wo, (uint64_t)L.Ho, (uint64_t)L.N};
+        const uint64_t str[3] = {(uint64_t)L.res_ld * 2, (uint64_t)L.res_ld * 2 * L.Wo,
+                                 (uint64_t)L.res_ld * 2 * L.Wo * L.Ho};
+        const uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        const uint32_t es[4] = {1, 1, 1, 1};
+        if (encode_tmap_4d(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.residual, dims, str, box, es,
+                           CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         GS_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kIgSmemBytes));
         attr_set = true;
     }
-    const int total = p.m_tiles * p.n_tiles;
-    const int grid = total < num_sms() ? total : num_sms();
-    igemm_kernel<<<grid, kIgThreads, kIgSmemBytes, stream>>>(tmA, tmB, tmC, p);
+    GS_REQUIRE(p.n_tiles <= num_sms(), "conv: %d output-channel tiles exceed the SM count", p.n_tiles);
+    int groups = num_sms() / p.n_tiles;
+    if (groups > p.m_tiles) groups = p.m_tiles;
+    const int grid = groups * p.n_tiles;
+    igemm_kernel<<<grid, kIgThreads, kIgSmemBytes, stream>>>(tmA, tmB, tmC, tmR, p);
     GS_LAUNCHED();
     return 0;
 }
@@ -680,6 +818,12 @@ static int check_geom(const gs_conv_geom* g) {
     const int wo = (g->W + 2 * g->pad - g->dil * (g->kw - 1) - 1) / g->stride + 1;
     GS_REQUIRE(ho == g->Ho && wo == g->Wo, "conv: output size (%d,%d) inconsistent with geometry (expect %d,%d)",
                g->Ho, g->Wo, ho, wo);
+    return 0;
+}
+
+extern "C" int gs_debug_set_trace(void* device_buffer_u64x256) {
+    unsigned long long* ptr = reinterpret_cast<unsigned long long*>(device_buffer_u64x256);
+    GS_CUDA_OK(cudaMemcpyToSymbol(gs::g_trace, &ptr, sizeof(ptr)));
     return 0;
 }
 

@@ -42,6 +42,10 @@ int gs_device_check(void);
 int64_t gs_launch_count(void);
 void gs_reset_launch_count(void);
 
+/* Debug: CTA 0 of the conv kernels writes %globaltimer stamps of its pipeline events into a 256-entry device
+ * buffer (NULL disables).  Used by tools/conv_trace.py to attribute time to TMA / MMA / epilogue. */
+int gs_debug_set_trace(void* device_buffer_u64x256);
+
 /* ---- convolution (tcgen05 / TMEM implicit GEMM) ---------------------------------------- */
 /* Geometry of one DynamicConv2d call.
  * replaces: [EXT] gaiavision DynamicConv2d.forward ==
