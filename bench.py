@@ -195,6 +195,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--ncu-cycle', action='store_true')
+    ap.add_argument('--graphs', type=int, default=1, help='CUDA-graph replay for recurring sub-nets (MAX / MIN)')
     ap.add_argument('--host-profile', action='store_true', help='cProfile one cycle -> gpurun_out/hostprof.txt')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -229,15 +230,21 @@ def main():
     metas = [dict(ori_shape=(IMG_H, IMG_W, 3), flip=False)] * BATCH
     it_count = [0]
 
+    graphed = gs.GraphedTrainStep(model, opt, graph_after=2, max_graphs=4) if args.graphs else None
+
     def iteration(img, lab):
         meta = fold_dict(sampler.sample())
         model.manipulate_arch(meta['arch'])
-        out = model.train_step(dict(img=img, img_metas=metas, gt_semantic_seg=lab), opt)
-        opt.zero_grad()
-        out['loss'].backward()
-        w = opt.flat.all_reduce_grads()
-        opt.grad_scale = 1.0 / w
-        opt.step()
+        batch = dict(img=img, img_metas=metas, gt_semantic_seg=lab)
+        if graphed is not None and gs._lib.PROFILE_CALLS is None and Fg.PROFILE is None:
+            out = graphed(json.dumps(meta['arch'], sort_keys=True), batch)
+        else:
+            out = model.train_step(batch, opt)
+            opt.zero_grad()
+            out['loss'].backward()
+            w = opt.flat.all_reduce_grads()
+            opt.grad_scale = 1.0 / w
+            opt.step()
         it_count[0] += 1
         return out
 
@@ -248,14 +255,14 @@ def main():
         return out
 
     def step_e2e():
-        loss = None
+        total = None
         for _ in range(CYCLE):
             himg, hlab = host_batches[it_count[0] % n_dev_batches]
-            img = himg.to(dev, non_blocking=True)
+            img = himg.to(dev, non_blocking=True)      # pinned host memory -> device, every iteration
             lab = hlab.to(dev, non_blocking=True)
             out = iteration(img, lab)
-            loss = out['loss'].item()          # device -> host read of the step result
-        return loss
+            total = out['loss'].detach() if total is None else total + out['loss'].detach()
+        return total.item()                            # device -> host read of the step result (sum of the 4 losses)
 
     def barrier():
         if world > 1:
@@ -320,7 +327,7 @@ def main():
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = imgs_per_step * args.steps / (ms_e2e / 1e3)
     h2d = CYCLE * (BATCH * 3 * IMG_H * IMG_W * 4 + BATCH * IMG_H * IMG_W * 8)
-    d2h = CYCLE * 4
+    d2h = 4
 
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), CUDA events around every launch ----
     roof, breakdown = None, None
@@ -399,6 +406,7 @@ def main():
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': workload_name(args.variant), 'variant': args.variant, 'global_batch': BATCH * world,
                        'images_per_step': imgs_per_step, 'parallelism': f'dp{world}',
+                       'cuda_graphs': 'MAX and MIN iterations replayed as CUDA graphs, random sub-nets eager' if args.graphs else 'off',
                        'l2': 'inputs + activations of every iteration (>1 GB) exceed the 126 MB L2; 4 rotating input batches',
                        'timing': 'CUDA events on the launching stream, barrier+sync both sides, max over ranks'},
             'clocks': clk, 'gpu_launches': launches, 'host_enqueue_ms_per_step': host_enqueue_ms,

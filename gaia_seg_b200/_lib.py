@@ -69,7 +69,7 @@ PROTOTYPES = {
     'gs_upsample_ce_bwd': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _F, _P, _P, _I, _P]),
     'gs_upsample_argmax': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'gs_upsample_bilinear_f32': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
-    'gs_sgd_flat': (_I, [_P, _P, _P, _L, _F, _F, _F, _F, _I, _P, _P]),
+    'gs_sgd_flat': (_I, [_P, _P, _P, _L, _P, _I, _P, _P]),
 }
 
 _lib = None

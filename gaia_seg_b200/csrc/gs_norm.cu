@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
                 double var = t.stats[t.C + c] * t.inv_count - m * m;
                 if (var < 0.0) var = 0.0;
                 const float mf = static_cast<float>(m);
-                const float istd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(t.eps)));
+                const float istd = rsqrtf(static_cast<float>(var) + t.eps);   // fp64 only where cancellation can occur
                 const float g = t.gamma ? __ldg(t.gamma + c) : 1.f;
                 const float b = t.beta ? __ldg(t.beta + c) : 0.f;
                 sc[i] = g * istd;
@@ -247,16 +247,16 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
             load8f(invstd + cv * 8, is);
             if (MASK == 2) { load8f(scale + cv * 8, sc); load8f(shift + cv * 8, sh); }
             long long p = (long long)blockIdx.x * R + ry;
-            for (; p + S < P; p += 2 * S) {
-                uint4 a[2], b[2], c[2];
+            for (; p + 3 * S < P; p += 4 * S) {
+                uint4 a[4], b[4], c[4];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < 4; ++u) {
                     a[u] = ldg_stream(dz + (p + u * S) * dz_ld8 + cv);
                     b[u] = ldg_stream(y + (p + u * S) * y_ld8 + cv);
                     if (HAS_Z) c[u] = ldg_stream(z + (p + u * S) * z_ld8 + cv);
                 }
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < 4; ++u) {
                     float g[8], yy[8], zz[8];
                     unpack8(a[u], g);
                     unpack8(b[u], yy);
@@ -327,7 +327,35 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
                 if (dbeta) dbeta[c] += static_cast<float>(sums[c]);
             }
         }
-        for (long long p = (long long)blockIdx.x * R + ry; p < P; p += S) {
+        long long p = (long long)blockIdx.x * R + ry;
+        for (; p + 3 * S < P; p += 4 * S) {
+            uint4 va[4], vb[4], vc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                va[u] = ldg_stream(dz + (p + u * S) * dz_ld8 + cv);
+                vb[u] = ldg_stream(y + (p + u * S) * y_ld8 + cv);
+                if (HAS_Z) vc[u] = ldg_stream(z + (p + u * S) * z_ld8 + cv);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float g[8], yy[8], zz[8], o[8];
+                unpack8(va[u], g);
+                unpack8(vb[u], yy);
+                if (HAS_Z) unpack8(vc[u], zz);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    bool dead = HAS_Z && !(zz[i] > 0.f);
+                    if (MASK == 2) dead = !(fmaf(yy[i], sc[i], sh[i]) > 0.f);
+                    const float gi = dead ? 0.f : g[i];
+                    g[i] = gi;
+                    const float xh = (yy[i] - mu[i]) * is[i];
+                    o[i] = k0[i] * (gi - k1[i] - xh * k2[i]);
+                }
+                stg_stream(dy + (p + u * S) * dy_ld8 + cv, pack8(o));
+                if (HAS_DRES) stg_stream(dres + (p + u * S) * dres_ld8 + cv, pack8(g));
+            }
+        }
+        for (; p < P; p += S) {
             float g[8], yy[8], zz[8], o[8];
             unpack8(ldg_stream(dz + p * dz_ld8 + cv), g);
             unpack8(ldg_stream(y + p * y_ld8 + cv), yy);
@@ -401,14 +429,13 @@ static int check_act(const void* p, long long ld, int C, const char* what) {
 
 using namespace gs;
 
-static inline int reduce_grid(const ColMap& m, long long P) {
-    // enough blocks for >= 4 per SM when the tensor allows it, at least 4 pixels per thread row
-    long long ppt = P / ((long long)m.R * 148 * 4);
-    if (ppt < 4) ppt = 4;
-    if (ppt > 64) ppt = 64;
-    return colmap_grid(m, P, (int)ppt, 148 * 8);
-}
-
+// Grid policy.  Every block of a REDUCING kernel ends with 2*C same-address fp64 atomics, and the L2 atomic units
+// serialise those (~8-17 ns per op and address, measured): the number of blocks is the dominant cost for these
+// 10-20 us kernels, so reductions use at most 2 blocks per SM with deep unrolling (>= 64 KB of loads in flight per SM).
+// Streaming (apply) kernels use up to 4 blocks per SM and at least 8 pixels per thread row so the per-channel
+// prologue is amortised.
+static inline int reduce_grid(const ColMap& m, long long P) { return colmap_grid(m, P, 8, 148 * 2); }
+static inline int stream_grid(const ColMap& m, long long P) { return colmap_grid(m, P, 8, 148 * 4); }
 
 extern "C" int gs_bn_stats(const void* x, int64_t P, int32_t C, int32_t ld, double* stats, void* stream) {
     if (check_act(x, ld, C, "bn_stats x")) return -1;
@@ -449,7 +476,7 @@ extern "C" int gs_bn_apply(const void* y, int32_t y_ld, const float* scale, cons
     if (residual && check_act(residual, res_ld, C, "bn_apply residual")) return -1;
     if (P <= 0) return 0;
     const ColMap m = make_colmap(C);
-    const int grid = reduce_grid(m, P);
+    const int grid = stream_grid(m, P);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     BnTrainArgs t{};
     if (residual)
@@ -473,7 +500,7 @@ extern "C" int gs_bn_apply_train(const void* y, int32_t y_ld, const double* stat
     GS_REQUIRE(stats && aff && count > 0, "bn_apply_train: null stats / aff or empty count");
     if (P <= 0) return 0;
     const ColMap m = make_colmap(C);
-    const int grid = reduce_grid(m, P);
+    const int grid = stream_grid(m, P);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     BnTrainArgs t{};
     t.stats = stats; t.inv_count = 1.0 / count; t.unbias = count > 1.0 ? count / (count - 1.0) : 1.0;
@@ -529,7 +556,7 @@ extern "C" int gs_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* y, int
     GS_REQUIRE(!relu || z || (scale && shift), "bn_bwd_apply: ReLU mask needs z or (scale, shift)");
     if (P <= 0) return 0;
     const ColMap m = make_colmap(C);
-    const int grid = reduce_grid(m, P);
+    const int grid = stream_grid(m, P);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const double inv_count = 1.0 / count;
     const int mask = !relu ? 0 : (z ? 1 : 2);
@@ -559,7 +586,7 @@ extern "C" int gs_affine_bwd(const void* dz, int32_t dz_ld, const void* z, int32
     if (dres && check_act(dres, dres_ld, C, "affine_bwd dres")) return -1;
     if (P <= 0) return 0;
     const ColMap m = make_colmap(C);
-    const int grid = reduce_grid(m, P);
+    const int grid = stream_grid(m, P);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define GS_AFF_BWD(HZ, HD)                                                                                      \
     affine_bwd_kernel<HZ, HD><<<grid, m.threads, 0, st>>>(                                                      \

@@ -13,8 +13,11 @@
 namespace gs {
 
 __global__ void __launch_bounds__(256) sgd_flat_kernel(float4* __restrict__ p, const float4* __restrict__ g,
-                                                       float4* __restrict__ buf, long long n4, float lr, float mom,
-                                                       float wd, float gscale, int first, uint2* __restrict__ shadow) {
+                                                       float4* __restrict__ buf, long long n4,
+                                                       const float* __restrict__ hyper, int first,
+                                                       uint2* __restrict__ shadow) {
+    // hyper-parameters live in device memory so that a captured CUDA graph of the step follows the LR schedule
+    const float lr = __ldg(hyper), mom = __ldg(hyper + 1), wd = __ldg(hyper + 2), gscale = __ldg(hyper + 3);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
          i += (long long)gridDim.x * blockDim.x) {
         float4 pv = p[i];
@@ -46,9 +49,9 @@ __global__ void __launch_bounds__(256) sgd_flat_kernel(float4* __restrict__ p, c
 
 using namespace gs;
 
-extern "C" int gs_sgd_flat(float* p, const float* g, float* momentum_buf, int64_t n, float lr, float momentum,
-                           float weight_decay, float grad_scale, int32_t first_step, void* shadow_bf16, void* stream) {
-    GS_REQUIRE(p && g && momentum_buf, "sgd_flat: null pointer");
+extern "C" int gs_sgd_flat(float* p, const float* g, float* momentum_buf, int64_t n, const float* hyper,
+                           int32_t first_step, void* shadow_bf16, void* stream) {
+    GS_REQUIRE(p && g && momentum_buf && hyper, "sgd_flat: null pointer");
     GS_REQUIRE(n % 4 == 0, "sgd_flat: n (%lld) must be a multiple of 4 (flat buffers are padded)", (long long)n);
     GS_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
                  reinterpret_cast<uintptr_t>(momentum_buf)) & 15) == 0, "sgd_flat: buffers must be 16-byte aligned");
@@ -58,7 +61,7 @@ extern "C" int gs_sgd_flat(float* p, const float* g, float* momentum_buf, int64_
     if (grid > 148 * 16) grid = 148 * 16;
     sgd_flat_kernel<<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(momentum_buf), n4,
-        lr, momentum, weight_decay, grad_scale, first_step, reinterpret_cast<uint2*>(shadow_bf16));
+        hyper, first_step, reinterpret_cast<uint2*>(shadow_bf16));
     GS_LAUNCHED();
     return 0;
 }

@@ -144,10 +144,40 @@ class _ZeroPool:
 _zero_pool = _ZeroPool()
 
 
+class CaptureArena:
+    """Statistic accumulators of ONE captured CUDA graph: a single buffer inside the graph's memory pool, zeroed by
+    one memset node at the start of the graph (a replay must start from zeros, the wrap-around policy of the eager
+    pool cannot guarantee that)."""
+
+    def __init__(self, device, size=1 << 20):
+        self.buf = torch.zeros(size, dtype=torch.float64, device=device)
+        self.off = 0
+
+    def begin(self):
+        self.buf.zero_()
+        self.off = 0
+
+    def take(self, n):
+        n = (n + 15) // 16 * 16
+        if self.off + n > self.buf.numel():
+            raise GsError('CaptureArena exhausted')
+        out = self.buf[self.off:self.off + n]
+        self.off += n
+        return out
+
+
+_capture_arena = None   # set by runner.GraphedTrainStep while a graph is being captured
+
+
 def zeros_f64(n, device):
+    if _capture_arena is not None:
+        return _capture_arena.take(n)[:n]
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         return torch.zeros(n, dtype=torch.float64, device=device)   # all-reduced buffers: keep them private
     return _zero_pool.take(n, device)[:n]
+
+
+_touched_bns = None     # list collecting the BN modules whose running stats a captured graph updates
 
 
 # ------------------------------------------------------------------------------------------------
@@ -378,6 +408,8 @@ def bn_train_apply(bn, y, stats, C, residual=None, relu=False):
          1 if relu else 0, z.data_ptr(), C, _pixels(y), C, _stream())
     if upd:
         bn._gs_nbt_pending = getattr(bn, '_gs_nbt_pending', 0) + 1
+        if _touched_bns is not None:
+            _touched_bns.append(bn)
     return z, aff, count
 
 

@@ -218,17 +218,31 @@ class GsSGD(torch.optim.Optimizer):
         self.momentum_buf = torch.zeros_like(self.flat.flat_p)
         self.grad_scale = grad_scale
         self._steps = 0
+        self._hyper_dev = torch.zeros(4, dtype=torch.float32, device=self.flat.flat_p.device)
+        self._hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self._hyper_last = None
+
+    def sync_hyper(self):
+        """Push {lr, momentum, weight_decay, grad_scale} to the device (only when they changed).  Called by step();
+        a graph-replaying caller calls it BEFORE the replay, outside the captured region."""
+        g = self.param_groups[0]
+        cur = (float(g['lr']), float(g['momentum']), float(g['weight_decay']), float(self.grad_scale))
+        if cur != self._hyper_last:
+            for i, v in enumerate(cur):
+                self._hyper_host[i] = v
+            self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+            self._hyper_last = cur
 
     def zero_grad(self, set_to_none=False):
         self.flat.zero_grad()
 
     @torch.no_grad()
     def step(self, closure=None):
-        g = self.param_groups[0]
         f = self.flat
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_hyper()
         call('gs_sgd_flat', f.flat_p.data_ptr(), f.flat_g.data_ptr(), self.momentum_buf.data_ptr(), f.total,
-             float(g['lr']), float(g['momentum']), float(g['weight_decay']), float(self.grad_scale),
-             1 if self._steps == 0 else 0, f.flat_shadow.data_ptr(), F_gs._stream())
+             self._hyper_dev.data_ptr(), 1 if self._steps == 0 else 0, f.flat_shadow.data_ptr(), F_gs._stream())
         for m in f.image_convs:
             F_gs.refresh_image_shadow(m)
         self._steps += 1
@@ -242,6 +256,97 @@ class GsSGD(torch.optim.Optimizer):
         self._steps = sd['steps']
         for g, s in zip(self.param_groups, sd['param_groups']):
             g.update(s)
+
+
+class GraphedTrainStep:
+    """One whole training iteration -- forward, fused loss, backward, gradient all-reduce, fused SGD -- replayed as
+    a CUDA graph for sub-nets that recur (the anchors of the sampler: MAX / MIN of the sandwich rule, the single arch
+    of finetune_supernet).  A MAX iteration is ~1500 kernel launches; replaying them costs one graph launch instead
+    of ~25 ms of Python.  Sub-nets seen fewer than `graph_after` times run eagerly (random sub-nets never repeat:
+    85 293 of them), and at most `max_graphs` graphs are kept (each owns the activation memory of its sub-net).
+
+    The graph bakes in pointers, shapes and the sub-net; everything that varies per iteration lives in device
+    memory: the input batch (static buffers), the SGD hyper-parameters (GsSGD._hyper_dev) and dropout's Philox
+    offsets (torch's graph-safe generator)."""
+
+    def __init__(self, model, optimizer, graph_after=2, max_graphs=6):
+        self.model, self.opt = model, optimizer
+        self.graph_after, self.max_graphs = graph_after, max_graphs
+        self.seen, self.graphs = {}, OrderedDict()
+
+    def _module(self):
+        return self.model.module if hasattr(self.model, 'module') else self.model
+
+    def _eager(self, batch):
+        out = self.model.train_step(batch, self.opt)
+        self.opt.zero_grad()
+        out['loss'].backward()
+        w = self.opt.flat.all_reduce_grads()
+        self.opt.grad_scale = 1.0 / w
+        self.opt.step()
+        return out
+
+    def __call__(self, arch_key, batch):
+        """arch_key: hashable id of the currently applied sub-net (e.g. json.dumps(meta['arch'], sort_keys=True))."""
+        img, gt = batch['img'], batch['gt_semantic_seg']
+        key = (arch_key, tuple(img.shape), tuple(gt.shape), self._module().training)
+        n = self.seen.get(key, 0) + 1
+        self.seen[key] = n
+        entry = self.graphs.get(key)
+        if entry is None:
+            if n <= self.graph_after:
+                return self._eager(batch)
+            entry = self._capture(key, batch)
+        else:
+            self.graphs.move_to_end(key)
+        entry['img'].copy_(img, non_blocking=True)
+        entry['gt'].copy_(gt, non_blocking=True)
+        w = 1
+        if dist.is_available() and dist.is_initialized():
+            w = dist.get_world_size()
+        self.opt.grad_scale = 1.0 / w
+        self.opt.sync_hyper()
+        entry['graph'].replay()
+        self.opt._steps += 1
+        for bn in entry['bns']:
+            bn._gs_nbt_pending = getattr(bn, '_gs_nbt_pending', 0) + 1
+        out = dict(entry['out'])
+        lv = out.get('log_vars')
+        if lv is not None and hasattr(lv, 'fresh'):
+            out['log_vars'] = lv.fresh()      # same device tensor, values of THIS replay
+        return out
+
+    def _capture(self, key, batch):
+        while len(self.graphs) >= self.max_graphs:
+            self.graphs.popitem(last=False)
+        dev = batch['img'].device
+        entry = dict(img=batch['img'].clone(), gt=batch['gt_semantic_seg'].clone())
+        static = dict(batch, img=entry['img'], gt_semantic_seg=entry['gt'])
+        w = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.opt.grad_scale = 1.0 / w
+        self.opt.sync_hyper()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        steps0 = self.opt._steps
+        F_gs._touched_bns = []
+        try:
+            with torch.cuda.graph(graph):
+                F_gs._capture_arena = F_gs.CaptureArena(dev)
+                F_gs._capture_arena.begin()
+                out = self.model.train_step(static, self.opt)
+                self.opt.zero_grad()
+                out['loss'].backward()
+                self.opt.flat.all_reduce_grads()
+                self.opt.step()
+        finally:
+            arena, F_gs._capture_arena = F_gs._capture_arena, None
+            bns, F_gs._touched_bns = F_gs._touched_bns, None
+        self.opt._steps = steps0            # capturing enqueued nothing; the replay below is the real iteration
+        for bn in bns:
+            bn._gs_nbt_pending -= 1
+        entry.update(graph=graph, out=out, bns=bns, arena=arena)
+        self.graphs[key] = entry
+        return entry
 
 
 def build_optimizer(model, cfg):

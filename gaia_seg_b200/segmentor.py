@@ -46,6 +46,10 @@ class LogVars(OrderedDict):
         self._stacked = stacked
         self._done = False
 
+    def fresh(self):
+        """A new view of the same device tensor (used after a CUDA-graph replay refreshed its values)."""
+        return LogVars(list(super().keys()), self._stacked)
+
     def _materialise(self):
         if not self._done:
             vals = self._stacked.tolist()

@@ -228,12 +228,14 @@ int gs_upsample_bilinear_f32(const float* src, int32_t N, int32_t h, int32_t w, 
 
 /* ---- optimizer ---------------------------------------------------------- */
 /* SGD(momentum, weight decay) over the FLAT fp32 master buffer (all parameters back to back, each padded
- * to a multiple of 64 elements) + refresh of the flat bf16 forward shadow at the same indices:
- *   g' = grad_scale*g + wd*p ; buf = mom*buf + g' (buf = g' on the first step) ; p -= lr*buf ;
- *   shadow = bf16(p)
+ * to a multiple of 64 elements) + refresh of the flat bf16 shadow at the same indices:
+ *   g' = grad_scale*g + wd*p ; buf = mom*buf + g' (buf = g' on the first step) ; p -= lr*buf ; shadow = bf16(p)
+ * hyper = DEVICE pointer to {lr, momentum, weight_decay, grad_scale} (fp32), so a captured CUDA graph of the
+ * training step follows the LR schedule.
  * replaces torch.optim.SGD.step (configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:175-178) */
-int gs_sgd_flat(float* p, const float* g, float* momentum_buf, int64_t n, float lr, float momentum,
-                float weight_decay, float grad_scale, int32_t first_step, void* shadow_bf16, void* stream);
+int gs_sgd_flat(float* p, const float* g, float* momentum_buf, int64_t n, const float* hyper, int32_t first_step,
+                void* shadow_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,38 @@ def test_segmentor_train_and_eval_parity(gs):
     _assert_all(C.model_checks(gs))
 
 
+def test_cuda_graph_replay_matches_eager(gs):
+    """GraphedTrainStep (capture on the 3rd occurrence of a sub-net, replay afterwards) must train like the eager
+    loop: same loss sequence (fp32 atomics make the two runs differ only at rounding level)."""
+    import json
+    cfg = C.small_cfg(aux=True)
+    losses = {}
+    for mode in ('eager', 'graph'):
+        om, gm, _ = C.build_pair(gs, cfg, seed=1)
+        opt = gs.GsSGD(gm, lr=0.05, momentum=0.9, weight_decay=5e-4)
+        stepper = gs.GraphedTrainStep(gm, opt, graph_after=2, max_graphs=2 if mode == 'graph' else 0)
+        if mode == 'eager':
+            stepper.graph_after = 10 ** 9
+        gm.train()
+        seq = []
+        for it in range(10):
+            name = ('max', 'min')[it % 2]
+            gm.manipulate_arch(C.SMALL_ARCHS[name])
+            g = torch.Generator().manual_seed(100 + it)
+            img = C.bf16r(torch.randn(2, 3, 64, 96, generator=g)).cuda()
+            lab = C._labels(g, 2, 19, 64, 96).cuda()
+            opt.param_groups[0]['lr'] = 0.05 * (1 - it / 10) ** 0.9          # LR schedule must reach the replay
+            out = stepper(json.dumps(C.SMALL_ARCHS[name], sort_keys=True),
+                          dict(img=img, img_metas=[{}, {}], gt_semantic_seg=lab))
+            seq.append(float(out['log_vars']['loss']))
+        losses[mode] = seq
+        if mode == 'graph':
+            assert len(stepper.graphs) == 2
+    for a, b in zip(losses['eager'], losses['graph']):
+        assert abs(a - b) <= 5e-3 * abs(a), (losses['eager'], losses['graph'])
+    assert losses['eager'][-1] < losses['eager'][0]          # and it actually trains
+
+
 def test_no_cpu_fallback(gs):
     conv = gs.DynamicConv2d(16, 16, 1)
     with pytest.raises(gs.GsError):
