@@ -230,7 +230,10 @@ def main():
     metas = [dict(ori_shape=(IMG_H, IMG_W, 3), flip=False)] * BATCH
     it_count = [0]
 
-    graphed = gs.GraphedTrainStep(model, opt, graph_after=2, max_graphs=4) if args.graphs else None
+    # with several ranks the graph holds forward + backward (incl. the peer-memory SyncBN exchanges); the NCCL gradient
+    # all-reduce and the optimizer launch stay eager
+    use_graphs = bool(args.graphs)
+    graphed = gs.GraphedTrainStep(model, opt, graph_after=2, max_graphs=4) if use_graphs else None
 
     def iteration(img, lab):
         meta = fold_dict(sampler.sample())
@@ -406,7 +409,7 @@ def main():
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': workload_name(args.variant), 'variant': args.variant, 'global_batch': BATCH * world,
                        'images_per_step': imgs_per_step, 'parallelism': f'dp{world}',
-                       'cuda_graphs': 'MAX and MIN iterations replayed as CUDA graphs, random sub-nets eager' if args.graphs else 'off',
+                       'cuda_graphs': 'MAX and MIN iterations replayed as CUDA graphs, random sub-nets eager' if use_graphs else 'off',
                        'l2': 'inputs + activations of every iteration (>1 GB) exceed the 126 MB L2; 4 rotating input batches',
                        'timing': 'CUDA events on the launching stream, barrier+sync both sides, max over ranks'},
             'clocks': clk, 'gpu_launches': launches, 'host_enqueue_ms_per_step': host_enqueue_ms,

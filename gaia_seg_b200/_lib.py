@@ -69,6 +69,12 @@ PROTOTYPES = {
     'gs_upsample_ce_bwd': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _F, _P, _P, _I, _P]),
     'gs_upsample_argmax': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'gs_upsample_bilinear_f32': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
+    'gs_comm_inbox_bytes': (_L, [_I]),
+    'gs_ipc_alloc': (_I, [_L, _P, _P]),
+    'gs_ipc_open': (_I, [_P, _P]),
+    'gs_ipc_close': (_I, [_P]),
+    'gs_ipc_free': (_I, [_P]),
+    'gs_syncbn_allreduce': (_I, [_P, _I, _P, _I, _I, _P, _P]),
     'gs_sgd_flat': (_I, [_P, _P, _P, _L, _P, _I, _P, _P]),
 }
 
@@ -128,11 +134,11 @@ def call(name, *args):
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        rc = getattr(_lib, name)(*args)
+        rc = getattr(load(), name)(*args)
         e1.record()
         PROFILE_CALLS.append((name, e0, e1))
     else:
-        rc = getattr(_lib, name)(*args)
+        rc = getattr(_lib or load(), name)(*args)
     if rc != 0:
         raise GsError(f'{name} failed ({rc}): {last_error()}')
 

@@ -172,8 +172,8 @@ _capture_arena = None   # set by runner.GraphedTrainStep while a graph is being 
 def zeros_f64(n, device):
     if _capture_arena is not None:
         return _capture_arena.take(n)[:n]
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        return torch.zeros(n, dtype=torch.float64, device=device)   # all-reduced buffers: keep them private
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and not PeerExchange.get():
+        return torch.zeros(n, dtype=torch.float64, device=device)   # NCCL-reduced buffers: keep them private
     return _zero_pool.take(n, device)[:n]
 
 
@@ -376,6 +376,69 @@ def bn_batch_mode(bn):
     return bn.training or not bn.track_running_stats or bn.running_mean is None
 
 
+class PeerExchange:
+    """NVLink peer-memory all-reduce of the packed SyncBN sums (gs_syncbn_allreduce): one small kernel per layer and
+    direction instead of a host-launched NCCL collective.  Set up once per process group: every rank allocates an
+    IPC-shareable inbox, the 64-byte handles travel through torch.distributed, peers map each other's inbox."""
+    _instances = {}
+
+    def __init__(self, group=None):
+        lib = _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise GsError('PeerExchange: at most 8 ranks (one NVSwitch domain)')
+        nbytes = lib.gs_comm_inbox_bytes(self.world)
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(lib.gs_ipc_alloc(nbytes, ctypes.byref(ptr), handle), 'gs_ipc_alloc')
+        self.own = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.ptrs = (ctypes.c_void_p * 8)()
+        self.opened = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs[r] = self.own
+            else:
+                p = ctypes.c_void_p()
+                _lib.check(lib.gs_ipc_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)), 'gs_ipc_open')
+                self.ptrs[r] = p.value
+                self.opened.append(p.value)
+        self.seq = torch.zeros(1, dtype=torch.int64, device=torch.device('cuda', torch.cuda.current_device()))
+        dist.barrier(group=group)
+
+    def all_reduce(self, stats):
+        call('gs_syncbn_allreduce', stats.data_ptr(), stats.numel(), self.ptrs, self.rank, self.world, self.seq.data_ptr(),
+             _stream())
+
+    @classmethod
+    def get(cls, group=None):
+        key = id(group) if group is not None else 0
+        inst = cls._instances.get(key)
+        if inst is None:
+            if os.environ.get('GS_SYNCBN_PEER', '1') == '0':
+                inst = False
+            else:
+                try:
+                    inst = cls(group)
+                except Exception as e:   # IPC unavailable (e.g. no P2P): fall back to NCCL, loudly
+                    import warnings
+                    warnings.warn(f'gaia_seg_b200: NVLink peer exchange unavailable ({e}); SyncBN falls back to NCCL all_reduce')
+                    inst = False
+            cls._instances[key] = inst
+        return inst
+
+
+def stats_all_reduce(stats, group=None):
+    """Sum the packed fp64 statistics over the SyncBN group (peer-memory kernel, NCCL as fallback)."""
+    ex = PeerExchange.get(group)
+    if ex:
+        ex.all_reduce(stats)
+    else:
+        dist.all_reduce(stats, group=group)
+
+
 def _sync_group(bn):
     """(process_group, world) when `bn` synchronises statistics across ranks, else (None, 1)."""
     if not getattr(bn, 'sync', False) or not dist.is_available() or not dist.is_initialized():
@@ -390,7 +453,7 @@ def bn_train_apply(bn, y, stats, C, residual=None, relu=False):
     shift, running-stat update of the channel prefix) + normalise + residual + ReLU.  Returns (z, aff, count)."""
     pg, world = _sync_group(bn)
     if world > 1:
-        dist.all_reduce(stats, group=pg)
+        stats_all_reduce(stats, pg)
     count = float(_pixels(y)) * world
     aff = torch.empty((4, C), dtype=torch.float32, device=y.device)
     upd = bn.training and bn.track_running_stats and bn.running_mean is not None
@@ -431,7 +494,7 @@ def bn_backward(bn, dz, y, aff, count, zmask, relu, want_dres):
         if gw or gb:   # parameter gradients come from the LOCAL sums (the gradient all-reduce averages them later)
             call('gs_bn_bwd_param', sums.data_ptr(), C, dgam, dbet, 1, st)
         dgam = dbet = None
-        dist.all_reduce(sums, group=pg)
+        stats_all_reduce(sums, pg)
     dy = new_act(N, C, H, W, dev)
     dres = new_act(N, C, H, W, dev) if want_dres else None
     call('gs_bn_bwd_apply', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),

@@ -286,6 +286,12 @@ class GraphedTrainStep:
         self.opt.step()
         return out
 
+    def _graphable(self):
+        """With several ranks the SyncBN exchange must be the capturable peer-memory kernel (not NCCL)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return True
+        return bool(F_gs.PeerExchange.get(None))
+
     def __call__(self, arch_key, batch):
         """arch_key: hashable id of the currently applied sub-net (e.g. json.dumps(meta['arch'], sort_keys=True))."""
         img, gt = batch['img'], batch['gt_semantic_seg']
@@ -294,7 +300,7 @@ class GraphedTrainStep:
         self.seen[key] = n
         entry = self.graphs.get(key)
         if entry is None:
-            if n <= self.graph_after:
+            if n <= self.graph_after or not self._graphable():
                 return self._eager(batch)
             entry = self._capture(key, batch)
         else:
@@ -307,13 +313,22 @@ class GraphedTrainStep:
         self.opt.grad_scale = 1.0 / w
         self.opt.sync_hyper()
         entry['graph'].replay()
-        self.opt._steps += 1
+        if entry['tail_eager']:               # several ranks: NCCL exchanges stay outside the graph
+            self.opt.flat.all_reduce_grads()
+            self.opt.step()
+        else:
+            self.opt._steps += 1
         for bn in entry['bns']:
             bn._gs_nbt_pending = getattr(bn, '_gs_nbt_pending', 0) + 1
         out = dict(entry['out'])
         lv = out.get('log_vars')
         if lv is not None and hasattr(lv, 'fresh'):
-            out['log_vars'] = lv.fresh()      # same device tensor, values of THIS replay
+            if entry['tail_eager']:
+                red = lv._stacked / w
+                dist.all_reduce(red)
+                out['log_vars'] = type(lv)(list(lv.keys()), red)
+            else:
+                out['log_vars'] = lv.fresh()  # same device tensor, values of THIS replay
         return out
 
     def _capture(self, key, batch):
@@ -328,23 +343,30 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         steps0 = self.opt._steps
+        tail_eager = w > 1     # the graph then holds forward + backward (+ the peer-memory SyncBN exchanges) only
+        mod = self._module()
         F_gs._touched_bns = []
         try:
+            if tail_eager:
+                mod.log_vars_reduce = False
             with torch.cuda.graph(graph):
                 F_gs._capture_arena = F_gs.CaptureArena(dev)
                 F_gs._capture_arena.begin()
                 out = self.model.train_step(static, self.opt)
                 self.opt.zero_grad()
                 out['loss'].backward()
-                self.opt.flat.all_reduce_grads()
-                self.opt.step()
+                if not tail_eager:
+                    self.opt.flat.all_reduce_grads()
+                    self.opt.step()
         finally:
             arena, F_gs._capture_arena = F_gs._capture_arena, None
             bns, F_gs._touched_bns = F_gs._touched_bns, None
+            if tail_eager:
+                mod.log_vars_reduce = True
         self.opt._steps = steps0            # capturing enqueued nothing; the replay below is the real iteration
         for bn in bns:
             bn._gs_nbt_pending -= 1
-        entry.update(graph=graph, out=out, bns=bns, arena=arena)
+        entry.update(graph=graph, out=out, bns=bns, arena=arena, tail_eager=tail_eager)
         self.graphs[key] = entry
         return entry
 

@@ -130,8 +130,10 @@ class EncoderDecoder(nn.Module):
                     losses[f'aux.{k}'] = v
         return losses
 
+    log_vars_reduce = True   # GraphedTrainStep turns this off while capturing and reduces after the replay
+
     @staticmethod
-    def _parse_losses(losses):
+    def _parse_losses(losses, reduce=True):
         names, vals = [], []
         for name, value in losses.items():
             if isinstance(value, torch.Tensor):
@@ -146,14 +148,14 @@ class EncoderDecoder(nn.Module):
         names.append('loss')
         vals.append(loss)
         stacked = torch.stack([v.detach().float() for v in vals])
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             stacked = stacked / dist.get_world_size()
             dist.all_reduce(stacked)
         return loss, LogVars(names, stacked)
 
     def train_step(self, data_batch, optimizer=None, **kwargs):
         losses = self(**data_batch)
-        loss, log_vars = self._parse_losses(losses)
+        loss, log_vars = self._parse_losses(losses, self.log_vars_reduce)
         return dict(loss=loss, log_vars=log_vars, num_samples=len(data_batch['img_metas']))
 
     def val_step(self, data_batch, **kwargs):

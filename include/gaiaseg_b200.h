@@ -226,6 +226,21 @@ int gs_upsample_argmax(const float* logits, int32_t N, int32_t h, int32_t w, int
 int gs_upsample_bilinear_f32(const float* src, int32_t N, int32_t h, int32_t w, int32_t K, int32_t ld, float* dst,
                              int32_t H, int32_t W, int32_t dst_ld, void* stream);
 
+/* ---- SyncBN statistic exchange over NVLink peer memory ------------------------------------------- */
+/* replaces the per-layer NCCL collectives of [EXT] torch.nn.SyncBatchNorm under gaiavision DynSyncBN
+ * (configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:20-23).  Every rank allocates an IPC-shareable inbox of
+ * gs_comm_inbox_bytes(world) bytes (gs_ipc_alloc -> 64-byte handle), exchanges the handles out of band
+ * (torch.distributed.all_gather_object) and maps the peers' inboxes (gs_ipc_open).  gs_syncbn_allreduce is ONE kernel:
+ * push the n packed fp64 sums to every inbox (P2P stores), release-flag with a device-resident sequence number,
+ * bounded acquire-spin for all ranks, sum in rank order (bit-identical on every rank), result in place. */
+int64_t gs_comm_inbox_bytes(int32_t world);
+int gs_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle_out_64);
+int gs_ipc_open(const void* handle_64, void** dev_ptr);
+int gs_ipc_close(void* dev_ptr);
+int gs_ipc_free(void* dev_ptr);
+int gs_syncbn_allreduce(double* stats, int32_t n, const void* const* peer_inboxes, int32_t rank, int32_t world,
+                        void* seq_dev, void* stream);
+
 /* ---- optimizer ---------------------------------------------------------- */
 /* SGD(momentum, weight decay) over the FLAT fp32 master buffer (all parameters back to back, each padded
  * to a multiple of 64 elements) + refresh of the flat bf16 shadow at the same indices:
