@@ -194,9 +194,11 @@ def main():
     ap.add_argument('--variant', default='os8', choices=['os8', 'os32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--no-infer', action='store_true')
     ap.add_argument('--ncu-cycle', action='store_true')
     ap.add_argument('--graphs', type=int, default=1, help='CUDA-graph replay for recurring sub-nets (MAX / MIN)')
     ap.add_argument('--host-profile', action='store_true', help='cProfile one cycle -> gpurun_out/hostprof.txt')
+    ap.add_argument('--kineto', action='store_true', help='torch.profiler (CUPTI) kernel times of one cycle -> gpurun_out/kineto_kernels.json')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -298,6 +300,21 @@ def main():
         torch.cuda.profiler.stop()
         print(json.dumps({'ncu_cycle': 'done', 'launches_per_cycle': None}))
         return
+    if args.kineto and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step_resident()
+            torch.cuda.synchronize()
+        agg = {}
+        for ev in prof.events():
+            if ev.device_type is not None and 'cuda' in str(ev.device_type).lower():
+                d = agg.setdefault(ev.name.split('(')[0][:90], [0.0, 0])
+                d[0] += ev.device_time_total if hasattr(ev, 'device_time_total') else ev.cuda_time_total
+                d[1] += 1
+        rows = sorted(({'kernel': k, 'ms': v[0] / 1e3, 'launches': v[1]} for k, v in agg.items()), key=lambda r: -r['ms'])
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'kineto_kernels.json'), 'w'), indent=0)
     if args.host_profile and rank == 0:
         import cProfile
         import pstats
@@ -396,6 +413,13 @@ def main():
         breakdown['conv_flops_per_step'] = tot_flops
         breakdown['whole_step_tflops'] = tot_flops / (ms / args.steps * 1e-3) / 1e12
 
+    # ---- second half of the BASELINE metric: sub-net inference imgs/s (config 5: whole-image 1x3x1024x2048, eval-mode
+    # BN folded into the conv epilogue, fused resize+argmax, label map read back to the host), rank 0 only ----
+    infer = None
+    if rank == 0 and not args.no_infer:
+        infer = infer_sweep(gs, model, dev, args.variant)
+        model.train()
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline(args.variant)
@@ -415,10 +439,39 @@ def main():
             'clocks': clk, 'gpu_launches': launches, 'host_enqueue_ms_per_step': host_enqueue_ms,
             'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps},
-            'roofline': roof, 'cpu_baseline': cpu_base, 'breakdown': breakdown}
+            'roofline': roof, 'cpu_baseline': cpu_base, 'subnet_infer': infer, 'breakdown': breakdown}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def infer_sweep(gs, model, dev, variant, n_subnets=6, reps=3):
+    """Per-sub-net whole-image inference throughput: MAX, MIN and random sub-nets (random.Random(0)), input
+    1x3x1024x2048 from pinned host memory, output int64 label map on the host (model(return_loss=False, ...))."""
+    import torch
+    from gaia_seg_b200.model_space import build_model_sampler, fold_dict
+    MAX, MIN, rnd = sampler_cfg(variant)
+    rs = build_model_sampler(dict(rnd, seed=0))
+    metas = [MAX, MIN] + [rs.sample() for _ in range(n_subnets - 2)]
+    g = torch.Generator().manual_seed(7)
+    himg = torch.randn(1, 3, 1024, 2048, generator=g).pin_memory()
+    meta = [[dict(ori_shape=(1024, 2048, 3), flip=False)]]
+    model.eval()
+    per, tot_imgs, tot_s = [], 0, 0.0
+    with torch.no_grad():
+        for m in metas:
+            model.manipulate_arch(fold_dict(m)['arch'])
+            model(return_loss=False, img=[himg.to(dev, non_blocking=True)], img_metas=meta)      # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                out = model(return_loss=False, img=[himg.to(dev, non_blocking=True)], img_metas=meta)
+            dt = time.perf_counter() - t0          # the .cpu() of the label map synchronises every call
+            per.append({'subnet': m.get('name', 'random'), 'imgs_per_s': reps / dt})
+            tot_imgs += reps
+            tot_s += dt
+    return {'value': tot_imgs / tot_s, 'unit': 'imgs/s', 'input': '1x3x1024x2048 whole-image, host->device->host',
+            'n_subnets': len(metas), 'per_subnet': per, 'label_map_shape': list(out[0].shape), 'label_dtype': str(out[0].dtype)}
 
 
 def cpu_baseline(variant):

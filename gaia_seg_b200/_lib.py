@@ -21,6 +21,12 @@ class ConvGeom(Structure):
                                        'stride', 'pad', 'dil', 'x_ld', 'y_ld')]
 
 
+class BnBwdFuse(Structure):
+    """struct gs_bn_bwd_fuse (include/gaiaseg_b200.h)."""
+    _fields_ = [('y', c_void_p), ('y_ld', c_int32), ('z', c_void_p), ('z_ld', c_int32), ('aff', c_void_p),
+                ('relu', c_int32), ('sums', c_void_p)]
+
+
 _P = c_void_p
 _I = c_int32
 _L = c_int64
@@ -38,7 +44,7 @@ PROTOTYPES = {
     'gs_debug_set_trace': (_I, [_P]),
     'gs_conv2d_fwd': (_I, [_G, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     'gs_conv2d_dgrad_workspace_bytes': (_L, [_G]),
-    'gs_conv2d_dgrad': (_I, [_G, _P, _P, _P, _P, _I, _P, _P]),
+    'gs_conv2d_dgrad': (_I, [_G, _P, _P, _P, _P, _I, _P, _P, _P]),
     'gs_conv2d_wgrad': (_I, [_G, _P, _P, _P, _P]),
     'gs_conv2d_fwd_simt': (_I, [_G, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     'gs_conv2d_dgrad_simt': (_I, [_G, _P, _P, _P, _P, _I, _P]),

@@ -98,8 +98,11 @@ class DynamicResLayer(nn.ModuleList, DynamicMixin):
     def forward(self, x):
         if getattr(self, '_deploying', False):
             return self.deploy_forward(x)
-        for i in range(self.depth_state):
-            x = self[i](x)
+        blocks = [self[i] for i in range(self.depth_state)]
+        if all(type(b) is DynamicBottleneck and (b.downsample is None or len(b.downsample) == 2) for b in blocks):
+            return F_gs.res_stage(x, blocks)      # one autograd node per stage (fused BN-backward reductions)
+        for b in blocks:
+            x = b(x)
         return x
 
 

@@ -18,6 +18,7 @@
 //
 // GEMM view (forward):  Y[pix, co] = sum_{r,s,ci} X[pix shifted by (r,s), ci] * W[co, r, s, ci]
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "../../include/gaiaseg_b200.h"
 #include "gs_host.h"
@@ -68,6 +69,15 @@ struct IgemmParams {
     const __nv_bfloat16* residual;
     long long res_ld;
     double* stats;
+    // stats_mode 1: sum / sum^2 of the stored output (DynBN forward statistics)
+    // stats_mode 2: the output is dz of a BN(+ReLU) layer -> sum g, sum g*xhat (BN backward reduction) with
+    //               g = dz * mask, xhat = (y - mean) * invstd; mask = [z > 0] if bwd_z else [fma(y, scale, shift) > 0]
+    int stats_mode;
+    int tw_shift;
+    const __nv_bfloat16* bwd_y; long long bwd_y_ld;
+    const __nv_bfloat16* bwd_z; long long bwd_z_ld;
+    const float* bwd_aff;   // [4][Cout]: mean, invstd, scale, shift
+    int bwd_relu;
 };
 
 __global__ void __launch_bounds__(kIgThreads, 1)
@@ -260,6 +270,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 }
             }
 
+            if (p.stats_mode == 2 && valid) {
+                // pull this tile's y (z) rows towards L2 while the MMA main loop of the tile is still running
+                const char* yp = reinterpret_cast<const char*>(p.bwd_y + pix * p.bwd_y_ld + n0 + half * 128);
+                const int bytes = (n_valid - half * 128) * 2;
+                for (int o = 0; o < bytes && o < 256; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + o));
+                if (p.bwd_relu && p.bwd_z != nullptr) {
+                    const char* zp = reinterpret_cast<const char*>(p.bwd_z + pix * p.bwd_z_ld + n0 + half * 128);
+                    for (int o = 0; o < bytes && o < 256; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(zp + o));
+                }
+            }
+
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after_sync();
             if (ep_tid == 0 && half == 0 && tr_t < 16) trace(144 + 4 * tr_t);
@@ -396,14 +417,57 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             const int chunk = cin >> 3;
                             const int word = (cin & 7) >> 1;
                             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                            if (p.stats_mode == 1) {
 #pragma unroll 8
-                            for (int r = 0; r < 32; ++r) {
-                                const int rr = q * 32 + r;
-                                const uint32_t wv = *reinterpret_cast<const uint32_t*>(
-                                    sub + rr * 128 + ((chunk ^ (rr & 7)) << 4) + word * 4);
-                                const float a = bf16_lo(wv), b = bf16_hi(wv);
-                                s0 += a; q0 = fmaf(a, a, q0);
-                                s1 += b; q1 = fmaf(b, b, q1);
+                                for (int r = 0; r < 32; ++r) {
+                                    const int rr = q * 32 + r;
+                                    const uint32_t wv = *reinterpret_cast<const uint32_t*>(
+                                        sub + rr * 128 + ((chunk ^ (rr & 7)) << 4) + word * 4);
+                                    const float a = bf16_lo(wv), b = bf16_hi(wv);
+                                    s0 += a; q0 = fmaf(a, a, q0);
+                                    s1 += b; q1 = fmaf(b, b, q1);
+                                }
+                            } else {
+                                // BN-backward reduction fused into the dgrad that produced dz (no separate pass over dz)
+                                const int col = n0 + j * 64 + cin;
+                                const float mu0 = __ldg(p.bwd_aff + col), mu1 = __ldg(p.bwd_aff + col + 1);
+                                const float is0 = __ldg(p.bwd_aff + p.Cout + col), is1 = __ldg(p.bwd_aff + p.Cout + col + 1);
+                                const float sc0 = __ldg(p.bwd_aff + 2 * p.Cout + col), sc1 = __ldg(p.bwd_aff + 2 * p.Cout + col + 1);
+                                const float sh0 = __ldg(p.bwd_aff + 3 * p.Cout + col), sh1 = __ldg(p.bwd_aff + 3 * p.Cout + col + 1);
+                                // all 32 row loads of y (and z) are issued back to back (addresses of rows outside the
+                                // image are clamped, their dz is zero) so ONE memory latency is exposed per sub-tile
+                                uint32_t yv[32], zv[32];
+#pragma unroll
+                                for (int r = 0; r < 32; ++r) {
+                                    const int rr = q * 32 + r;
+                                    int hh = h0 + (rr >> p.tw_shift), ww = w0 + (rr & (p.TW - 1));
+                                    hh = hh < p.Ho ? hh : p.Ho - 1;
+                                    ww = ww < p.Wo ? ww : p.Wo - 1;
+                                    const long long px = (static_cast<long long>(img) * p.Ho + hh) * p.Wo + ww;
+                                    yv[r] = __ldg(reinterpret_cast<const uint32_t*>(p.bwd_y + px * p.bwd_y_ld + col));
+                                    if (p.bwd_relu && p.bwd_z != nullptr)
+                                        zv[r] = __ldg(reinterpret_cast<const uint32_t*>(p.bwd_z + px * p.bwd_z_ld + col));
+                                }
+#pragma unroll
+                                for (int r = 0; r < 32; ++r) {
+                                    const int rr = q * 32 + r;
+                                    const uint32_t wv = *reinterpret_cast<const uint32_t*>(
+                                        sub + rr * 128 + ((chunk ^ (rr & 7)) << 4) + word * 4);   // zero for rows outside
+                                    const float y0 = bf16_lo(yv[r]), y1 = bf16_hi(yv[r]);
+                                    bool dead0 = false, dead1 = false;
+                                    if (p.bwd_relu) {
+                                        if (p.bwd_z != nullptr) {
+                                            dead0 = !(bf16_lo(zv[r]) > 0.f);
+                                            dead1 = !(bf16_hi(zv[r]) > 0.f);
+                                        } else {
+                                            dead0 = !(fmaf(y0, sc0, sh0) > 0.f);
+                                            dead1 = !(fmaf(y1, sc1, sh1) > 0.f);
+                                        }
+                                    }
+                                    const float g0 = dead0 ? 0.f : bf16_lo(wv), g1 = dead1 ? 0.f : bf16_hi(wv);
+                                    s0 += g0; q0 = fmaf(g0, (y0 - mu0) * is0, q0);
+                                    s1 += g1; q1 = fmaf(g1, (y1 - mu1) * is1, q1);
+                                }
                             }
                             st_s[(j - j_lo) * 2] += s0; st_q[(j - j_lo) * 2] += q0;
                             st_s[(j - j_lo) * 2 + 1] += s1; st_q[(j - j_lo) * 2 + 1] += q1;
@@ -478,6 +542,7 @@ struct IgemmLaunch {
     int in_mul, base, step;
     void* out; long long out_ld; int out_f32;
     const float* scale; const float* shift; const void* residual; long long res_ld; int relu; double* stats;
+    const gs_bn_bwd_fuse* fuse;   // non-NULL: `stats` receives the BN-backward sums of the layer that produced the conv input
 };
 
 static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
@@ -502,10 +567,21 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     p.scale = L.scale; p.shift = L.shift;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(L.residual); p.res_ld = L.res_ld;
     p.stats = L.stats;
+    p.stats_mode = L.stats ? 1 : 0;
+    for (p.tw_shift = 0; (1 << p.tw_shift) < p.TW; ++p.tw_shift) {}
+    if (L.fuse != nullptr) {
+        GS_REQUIRE(L.fuse->y && L.fuse->aff && L.fuse->sums, "dgrad fuse: null pointer");
+        GS_REQUIRE(L.fuse->y_ld % 8 == 0 && (!L.fuse->z || L.fuse->z_ld % 8 == 0), "dgrad fuse: pitches must be multiples of 8");
+        p.stats = L.fuse->sums;
+        p.stats_mode = 2;
+        p.bwd_y = reinterpret_cast<const __nv_bfloat16*>(L.fuse->y); p.bwd_y_ld = L.fuse->y_ld;
+        p.bwd_z = reinterpret_cast<const __nv_bfloat16*>(L.fuse->z); p.bwd_z_ld = L.fuse->z_ld;
+        p.bwd_aff = L.fuse->aff; p.bwd_relu = L.fuse->relu;
+    }
     const bool tma_store_ok = !L.out_f32 && (L.out_ld % 8 == 0) && (L.Cout % 8 == 0) &&
                               ((reinterpret_cast<uintptr_t>(L.out) & 15) == 0);
     p.direct = tma_store_ok ? 0 : 1;
-    GS_REQUIRE(!(p.direct && L.stats), "conv: statistics need the bf16 TMA-store epilogue (Co %% 8 == 0)");
+    GS_REQUIRE(!(p.direct && (L.stats || L.fuse)), "conv: statistics need the bf16 TMA-store epilogue (Co %% 8 == 0)");
     if (L.residual) {
         GS_REQUIRE(L.res_ld % 8 == 0 && L.Cout % 8 == 0 && (reinterpret_cast<uintptr_t>(L.residual) & 15) == 0,
                    "conv: residual needs Co %% 8 == 0 and 16-byte alignment");
@@ -764,7 +840,8 @@ static int launch_wgrad(const gs_conv_geom* g, const void* x, const void* dy, fl
     p.dw = dw; p.Ci_max = g->Ci_max;
     p.row_stride = static_cast<long long>(g->kh) * g->kw * g->Ci_max;
     const int items = p.co_tiles * p.ci_tiles * g->kh * g->kw;
-    int splitk = (int)gs_ceil_div(2 * num_sms(), items);
+    static const int waves_x2 = getenv("GS_WGRAD_HALF_WAVES") ? atoi(getenv("GS_WGRAD_HALF_WAVES")) : 4;
+    int splitk = (int)gs_ceil_div((long long)waves_x2 * num_sms() / 2, items);
     if (splitk > p.chunks_total) splitk = p.chunks_total;
     if (splitk < 1) splitk = 1;
     // keep at least 8 pixel-chunks (512 pixels) per CTA so the fp32 atomics stay a small tail
@@ -849,7 +926,8 @@ extern "C" int64_t gs_conv2d_dgrad_workspace_bytes(const gs_conv_geom* g) {
 }
 
 extern "C" int gs_conv2d_dgrad(const gs_conv_geom* g, const void* dy, const void* w_krsc, void* dx,
-                               const void* residual, int32_t res_ld, void* workspace, void* stream_) {
+                               const void* residual, int32_t res_ld, void* workspace, const gs_bn_bwd_fuse* fuse,
+                               void* stream_) {
     if (check_geom(g)) return -1;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     IgemmLaunch L{};
@@ -876,6 +954,7 @@ extern "C" int gs_conv2d_dgrad(const gs_conv_geom* g, const void* dy, const void
     L.in_mul = 1; L.base = g->pad; L.step = -g->dil;
     L.out = dx; L.out_ld = g->x_ld; L.out_f32 = 0;
     L.scale = nullptr; L.shift = nullptr; L.residual = residual; L.res_ld = res_ld; L.relu = 0; L.stats = nullptr;
+    L.fuse = fuse;
     return launch_igemm(L, stream);
 }
 

@@ -12,6 +12,8 @@
 #include "gs_host.h"
 #include "gs_vec.cuh"
 
+#include <stdlib.h>
+
 namespace gs {
 
 // ------------------------------------------------------------------------------------------------
@@ -434,8 +436,18 @@ using namespace gs;
 // 10-20 us kernels, so reductions use at most 2 blocks per SM with deep unrolling (>= 64 KB of loads in flight per SM).
 // Streaming (apply) kernels use up to 4 blocks per SM and at least 8 pixels per thread row so the per-channel
 // prologue is amortised.
-static inline int reduce_grid(const ColMap& m, long long P) { return colmap_grid(m, P, 8, 148 * 2); }
-static inline int stream_grid(const ColMap& m, long long P) { return colmap_grid(m, P, 8, 148 * 4); }
+static inline int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+static inline int reduce_grid(const ColMap& m, long long P) {
+    static const int bps = env_int("GS_BN_REDUCE_BLOCKS_PER_SM", 2), ppt = env_int("GS_BN_REDUCE_PPT", 8);
+    return colmap_grid(m, P, ppt, 148 * bps);
+}
+static inline int stream_grid(const ColMap& m, long long P) {
+    static const int bps = env_int("GS_BN_STREAM_BLOCKS_PER_SM", 4), ppt = env_int("GS_BN_STREAM_PPT", 8);
+    return colmap_grid(m, P, ppt, 148 * bps);
+}
 
 extern "C" int gs_bn_stats(const void* x, int64_t P, int32_t C, int32_t ld, double* stats, void* stream) {
     if (check_act(x, ld, C, "bn_stats x")) return -1;

@@ -76,11 +76,24 @@ int gs_conv2d_fwd(const gs_conv_geom* g, const void* x, const void* w_krsc, void
                   const float* shift, const void* residual, int32_t res_ld, int32_t flags, double* stats,
                   void* stream);
 
+/* Optional fusion for gs_conv2d_dgrad: dx is the gradient dz flowing into the BN(+ReLU) layer that PRODUCED the conv
+ * input, so the dgrad epilogue can do that layer's BN-backward reduction while the tile is on chip:
+ *   sums[0:Ci] += sum g, sums[Ci:2Ci] += sum g*xhat,  g = dx * mask, xhat = (y - mean) * invstd,
+ *   mask = none (relu == 0) | [z > 0] (z != NULL) | [fma(y, scale, shift) > 0];  aff = [mean|invstd|scale|shift] ([4][Ci]).
+ * Saves the separate gs_bn_bwd_reduce pass (one read of dz and one launch per layer). */
+typedef struct gs_bn_bwd_fuse {
+    const void* y; int32_t y_ld;     /* bf16 conv output of the producer layer, same pixels / channels as dx */
+    const void* z; int32_t z_ld;     /* bf16 layer output (mask source when a residual was added), or NULL */
+    const float* aff;                /* [4][Ci] */
+    int32_t relu;
+    double* sums;                    /* fp64 [2*Ci], accumulated */
+} gs_bn_bwd_fuse;
+
 /* dx = conv_transpose(dy, w[:Co,:Ci]) (+ residual).  replaces autograd of F.conv2d (cuDNN dgrad).
- * For stride > 1 `workspace` must hold gs_conv2d_dgrad_workspace_bytes(g) bytes. */
+ * For stride > 1 `workspace` must hold gs_conv2d_dgrad_workspace_bytes(g) bytes.  `fuse` may be NULL. */
 int64_t gs_conv2d_dgrad_workspace_bytes(const gs_conv_geom* g);
 int gs_conv2d_dgrad(const gs_conv_geom* g, const void* dy, const void* w_krsc, void* dx, const void* residual,
-                    int32_t res_ld, void* workspace, void* stream);
+                    int32_t res_ld, void* workspace, const gs_bn_bwd_fuse* fuse, void* stream);
 
 /* dw_krsc[:Co, :, :, :Ci] += dy^T * im2col(x).  replaces autograd of F.conv2d (cuDNN wgrad);
  * entries outside the active slice are untouched (they stay zero, as in the reference where the
