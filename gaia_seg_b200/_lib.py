@@ -63,6 +63,9 @@ PROTOTYPES = {
     'gs_maxpool3x3s2_bwd': (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     'gs_adaptive_avgpool_fwd': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     'gs_adaptive_avgpool_bwd': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
+    'gs_upsample_bf16_fwd': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
+    'gs_upsample_bf16_bwd': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
+    'gs_zero_channels': (_I, [_P, _I, _L, _I, _P]),
     'gs_copy_channels': (_I, [_P, _I, _P, _I, _L, _I, _P]),
     'gs_add_channels': (_I, [_P, _I, _P, _I, _L, _I, _P]),
     'gs_nchw_f32_to_nhwc_bf16': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _P]),

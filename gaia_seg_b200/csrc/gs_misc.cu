@@ -336,6 +336,112 @@ __global__ void im2col_image_kernel(const float* __restrict__ img, int N, int C,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// bilinear resize of a bf16 NHWC map (align_corners = False) -- the PPM branches of the PSP head
+// (resize at gaiaseg/models/decode_heads/dynamic_psp_head.py:67-71).  Source maps are tiny (s x s, s <= 6).
+// forward: one thread per (output pixel, 8-channel vector).  backward: gather, one block per (n, source cell).
+// ------------------------------------------------------------------------------------------------
+struct Tap2 {
+    int i0, i1;
+    float l0, l1;
+};
+__device__ __forceinline__ Tap2 src_tap2(float scale, int dst, int in_size) {
+    float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    Tap2 t;
+    t.i0 = static_cast<int>(src);
+    if (t.i0 > in_size - 1) t.i0 = in_size - 1;
+    t.i1 = t.i0 + ((t.i0 < in_size - 1) ? 1 : 0);
+    t.l1 = src - static_cast<float>(t.i0);
+    t.l1 = fminf(fmaxf(t.l1, 0.f), 1.f);
+    t.l0 = 1.f - t.l1;
+    return t;
+}
+
+__global__ void upsample_bf16_fwd_kernel(const uint4* __restrict__ src, long long src_ld8, int N, int h, int w, int C8,
+                                         uint4* __restrict__ dst, long long dst_ld8, int H, int W, float rh, float rw) {
+    const long long total = (long long)N * H * W * C8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % C8);
+        long long t = i / C8;
+        const int x = (int)(t % W); t /= W;
+        const int y = (int)(t % H);
+        const int n = (int)(t / H);
+        const Tap2 ty = src_tap2(rh, y, h), tx = src_tap2(rw, x, w);
+        float a[8], b[8], c[8], d[8], o[8];
+        unpack8(__ldg(src + ((long long)(n * h + ty.i0) * w + tx.i0) * src_ld8 + cv), a);
+        unpack8(__ldg(src + ((long long)(n * h + ty.i0) * w + tx.i1) * src_ld8 + cv), b);
+        unpack8(__ldg(src + ((long long)(n * h + ty.i1) * w + tx.i0) * src_ld8 + cv), c);
+        unpack8(__ldg(src + ((long long)(n * h + ty.i1) * w + tx.i1) * src_ld8 + cv), d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = ty.l0 * (tx.l0 * a[k] + tx.l1 * b[k]) + ty.l1 * (tx.l0 * c[k] + tx.l1 * d[k]);
+        stg_stream(dst + ((long long)(n * H + y) * W + x) * dst_ld8 + cv, pack8(o));
+    }
+}
+
+__global__ void __launch_bounds__(256) upsample_bf16_bwd_kernel(const uint4* __restrict__ ddst, long long ddst_ld8, int H,
+                                                                int W, int C8, uint4* __restrict__ dsrc,
+                                                                long long dsrc_ld8, int h, int w, float rh, float rw) {
+    __shared__ float red[256 * 8];
+    const int cell = blockIdx.x % (h * w);
+    const int n = blockIdx.x / (h * w);
+    const int ci = cell / w, cj = cell % w;
+    const float inv_rh = 1.f / rh, inv_rw = 1.f / rw;
+    int ylo = (int)floorf((ci - 0.5f) * inv_rh - 0.5f) - 1, yhi = (int)ceilf((ci + 1.5f) * inv_rh - 0.5f) + 1;
+    int xlo = (int)floorf((cj - 0.5f) * inv_rw - 0.5f) - 1, xhi = (int)ceilf((cj + 1.5f) * inv_rw - 0.5f) + 1;
+    ylo = ylo < 0 ? 0 : ylo; xlo = xlo < 0 ? 0 : xlo;
+    yhi = yhi > H - 1 ? H - 1 : yhi; xhi = xhi > W - 1 ? W - 1 : xhi;
+    const int bw = xhi - xlo + 1, npx = (yhi - ylo + 1) * bw;
+    const int Vc = C8 < 32 ? C8 : 32;
+    const int R = 256 / Vc;
+    const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
+    for (int cv0 = blockIdx.y * Vc; cv0 < C8; cv0 += gridDim.y * Vc) {
+        const int cv = cv0 + cx;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        if (cv < C8 && ry < R) {
+            for (int q = ry; q < npx; q += R) {
+                const int y = ylo + q / bw, x = xlo + q % bw;
+                const Tap2 ty = src_tap2(rh, y, h), tx = src_tap2(rw, x, w);
+                const float wy = (ty.i0 == ci ? ty.l0 : 0.f) + (ty.i1 == ci ? ty.l1 : 0.f);
+                const float wx = (tx.i0 == cj ? tx.l0 : 0.f) + (tx.i1 == cj ? tx.l1 : 0.f);
+                const float wgt = wy * wx;
+                if (wgt == 0.f) continue;
+                float g[8];
+                unpack8(__ldg(ddst + ((long long)(n * H + y) * W + x) * ddst_ld8 + cv), g);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, g[k], acc[k]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[k];
+        __syncthreads();
+        if (ry == 0 && cv < C8) {
+            float sum[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sum[k] = 0.f;
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sum[k] += red[(r * Vc + cx) * 8 + k];
+            dsrc[((long long)n * h * w + cell) * dsrc_ld8 + cv] = pack8(sum);
+        }
+    }
+}
+
+// zero-fill channels [0, C) of P pixels (the gap of the segmented PSP concat)
+__global__ void zero_channels_kernel(uint4* __restrict__ dst, long long dst_ld8, long long P, int C8) {
+    const long long total = P * C8;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / C8;
+        stg_stream(dst + p * dst_ld8 + (int)(i - p * C8), z);
+    }
+}
+
 static int check_act8(const void* p, long long ld, int C, const char* what) {
     GS_REQUIRE(p != nullptr, "%s: null pointer", what);
     GS_REQUIRE(C > 0 && C % 8 == 0, "%s: channels (%d) must be a positive multiple of 8", what, C);
@@ -396,6 +502,44 @@ extern "C" int gs_adaptive_avgpool_bwd(const void* dy, int32_t dy_ld, int32_t N,
     adaptive_pool_bwd_kernel<<<flat_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const uint4*>(dy), dy_ld / 8, N, H, W, C / 8, S, reinterpret_cast<uint4*>(dx), dx_ld / 8,
         accumulate);
+    GS_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gs_upsample_bf16_fwd(const void* src, int32_t src_ld, int32_t N, int32_t h, int32_t w, int32_t C, void* dst,
+                                    int32_t dst_ld, int32_t H, int32_t W, void* stream) {
+    if (check_act8(src, src_ld, C, "upsample_bf16 src") || check_act8(dst, dst_ld, C, "upsample_bf16 dst")) return -1;
+    const long long total = (long long)N * H * W * (C / 8);
+    if (total <= 0) return 0;
+    const float rh = static_cast<float>(h) / static_cast<float>(H), rw = static_cast<float>(w) / static_cast<float>(W);
+    upsample_bf16_fwd_kernel<<<flat_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint4*>(src), src_ld / 8, N, h, w, C / 8, reinterpret_cast<uint4*>(dst), dst_ld / 8, H, W,
+        rh, rw);
+    GS_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gs_upsample_bf16_bwd(const void* ddst, int32_t ddst_ld, int32_t N, int32_t H, int32_t W, int32_t C,
+                                    void* dsrc, int32_t dsrc_ld, int32_t h, int32_t w, void* stream) {
+    if (check_act8(ddst, ddst_ld, C, "upsample_bf16_bwd ddst") || check_act8(dsrc, dsrc_ld, C, "upsample_bf16_bwd dsrc"))
+        return -1;
+    GS_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0, "upsample_bf16_bwd: bad shape");
+    const float rh = static_cast<float>(h) / static_cast<float>(H), rw = static_cast<float>(w) / static_cast<float>(W);
+    const int C8 = C / 8;
+    const int Vc = C8 < 32 ? C8 : 32;
+    dim3 grid(N * h * w, (C8 + Vc - 1) / Vc);
+    upsample_bf16_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint4*>(ddst), ddst_ld / 8, H, W, C8, reinterpret_cast<uint4*>(dsrc), dsrc_ld / 8, h, w, rh,
+        rw);
+    GS_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gs_zero_channels(void* dst, int32_t dst_ld, int64_t P, int32_t C, void* stream) {
+    if (check_act8(dst, dst_ld, C, "zero_channels dst")) return -1;
+    if (P <= 0) return 0;
+    zero_channels_kernel<<<flat_grid(P * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<uint4*>(dst), dst_ld / 8, P, C / 8);
     GS_LAUNCHED();
     return 0;
 }

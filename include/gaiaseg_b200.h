@@ -187,6 +187,14 @@ int gs_adaptive_avgpool_fwd(const void* x, int32_t N, int32_t H, int32_t W, int3
                             void* y, int32_t y_ld, void* stream);
 int gs_adaptive_avgpool_bwd(const void* dy, int32_t dy_ld, int32_t N, int32_t H, int32_t W, int32_t C, int32_t S,
                             void* dx, int32_t dx_ld, int32_t accumulate, void* stream);
+/* bilinear resize (align_corners = False) of a bf16 NHWC map and its adjoint -- the PPM branches of the PSP head
+ * (resize at gaiaseg/models/decode_heads/dynamic_psp_head.py:67-71); dst may be a channel slice of the concat buffer */
+int gs_upsample_bf16_fwd(const void* src, int32_t src_ld, int32_t N, int32_t h, int32_t w, int32_t C, void* dst,
+                         int32_t dst_ld, int32_t H, int32_t W, void* stream);
+int gs_upsample_bf16_bwd(const void* ddst, int32_t ddst_ld, int32_t N, int32_t H, int32_t W, int32_t C, void* dsrc,
+                         int32_t dsrc_ld, int32_t h, int32_t w, void* stream);
+/* dst[p, 0:C] = 0 (the gap between the backbone feature and the pyramid branches in the segmented PSP concat) */
+int gs_zero_channels(void* dst, int32_t dst_ld, int64_t P, int32_t C, void* stream);
 /* strided 2-D copy of bf16 rows (concat, torch.cat at dynamic_fcn_head.py:133): dst[p, 0:C] = src[p, 0:C] */
 int gs_copy_channels(const void* src, int32_t src_ld, void* dst, int32_t dst_ld, int64_t P, int32_t C, void* stream);
 /* dst[p, 0:C] += src[p, 0:C] (bf16, fp32 math) */

@@ -73,9 +73,10 @@ class DynamicConv2d(nn.Conv2d, DynamicMixin):
         assert 0 < width <= self.out_channels
         self.width_state = width
 
-    def forward(self, x):
+    def forward(self, x, cols=None):
         co, ci = self.width_state, x.size(1)
-        w = self.weight[:co, :ci]
+        # `cols`: explicit input-channel columns (the segmented `channel_record` slice of the PSP bottleneck)
+        w = self.weight[:co, :ci] if cols is None else self.weight[:co][:, cols]
         b = self.bias[:co] if self.bias is not None else None
         if getattr(self, '_deploying', False):
             self.weight = nn.Parameter(w.detach().clone())
@@ -401,6 +402,60 @@ class DynamicFCNHead(nn.Module, DynamicMixin):
         return self.losses(self.forward(inputs), gt_semantic_seg)
 
 
+class DynamicPPM(nn.ModuleList):
+    """gaiaseg/models/decode_heads/dynamic_psp_head.py:25-73."""
+
+    def __init__(self, pool_scales, in_channels, channels, conv_cfg, norm_cfg, act_cfg, align_corners):
+        super().__init__()
+        self.align_corners = align_corners
+        for s in pool_scales:
+            self.append(nn.Sequential(nn.AdaptiveAvgPool2d(s),
+                                      DynamicConvModule(in_channels, channels, 1, conv_cfg=conv_cfg, norm_cfg=norm_cfg,
+                                                        act_cfg=act_cfg)))
+
+    def forward(self, x):
+        return [F.interpolate(ppm(x), size=x.size()[2:], mode='bilinear', align_corners=self.align_corners)
+                for ppm in self]
+
+
+class DynamicPSPHead(DynamicFCNHead):
+    """gaiaseg/models/decode_heads/dynamic_psp_head.py:75-173 + psp_head.py:228-241.  `channel_record` is read as a
+    SEGMENTED input slice: segment k of the concatenated input uses the weight columns starting at the
+    MAX-width offset of segment k; 'prefix' = plain prefix slice of the concatenation."""
+
+    def __init__(self, in_channels, channels, num_classes, pool_scales=(1, 2, 3, 6), dropout_ratio=0.1, conv_cfg=None,
+                 norm_cfg=None, act_cfg=dict(type='ReLU'), in_index=-1,
+                 loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0), ignore_index=255,
+                 align_corners=False, channel_record_mode='segmented', **_ignored):
+        nn.Module.__init__(self)
+        self.in_channels, self.channels, self.num_classes, self.in_index = in_channels, channels, num_classes, in_index
+        self.loss_weight = loss_decode.get('loss_weight', 1.0)
+        self.ignore_index, self.align_corners = ignore_index, align_corners
+        self.channel_record_mode = channel_record_mode
+        self.conv_seg = DynamicConv2d(channels, num_classes, kernel_size=1, padding=0)
+        self.dropout = nn.Dropout2d(dropout_ratio) if dropout_ratio > 0 else None
+        self.psp_modules = DynamicPPM(pool_scales, in_channels, channels, conv_cfg, norm_cfg, act_cfg, align_corners)
+        self.bottleneck = DynamicConvModule(in_channels + len(pool_scales) * channels, channels, 3, padding=1,
+                                            conv_cfg=conv_cfg, norm_cfg=norm_cfg, act_cfg=act_cfg)
+
+    def forward(self, inputs):                                               # psp_head.py:228-241
+        x = inputs[self.in_index]
+        psp_outs = [x] + self.psp_modules(x)
+        channel_record = [t.size(1) for t in psp_outs]
+        cat = torch.cat(psp_outs, dim=1)
+        bt = self.bottleneck
+        if self.channel_record_mode == 'prefix':
+            out = bt(cat)
+        else:
+            conv = bt.conv
+            max_off = [0, self.in_channels] + [self.in_channels + self.channels * i for i in range(1, len(channel_record))]
+            cols = torch.cat([torch.arange(max_off[k], max_off[k] + c) for k, c in enumerate(channel_record)])
+            out = bt.activate(bt.norm(conv(cat, cols)))
+        if self.dropout is not None:
+            out = self.dropout(out)
+        return self.conv_seg(out)
+
+
 class DynamicEncoderDecoder(nn.Module, DynamicMixin):
     """gaiaseg/models/segmentors/dynamic_encoder_decoder.py:8-42 + [EXT] mmseg EncoderDecoder (inference restated
     in-tree at gaiaseg/models/segmentors/dynamic_distiller.py:252-262, 461-521)."""
@@ -451,7 +506,8 @@ class DynamicEncoderDecoder(nn.Module, DynamicMixin):
         return F.softmax(seg_logit, dim=1).argmax(dim=1)
 
 
-_TYPES = dict(DynamicResNet=DynamicResNet, DynamicFCNHead=DynamicFCNHead, DynamicEncoderDecoder=DynamicEncoderDecoder)
+_TYPES = dict(DynamicResNet=DynamicResNet, DynamicFCNHead=DynamicFCNHead, DynamicPSPHead=DynamicPSPHead,
+              DynamicEncoderDecoder=DynamicEncoderDecoder)
 
 
 def _build(cfg):

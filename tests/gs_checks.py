@@ -436,7 +436,7 @@ def argmax_checks(gs):
 # ------------------------------------------------------------------------------------------------
 # model level
 # ------------------------------------------------------------------------------------------------
-def small_cfg(num_classes=19, deep_stem=False, os8=False, aux=False, dropout=0.0, sync=True):
+def small_cfg(num_classes=19, deep_stem=False, os8=False, aux=False, dropout=0.0, sync=True, psp=False):
     norm = dict(type='DynSyncBN' if sync else 'DynBN', requires_grad=True)
     if sync:
         norm['group_size'] = 1
@@ -451,6 +451,11 @@ def small_cfg(num_classes=19, deep_stem=False, os8=False, aux=False, dropout=0.0
                                 num_classes=num_classes, norm_cfg=dict(type='SyncBN', requires_grad=True),
                                 align_corners=False,
                                 loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0)))
+    if psp:   # the reference's in-tree training config: PSP decode head (+ FCN aux head)
+        cfg['decode_head'] = dict(type='DynamicPSPHead', conv_cfg=dict(type='DynConv2d'), in_channels=320, in_index=3,
+                                  channels=64, pool_scales=(1, 2, 3, 6), dropout_ratio=dropout, num_classes=num_classes,
+                                  norm_cfg=dict(type='SyncBN', requires_grad=True), align_corners=False,
+                                  loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0))
     if aux:
         cfg['auxiliary_head'] = dict(type='DynamicFCNHead', conv_cfg=dict(type='DynConv2d'), in_channels=256, in_index=2,
                                      channels=32, num_convs=1, concat_input=False, dropout_ratio=dropout,
@@ -520,7 +525,8 @@ def _oracle_train_pass(cfg, sd0, arch, img, lab, dtype, emulate):
     return float(loss), float(losses['decode.acc_seg']), grads, rmeans
 
 
-def model_checks(gs, variants=(('os32', {}), ('os8_deepstem_aux', dict(deep_stem=True, os8=True, aux=True)))):
+def model_checks(gs, variants=(('os32', {}), ('os8_deepstem_aux', dict(deep_stem=True, os8=True, aux=True)),
+                               ('psp_aux', dict(psp=True, aux=True, os8=True)))):
     """Whole segmentor, same sampled sub-net on both sides.
     vs the fp32 oracle (stated bf16 tolerance; activations are stored in bf16 between layers): loss 2e-2 relative,
        acc_seg within 1 point, eval-mode label maps >= 97 % pixel agreement (disagreements at small margins).
