@@ -225,7 +225,9 @@ def main():
     model.train()
     opt = gs.GsSGD(model, lr=0.01, momentum=0.9, weight_decay=5e-4)
     MAX, MIN, rnd = sampler_cfg(args.variant)
-    sampler = build_model_sampler(sandwich_sampler_cfg(MAX, MIN, rnd, num_random=2, seed=0))  # shared seed: all ranks agree
+    def new_sampler(seed):
+        return build_model_sampler(sandwich_sampler_cfg(MAX, MIN, rnd, num_random=2, seed=seed))
+    sampler_box = [new_sampler(0)]                 # shared seed: all ranks draw the same sub-nets, no broadcast needed
     n_dev_batches = 4
     dev_batches = [synth_batch(rank, i, device=dev) for i in range(n_dev_batches)]
     host_batches = [synth_batch(rank, 100 + i, pin=True) for i in range(n_dev_batches)]
@@ -238,7 +240,7 @@ def main():
     graphed = gs.GraphedTrainStep(model, opt, graph_after=2, max_graphs=4) if use_graphs else None
 
     def iteration(img, lab):
-        meta = fold_dict(sampler.sample())
+        meta = fold_dict(sampler_box[0].sample())
         model.manipulate_arch(meta['arch'])
         batch = dict(img=img, img_metas=metas, gt_semantic_seg=lab)
         if graphed is not None and gs._lib.PROFILE_CALLS is None and Fg.PROFILE is None:
@@ -336,7 +338,12 @@ def main():
     torch.cuda.synchronize()
     gs._lib.reset_launch_count()
     t_w0 = time.time()
+    sampler_box[0] = new_sampler(1)                # the timed loops below all see the SAME sequence of random sub-nets
+    ms0 = torch.cuda.memory_stats(dev)
     ms = timed(step_resident, args.steps)
+    ms1 = torch.cuda.memory_stats(dev)
+    alloc_info = {'cudaMalloc_calls_in_timed_region': ms1.get('num_device_alloc', 0) - ms0.get('num_device_alloc', 0),
+                  'reserved_GB': round(ms1.get('reserved_bytes.all.current', 0) / 2 ** 30, 2)}
     clocks.window(t_w0, time.time())
     launches = gs._lib.launch_count()
     clk = clocks.stop() if rank == 0 else {}
@@ -344,7 +351,9 @@ def main():
     value = imgs_per_step * args.steps / (ms / 1e3)
 
     step_e2e()
+    sampler_box[0] = new_sampler(1)
     ms_e2e = timed(step_e2e, args.steps)
+    sampler_box[0] = new_sampler(1)
     e2e_value = imgs_per_step * args.steps / (ms_e2e / 1e3)
     h2d = CYCLE * (BATCH * 3 * IMG_H * IMG_W * 4 + BATCH * IMG_H * IMG_W * 8)
     d2h = 4
@@ -436,7 +445,7 @@ def main():
                        'cuda_graphs': 'MAX and MIN iterations replayed as CUDA graphs, random sub-nets eager' if use_graphs else 'off',
                        'l2': 'inputs + activations of every iteration (>1 GB) exceed the 126 MB L2; 4 rotating input batches',
                        'timing': 'CUDA events on the launching stream, barrier+sync both sides, max over ranks'},
-            'clocks': clk, 'gpu_launches': launches, 'host_enqueue_ms_per_step': host_enqueue_ms,
+            'clocks': clk, 'gpu_launches': launches, 'allocator': alloc_info, 'host_enqueue_ms_per_step': host_enqueue_ms,
             'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps},
             'roofline': roof, 'cpu_baseline': cpu_base, 'subnet_infer': infer, 'breakdown': breakdown}

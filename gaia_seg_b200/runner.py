@@ -273,6 +273,10 @@ class GraphedTrainStep:
         self.model, self.opt = model, optimizer
         self.graph_after, self.max_graphs = graph_after, max_graphs
         self.seen, self.graphs = {}, OrderedDict()
+        # every iteration (eager, capture, replay) runs on ONE dedicated side stream: a graph may only be captured on a
+        # stream whose tensors carry no dependency on uncaptured work of another stream (autograd would otherwise
+        # insert cross-stream waits during the captured backward: cudaErrorStreamCaptureIsolation)
+        self.stream = None
 
     def _module(self):
         return self.model.module if hasattr(self.model, 'module') else self.model
@@ -294,6 +298,16 @@ class GraphedTrainStep:
 
     def __call__(self, arch_key, batch):
         """arch_key: hashable id of the currently applied sub-net (e.g. json.dumps(meta['arch'], sort_keys=True))."""
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            out = self._run(arch_key, batch)
+        cur.wait_stream(self.stream)
+        return out
+
+    def _run(self, arch_key, batch):
         img, gt = batch['img'], batch['gt_semantic_seg']
         key = (arch_key, tuple(img.shape), tuple(gt.shape), self._module().training)
         n = self.seen.get(key, 0) + 1
@@ -349,7 +363,7 @@ class GraphedTrainStep:
         try:
             if tail_eager:
                 mod.log_vars_reduce = False
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=self.stream):
                 F_gs._capture_arena = F_gs.CaptureArena(dev)
                 F_gs._capture_arena.begin()
                 out = self.model.train_step(static, self.opt)

@@ -86,7 +86,7 @@ def emulate_bf16_storage(om):
     (random labels, train-mode BN) amplifies bf16 storage noise ~100x."""
     hooks = []
     rnd = lambda mod, inp, out: RoundBF16Sym.apply(out)
-    pre = lambda mod, inp: (RoundGradBF16.apply(inp[0]),)
+    pre = lambda mod, inp: (RoundGradBF16.apply(inp[0]),) + tuple(inp[1:])
     for name, m in om.named_modules():
         if isinstance(m, O.DynamicConv2d):
             # every conv's data gradient is stored in bf16; a bottleneck's conv1 dgrad is fused with the residual
