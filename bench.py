@@ -26,6 +26,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# every iteration trains a DIFFERENT sub-net, i.e. a different set of activation sizes: with the default caching
+# allocator that means cudaMalloc / cudaFree (device-synchronising) in the steady state; expandable segments grow in place
+os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'expandable_segments:True')
 
 IMG_H, IMG_W, NUM_CLASSES, BATCH = 512, 1024, 19, 2
 CYCLE = 4  # MAX, MIN, rand, rand

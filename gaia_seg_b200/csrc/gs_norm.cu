@@ -442,7 +442,8 @@ static inline int env_int(const char* name, int dflt) {
 }
 static inline int reduce_grid(const ColMap& m, long long P) {
     static const int bps = env_int("GS_BN_REDUCE_BLOCKS_PER_SM", 2), ppt = env_int("GS_BN_REDUCE_PPT", 8);
-    return colmap_grid(m, P, ppt, 148 * bps);
+    const int per_sm = m.threads <= 192 ? bps + 1 : bps;   // narrow blocks (C8 = 160, 320): keep >= 480 threads per SM
+    return colmap_grid(m, P, ppt, 148 * per_sm);
 }
 static inline int stream_grid(const ColMap& m, long long P) {
     static const int bps = env_int("GS_BN_STREAM_BLOCKS_PER_SM", 4), ppt = env_int("GS_BN_STREAM_PPT", 8);

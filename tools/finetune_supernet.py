@@ -2,6 +2,8 @@
 """finetune_supernet -- the reference's tools/finetune_supernet.py:139-366: for every rule-selected model_meta:
 one-anchor sampler with that single arch -> train_segmentor -> reload latest.pth -> test -> metrics json."""
 import argparse
+import os
+os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'expandable_segments:True')  # sub-net sizes change every iteration
 import json
 import os
 import os.path as osp

@@ -5,6 +5,8 @@ dataset.evaluate, append metric -> dump metrics json.  `caliberate_bn.use_miniba
 statistics (:190-198).  Sub-nets can also be sharded across ranks (--shard-subnets): independent units, no
 communication, the natural multi-GPU mode for a 50-sub-net sweep."""
 import argparse
+import os
+os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'expandable_segments:True')  # sub-net sizes change every iteration
 import json
 import os
 import os.path as osp
