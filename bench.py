@@ -26,9 +26,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# every iteration trains a DIFFERENT sub-net, i.e. a different set of activation sizes: with the default caching
-# allocator that means cudaMalloc / cudaFree (device-synchronising) in the steady state; expandable segments grow in place
-os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'expandable_segments:True')
 
 IMG_H, IMG_W, NUM_CLASSES, BATCH = 512, 1024, 19, 2
 CYCLE = 4  # MAX, MIN, rand, rand
@@ -198,6 +195,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--no-infer', action='store_true')
+    ap.add_argument('--pool-gb', type=float, default=32.0, help='activation pool reserved up front (see runner.reserve_activation_pool)')
     ap.add_argument('--ncu-cycle', action='store_true')
     ap.add_argument('--graphs', type=int, default=1, help='CUDA-graph replay for recurring sub-nets (MAX / MIN)')
     ap.add_argument('--host-profile', action='store_true', help='cProfile one cycle -> gpurun_out/hostprof.txt')
@@ -227,6 +225,8 @@ def main():
     model = gs.build_segmentor(supernet_cfg(args.variant), train_cfg=dict(), test_cfg=dict(mode='whole')).to(dev)
     model.train()
     opt = gs.GsSGD(model, lr=0.01, momentum=0.9, weight_decay=5e-4)
+    if not args.graphs:
+        gs.reserve_activation_pool(args.pool_gb, dev)
     MAX, MIN, rnd = sampler_cfg(args.variant)
     def new_sampler(seed):
         return build_model_sampler(sandwich_sampler_cfg(MAX, MIN, rnd, num_random=2, seed=seed))
@@ -240,7 +240,7 @@ def main():
     # with several ranks the graph holds forward + backward (incl. the peer-memory SyncBN exchanges); the NCCL gradient
     # all-reduce and the optimizer launch stay eager
     use_graphs = bool(args.graphs)
-    graphed = gs.GraphedTrainStep(model, opt, graph_after=2, max_graphs=4) if use_graphs else None
+    graphed = gs.GraphedTrainStep(model, opt, graph_after=2, max_graphs=4, pool_gb=args.pool_gb) if use_graphs else None
 
     def iteration(img, lab):
         meta = fold_dict(sampler_box[0].sample())

@@ -18,7 +18,7 @@ from .segmentor import (SEGMENTORS, DynamicEncoderDecoder, EncoderDecoder, build
 from .model_space import (MODEL_SAMPLERS, ManipulateArchHook, ModelSpaceManager, broadcast_object,
                           build_model_sampler, fold_dict, sandwich_sampler_cfg, unfold_dict)
 from .runner import (Config, FlatParams, GraphedTrainStep, GsDataParallel, GsSGD, IterBasedRunner, build_optimizer, build_runner,
-                     get_dist_info, init_dist, load_checkpoint, save_checkpoint, scatter_batch)
+                     get_dist_info, init_dist, load_checkpoint, reserve_activation_pool, save_checkpoint, scatter_batch)
 from .apis import (DATASETS, CrossArchEvalHook, DistCrossArchEvalHook, SyntheticSegDataset, build_dataloader,
                    build_dataset, multi_gpu_test, set_random_seed, single_gpu_test, train_segmentor)
 

@@ -251,6 +251,8 @@ def train_segmentor(model, train_sampler, val_sampler, dataset, cfg, distributed
                                      drop_last=True) for ds in dataset]
     model = GsDataParallel(model.cuda(), device_ids=[torch.cuda.current_device()], broadcast_buffers=False,
                            find_unused_parameters=cfg.get('find_unused_parameters', True))
+    from .runner import reserve_activation_pool
+    reserve_activation_pool(cfg.get('activation_pool_gb', 32.0))
     _, world_size = get_dist_info()
     lr_scaler_config = cfg.get('lr_scaler', None)
     if lr_scaler_config is not None:

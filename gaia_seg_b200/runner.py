@@ -258,6 +258,20 @@ class GsSGD(torch.optim.Optimizer):
             g.update(s)
 
 
+def reserve_activation_pool(gigabytes=32.0, device=None):
+    """Every iteration trains a DIFFERENT sub-net, i.e. a different set of activation sizes.  With a cold caching
+    allocator each new size class costs a device-synchronising cudaMalloc in the middle of the step (measured: +24 ms per
+    sandwich cycle until the pool has grown).  Allocating one large block up front and releasing it to the cache gives
+    the allocator a single segment it can split for every later request (180 GB of HBM: 32 GB is affordable)."""
+    if gigabytes <= 0:
+        return
+    device = device or torch.device('cuda', torch.cuda.current_device())
+    free, _ = torch.cuda.mem_get_info(device)
+    n = min(int(gigabytes * 2 ** 30), int(free * 0.6))
+    block = torch.empty(n, dtype=torch.uint8, device=device)
+    del block
+
+
 class GraphedTrainStep:
     """One whole training iteration -- forward, fused loss, backward, gradient all-reduce, fused SGD -- replayed as
     a CUDA graph for sub-nets that recur (the anchors of the sampler: MAX / MIN of the sandwich rule, the single arch
@@ -269,8 +283,9 @@ class GraphedTrainStep:
     memory: the input batch (static buffers), the SGD hyper-parameters (GsSGD._hyper_dev) and dropout's Philox
     offsets (torch's graph-safe generator)."""
 
-    def __init__(self, model, optimizer, graph_after=2, max_graphs=6):
+    def __init__(self, model, optimizer, graph_after=2, max_graphs=6, pool_gb=32.0):
         self.model, self.opt = model, optimizer
+        self.pool_gb = pool_gb
         self.graph_after, self.max_graphs = graph_after, max_graphs
         self.seen, self.graphs = {}, OrderedDict()
         # every iteration (eager, capture, replay) runs on ONE dedicated side stream: a graph may only be captured on a
@@ -298,11 +313,14 @@ class GraphedTrainStep:
 
     def __call__(self, arch_key, batch):
         """arch_key: hashable id of the currently applied sub-net (e.g. json.dumps(meta['arch'], sort_keys=True))."""
-        if self.stream is None:
+        first = self.stream is None
+        if first:
             self.stream = torch.cuda.Stream()
         cur = torch.cuda.current_stream()
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
+            if first:
+                reserve_activation_pool(self.pool_gb)     # block pools are per stream: reserve on OUR stream
             out = self._run(arch_key, batch)
         cur.wait_stream(self.stream)
         return out
@@ -381,6 +399,7 @@ class GraphedTrainStep:
         for bn in bns:
             bn._gs_nbt_pending -= 1
         entry.update(graph=graph, out=out, bns=bns, arena=arena, tail_eager=tail_eager)
+        reserve_activation_pool(self.pool_gb)   # torch.cuda.graph() empties the allocator cache before capturing
         self.graphs[key] = entry
         return entry
 

@@ -3,7 +3,6 @@
 one-anchor sampler with that single arch -> train_segmentor -> reload latest.pth -> test -> metrics json."""
 import argparse
 import os
-os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'expandable_segments:True')  # sub-net sizes change every iteration
 import json
 import os
 import os.path as osp

@@ -6,7 +6,6 @@ statistics (:190-198).  Sub-nets can also be sharded across ranks (--shard-subne
 communication, the natural multi-GPU mode for a 50-sub-net sweep."""
 import argparse
 import os
-os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'expandable_segments:True')  # sub-net sizes change every iteration
 import json
 import os
 import os.path as osp

@@ -5,7 +5,6 @@ cfg -> build_segmentor -> build_model_sampler(train_sampler / val_sampler) -> bu
 NameError on `sample_subnet_num` is not reproduced)."""
 import argparse
 import os
-os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'expandable_segments:True')  # sub-net sizes change every iteration
 import os
 import os.path as osp
 import time
