@@ -650,6 +650,119 @@ def stage_checks(gs):
     return out
 
 
+def psp_op_checks(gs):
+    """AdaptiveAvgPool2d(s) and the fused resize-into-concat of the PSP head against F.adaptive_avg_pool2d /
+    F.interpolate + torch.cat, forward and backward (segmented layout: zero gap between feature and branches)."""
+    from gaia_seg_b200.psp_head import AdaptiveAvgPoolFn, PSPCatFn
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    out = []
+    g = torch.Generator().manual_seed(3)
+    x = bf16r(torch.randn(2, 48, 20, 28, generator=g))
+    for S in (1, 2, 3, 6):
+        xo = x.clone().requires_grad_(True)
+        yo = F.adaptive_avg_pool2d(xo, S)
+        dy = bf16r(torch.randn(yo.shape, generator=g))
+        yo.backward(dy)
+        xg = Fg.as_act(x.to(dev)).requires_grad_(True)
+        yg = AdaptiveAvgPoolFn.apply(xg, S)
+        yg.backward(Fg.as_act(dy.to(dev)))
+        torch.cuda.synchronize()
+        out.append(check_bf16(yg.float(), yo, f'adaptive_avgpool[{S}].fwd', 2.0))
+        out.append(check_bf16(xg.grad.float(), xo.grad, f'adaptive_avgpool[{S}].bwd', 2.0))
+    branches = [bf16r(torch.randn(2, 16, s, s, generator=g)) for s in (1, 2, 3, 6)]
+    xo = x.clone().requires_grad_(True)
+    bo = [b.clone().requires_grad_(True) for b in branches]
+    x_slot = 64
+    cat_o = torch.cat([xo, torch.zeros(2, x_slot - 48, 20, 28)] +
+                      [F.interpolate(b, size=(20, 28), mode='bilinear', align_corners=False) for b in bo], dim=1)
+    d = bf16r(torch.randn(cat_o.shape, generator=g))
+    cat_o.backward(d)
+    xg = Fg.as_act(x.to(dev)).requires_grad_(True)
+    bg = [Fg.as_act(b.to(dev)).requires_grad_(True) for b in branches]
+    cat_g = PSPCatFn.apply(x_slot, xg, *bg)
+    cat_g.backward(Fg.as_act(d.to(dev)))
+    torch.cuda.synchronize()
+    out.append(check_bf16(cat_g.float(), cat_o, 'psp_concat.fwd (copy + zero gap + 4 fused resizes)', 2.0))
+    out.append(check_bf16(xg.grad.float(), xo.grad, 'psp_concat.dx', 2.0))
+    for i, (a, b) in enumerate(zip(bg, bo)):
+        out.append(check_bf16(a.grad.float(), b.grad, f'psp_concat.dbranch[{i}] (resize adjoint)', 3.0))
+    return out
+
+
+def full_size_checks(gs):
+    """BASELINE-sized inputs (2 x 3 x 512 x 1024, 19 classes; supernet of bench.py) through properties that do not need
+    a full CPU backward: (1) the fused loss at full size against the oracle loss on the same logits, exact ignored-pixel
+    count; (2) MIN sub-net of the real supernet, train-mode forward + loss against the fp32 oracle (2e-2) and
+    eval-mode label maps (>= 97 %); (3) config 4: the physically EXTRACTED sub-net (deploy) returns bit-identical
+    logits to the supernet with manipulate_arch applied; (4) linearity of the tcgen05 conv at full width
+    (conv(a*x1 + x2) == a*conv(x1) + conv(x2) within bf16 rounding), prefix-slice independence (weights outside the
+    slice do not influence the output: bit-exact)."""
+    import copy
+    import bench as B
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    out = []
+    g = torch.Generator().manual_seed(11)
+    N, K, h, w, H, W = 2, 19, 64, 128, 512, 1024
+    logits = torch.randn(N, K, h, w, generator=g) * 2
+    lab = _labels(g, N, K, H, W)
+    up = F.interpolate(logits, size=(H, W), mode='bilinear', align_corners=False)
+    loss_o = O.cross_entropy(up, lab.squeeze(1), 255)
+    lg = logits.to(dev).contiguous(memory_format=torch.channels_last)
+    loss_g, acc_g, counts = Fg.upsample_ce(lg, lab.to(dev), 255, 1.0)
+    out.append(check_f32(loss_g.reshape(1), loss_o.reshape(1), 'full_size.upsample_ce.loss', 1e-4))
+    out.append(dict(name='full_size.upsample_ce.ignored_count_exact', ok=int(counts[0]) == int((lab == 255).sum()),
+                    err=abs(int(counts[0]) - int((lab == 255).sum())), tol=0))
+    # (2) + (3): the real supernet, MIN sub-net
+    cfg = B.supernet_cfg('os8')
+    cfg['decode_head']['dropout_ratio'] = 0.0
+    om = O.build_segmentor(cfg)
+    randomize(om, 5)
+    gm = gs.build_segmentor(cfg, train_cfg=dict(), test_cfg=dict(mode='whole'))
+    gm.load_state_dict(om.state_dict(), strict=True)
+    gm = gm.cuda()
+    _, MIN, _ = B.sampler_cfg('os8')
+    arch = gs.fold_dict(MIN)['arch']
+    om.manipulate_arch(arch); gm.manipulate_arch(arch)
+    img = bf16r(torch.randn(2, 3, 512, 1024, generator=g))
+    om.train(); gm.train()
+    with torch.no_grad():
+        lo = om.parse_losses(om.forward_train(img, None, lab))
+        res = gm.train_step(dict(img=img.cuda(), img_metas=[{}, {}], gt_semantic_seg=lab.cuda()), None)
+    out.append(check_f32(res['loss'].reshape(1), lo.reshape(1), 'full_size.supernet_MIN.train_loss_vs_fp32_oracle', 2e-2))
+    om.eval(); gm.eval()
+    metas = [[dict(ori_shape=(512, 1024, 3), flip=False)] * 2]
+    with torch.no_grad():
+        pred_o = om.simple_test(img)
+        pred_g = gm(return_loss=False, img=[img.cuda()], img_metas=metas)
+        logits_super = gm.encode_decode_lowres(img.cuda(), metas[0]).clone()
+        sub = copy.deepcopy(gm)
+        sub.deploy()
+        logits_sub = sub.encode_decode_lowres(img.cuda(), metas[0])
+    agree = float((torch.from_numpy(__import__('numpy').stack(pred_g)) == pred_o).float().mean())
+    out.append(dict(name='full_size.supernet_MIN.labelmap_agreement', ok=agree >= 0.97, err=1 - agree, tol=0.03))
+    n_sub, n_sup = sum(p.numel() for p in sub.parameters()), sum(p.numel() for p in gm.parameters())
+    out.append(dict(name='full_size.extracted_subnet_bit_identical_logits', ok=bool(torch.equal(logits_sub, logits_super)) and n_sub < n_sup,
+                    err=float((logits_sub - logits_super).abs().max()), tol=0, params_sub=n_sub, params_super=n_sup))
+    # (4) linearity / slice independence on a full-width layer (stage-3 3x3, dilation 2)
+    conv = gs.DynamicConv2d(320, 320, 3, padding=2, dilation=2, bias=False).to(dev)
+    conv.manipulate_width(256)
+    x1 = Fg.as_act(bf16r(torch.randn(2, 192, 64, 128, generator=g)).to(dev))
+    x2 = Fg.as_act(bf16r(torch.randn(2, 192, 64, 128, generator=g)).to(dev))
+    y1 = Fg.conv_forward(x1, conv, 256)[0].float()
+    y2 = Fg.conv_forward(x2, conv, 256)[0].float()
+    y12 = Fg.conv_forward(Fg.as_act((2.0 * x1.float() + x2.float())), conv, 256)[0].float()
+    out.append(check_bf16(y12, 2.0 * y1 + y2, 'full_size.conv_linearity', 8.0))   # 3 independent bf16 roundings
+    with torch.no_grad():
+        conv.weight[256:] = 7.0          # outside the active [:256, :192] slice
+        conv.weight[:, 192:] = -3.0
+    y1b = Fg.conv_forward(x1, conv, 256)[0].float()
+    out.append(dict(name='full_size.conv_prefix_slice_independence_bit_exact', ok=bool(torch.equal(y1, y1b)),
+                    err=float((y1 - y1b).abs().max()), tol=0))
+    return out
+
+
 def all_checks(gs, with_simt=True):
     res = []
     groups = [('conv_tc', lambda: sum((conv_case_checks(c, gs, 'tc') for c in CONV_CASES), []))]

@@ -48,6 +48,14 @@ def test_res_stage_fwd_bwd(gs):
     _assert_all(C.stage_checks(gs))
 
 
+def test_psp_pool_and_concat_ops(gs):
+    _assert_all(C.psp_op_checks(gs))
+
+
+def test_full_size_properties(gs):
+    _assert_all(C.full_size_checks(gs))
+
+
 def test_maxpool(gs):
     _assert_all(C.maxpool_checks(gs))
 

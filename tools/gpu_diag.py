@@ -20,6 +20,8 @@ GROUPS = {
     'tc_epilogue': ({}, "C.conv_epilogue_checks(gs) + C.image_conv_checks(gs)"),
     'tc_bn': ({}, "C.bn_checks(gs)"),
     'stage_tc': ({}, "C.stage_checks(gs)"),
+    'psp_ops': ({}, "C.psp_op_checks(gs)"),
+    'full_size': ({}, "C.full_size_checks(gs)"),
     'model_tc': ({}, "C.model_checks(gs)"),
 }
 
