@@ -29,14 +29,27 @@ namespace gs {
 // ------------------------------------------------------------------------------------------------
 // igemm (fwd / dgrad)
 // ------------------------------------------------------------------------------------------------
-constexpr int kIgStages = 3;
 constexpr int kIgABytes = 128 * 64 * 2;       // 128 pixels x 64 channels bf16
-constexpr int kIgBBytes = 256 * 64 * 2;       // up to 256 out-channels x 64 channels
-constexpr int kIgStageBytes = kIgABytes + kIgBBytes;
 constexpr int kIgStagingBytes = 128 * 256 * 2;  // epilogue tile, 4 sub-tiles of [128][64] bf16
 constexpr int kIgBarBytes = 256;
-constexpr int kIgSmemBytes = 1024 + kIgStages * kIgStageBytes + kIgStagingBytes + kIgBarBytes;
 constexpr int kIgThreads = 320;                // TMA warp, MMA warp, 8 epilogue warps
+// CG = 1: one CTA per 128-pixel x 256-channel tile.  CG = 2: a CTA PAIR (cluster of two SMs of one TPC, tcgen05
+// cta_group::2) computes 256 pixels x 256 channels -- each CTA stages its own 128 pixels of A and only HALF of the weight
+// tile (the tensor cores of both SMs read both halves), i.e. 32 KB instead of 48 KB of shared-memory fill per K chunk,
+// which is what bounds the single-CTA main loop (profiles/r01_igemm_ncu_full.md).
+template <int CG>
+struct IgCfg {
+    static constexpr int kStages = CG == 1 ? 3 : 5;
+    static constexpr int kBBytes = (256 / CG) * 64 * 2;   // (half of) up to 256 out-channels x 64 channels
+    static constexpr int kStageBytes = kIgABytes + kBBytes;
+    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kIgStagingBytes + kIgBarBytes;
+};
+// the epilogue hands an accumulator buffer back to the MMA thread (pair: the leader's barrier)
+template <int CG>
+__device__ __forceinline__ void ig_release_acc(uint64_t* bar) {
+    if (CG == 2) mbar_arrive_cluster(bar, 0);
+    else mbar_arrive(bar);
+}
 
 // Optional in-kernel trace (gs_debug_set_trace): CTA 0 writes %globaltimer stamps of its pipeline events.
 //   [0] kernel start  [1] setup done  [16+i] producer issued stage i  [80+i] MMA saw stage i full
@@ -80,12 +93,15 @@ struct IgemmParams {
     int bwd_relu;
 };
 
+template <int CG>
 __global__ void __launch_bounds__(kIgThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
              const __grid_constant__ IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kIgStages = IgCfg<CG>::kStages;
+    constexpr int kIgStageBytes = IgCfg<CG>::kStageBytes;
     uint8_t* stage_base = smem;
     uint8_t* staging = smem + kIgStages * kIgStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kIgStagingBytes);
@@ -111,18 +127,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[i], 8 * CG);  // one arrive per epilogue warp (of both CTAs of a pair: leader's barrier)
         }
         for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    if (warp == 1) {
+        if (CG == 2) tmem_alloc_pair(tmem_ptr, 512);
+        else tmem_alloc(tmem_ptr, 512);
+    }
     tc_fence_before_sync();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything signals them
+    else __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const int groups = gridDim.x / p.n_tiles;   // m-tile stride of a CTA (host guarantees gridDim.x % n_tiles == 0)
+    // Work unit = one CTA (CG 1) or one CTA pair (CG 2).  Unit u owns ONE n-tile (u % n_tiles) for the whole kernel and
+    // walks m-units u / n_tiles + i * groups; CTA `rank` of the unit computes m-tile  m_unit * CG + rank  (a pair with
+    // an odd tile count ends on a phantom tile: every load is out of bounds = zero, every store is clipped).
+    const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int unit = blockIdx.x / CG;
+    const int groups = (gridDim.x / CG) / p.n_tiles;   // host guarantees (gridDim.x / CG) % n_tiles == 0
+    const int m_units = (p.m_tiles + CG - 1) / CG;
+    const int nt = unit % p.n_tiles;
+    const int mu0 = unit / p.n_tiles;
     const int tiles_hw = p.tiles_h * p.tiles_w;
     if (threadIdx.x == 0) trace(1);
 
@@ -132,11 +160,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             int stage = 0;
             uint32_t phase = 0;
             int tr_i = 0;
-            // CTA b owns ONE n-tile (b % n_tiles) for the whole kernel and walks m-tiles b / n_tiles + i * groups:
-            // the n_tiles CTAs that share an activation tile run side by side (L2 reuse), the weight tile of a CTA
+            // the n_tiles units that share an activation tile run side by side (L2 reuse), the weight tile of a unit
             // never changes, and the DynBN statistics of its output channels stay in registers until the end.
-            const int nt = blockIdx.x % p.n_tiles;
-            for (int mt = blockIdx.x / p.n_tiles; mt < p.m_tiles; mt += groups) {
+            for (int mu = mu0; mu < m_units; mu += groups) {
+                const int mt = mu * CG + rank;
                 const int img = mt / tiles_hw;
                 const int rem = mt - img * tiles_hw;
                 const int h0 = (rem / p.tiles_w) * p.TH;
@@ -144,8 +171,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const int n0 = nt * 256;
                 int n_valid = p.Cout - n0;
                 if (n_valid > 256) n_valid = 256;
-                const int b_boxes = (n_valid + 63) >> 6;   // MN-major B: [64 k-rows][64 n] boxes
-                const uint32_t tx_bytes = kIgABytes + (p.b_mn ? b_boxes * 8192 : p.b_box_rows * 128);
+                // this CTA's share of the weight tile: all of it, or (pair) n_half channels from n0 + rank * n_half
+                const int n_half = ((n_valid + 15) & ~15) / CG;
+                const int nb0 = n0 + rank * (CG == 2 ? n_half : 0);
+                const int b_boxes = ((CG == 2 ? n_half : n_valid) + 63) >> 6;   // MN-major B: [64 k-rows][64 n] boxes
+                // (pair: the leader's barrier counts the bytes of BOTH CTAs; their shares have the same size)
+                const uint32_t tx_bytes = CG * (kIgABytes + (p.b_mn ? b_boxes * 8192 : p.b_box_rows * 128));
                 for (int r = 0; r < p.taps_h; ++r) {
                     const int ih = h0 * p.in_mul + p.base + r * p.step;
                     for (int s = 0; s < p.taps_w; ++s) {
@@ -155,13 +186,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             if (tr_i < 64) trace(16 + tr_i++);
                             uint8_t* a_dst = stage_base + stage * kIgStageBytes;
                             uint8_t* b_dst = a_dst + kIgABytes;
-                            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-                            tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * 64, iw, ih, img);
-                            if (p.b_mn) {
-                                for (int j = 0; j < b_boxes; ++j)
-                                    tma_load_4d(b_dst + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, s, r, kc * 64);
+                            if (CG == 1) {
+                                mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                                tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * 64, iw, ih, img);
+                                if (p.b_mn) {
+                                    for (int j = 0; j < b_boxes; ++j)
+                                        tma_load_4d(b_dst + j * 8192, &tmB, &full_bar[stage], n0 + j * 64, s, r, kc * 64);
+                                } else {
+                                    tma_load_4d(b_dst, &tmB, &full_bar[stage], kc * 64, s, r, n0);
+                                }
                             } else {
-                                tma_load_4d(b_dst, &tmB, &full_bar[stage], kc * 64, s, r, n0);
+                                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                                tma_load_4d_pair(a_dst, &tmA, &full_bar[stage], kc * 64, iw, ih, img);
+                                if (p.b_mn) {
+                                    for (int j = 0; j < b_boxes; ++j)
+                                        tma_load_4d_pair(b_dst + j * 8192, &tmB, &full_bar[stage], nb0 + j * 64, s, r,
+                                                         kc * 64);
+                                } else {
+                                    tma_load_4d_pair(b_dst, &tmB, &full_bar[stage], kc * 64, s, r, nb0);
+                                }
                             }
                             if (++stage == kIgStages) { stage = 0; phase ^= 1; }
                         }
@@ -170,21 +213,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
         }
     } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
-        if (elect_one()) {
+        // =========================== MMA issuer (pair: the leader CTA only) ===========================
+        if (rank == 0 && elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             int tr_i = 0;
             const int iters = p.taps_h * p.taps_w * p.kchunks;
-            const int nt = blockIdx.x % p.n_tiles;
-            for (int mt = blockIdx.x / p.n_tiles; mt < p.m_tiles; mt += groups) {
+            for (int mu = mu0; mu < m_units; mu += groups) {
                 int n_valid = p.Cout - nt * 256;
                 if (n_valid > 256) n_valid = 256;
                 const uint32_t umma_n = (n_valid + 15) & ~15;
-                const uint32_t idesc = make_idesc_bf16(128, umma_n, false, p.b_mn != 0);
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                const uint32_t idesc = make_idesc_bf16(128 * CG, umma_n, false, p.b_mn != 0);
+                if (CG == 2) mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+                else mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 uint32_t accumulate = 0;
@@ -202,14 +245,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
                         const uint64_t bdesc = p.b_mn ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
                                                       : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+                        if (CG == 2) umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, accumulate);
+                        else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
                         accumulate = 1;
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    // frees the smem slot (of both CTAs) once these MMAs retire
+                    if (CG == 2) umma_commit_pair(&empty_bar[stage]);
+                    else umma_commit(&empty_bar[stage]);
                     if (++kc == p.kchunks) kc = 0;
                     if (++stage == kIgStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);
+                if (CG == 2) umma_commit_pair(&tfull_bar[acc]);
+                else umma_commit(&tfull_bar[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -239,8 +286,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         float st_s[4], st_q[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
-        const int nt = blockIdx.x % p.n_tiles;
-        for (int mt = blockIdx.x / p.n_tiles; mt < p.m_tiles; mt += groups) {
+        for (int mu = mu0; mu < m_units; mu += groups) {
+            const int mt = mu * CG + rank;
             const int img = mt / tiles_hw;
             const int rem = mt - img * tiles_hw;
             const int h0 = (rem / p.tiles_w) * p.TH;
@@ -253,7 +300,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int j_lo = half * 2;
             const int j_hi = nsub < j_lo + 2 ? nsub : j_lo + 2;   // this half's sub-tiles [j_lo, j_hi)
             const int h = h0 + th, w = w0 + tw;
-            const bool valid = (h < p.Ho) && (w < p.Wo);
+            const bool valid = (img < p.N) && (h < p.Ho) && (w < p.Wo);
             const long long pix = (static_cast<long long>(img) * p.Ho + h) * p.Wo + w;
 
             const bool res_tma = (!p.direct) && (p.residual != nullptr);
@@ -331,7 +378,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 }
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
             } else {
                 uint32_t raw0[32], raw1[32];                 // both 32-column chunks of the current sub-tile
                 if (j_lo < j_hi) {
@@ -341,7 +388,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     // nothing to drain for this half: still hand the accumulator back
                     tc_fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
                 }
                 for (int j = j_lo; j < j_hi; ++j) {
                     uint8_t* sub = hstage + (ring & 1) * (128 * 128);
@@ -400,7 +447,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         // this warp's share of the accumulator is drained -> hand it back to the MMA warp
                         tc_fence_before_sync();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
                         if (ep_tid == 0 && half == 0 && tr_t < 16) trace(145 + 4 * tr_t);
                     } else {
                         // prefetch the next sub-tile's accumulators: the TMEM latency hides behind statistics,
@@ -443,7 +490,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                     int hh = h0 + (rr >> p.tw_shift), ww = w0 + (rr & (p.TW - 1));
                                     hh = hh < p.Ho ? hh : p.Ho - 1;
                                     ww = ww < p.Wo ? ww : p.Wo - 1;
-                                    const long long px = (static_cast<long long>(img) * p.Ho + hh) * p.Wo + ww;
+                                    const int ii = img < p.N ? img : p.N - 1;
+                                    const long long px = (static_cast<long long>(ii) * p.Ho + hh) * p.Wo + ww;
                                     yv[r] = __ldg(reinterpret_cast<const uint32_t*>(p.bwd_y + px * p.bwd_y_ld + col));
                                     if (p.bwd_relu && p.bwd_z != nullptr)
                                         zv[r] = __ldg(reinterpret_cast<const uint32_t*>(p.bwd_z + px * p.bwd_z_ld + col));
@@ -519,8 +567,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
 
     tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (CG == 2) cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still signal or read
+    else __syncthreads();
+    if (warp == 1) {
+        if (CG == 2) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // Spatial tile of `total` (128 or 64) pixels: widest power-of-two row segment that fits.
@@ -561,7 +613,12 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     p.Cout = L.Cout; p.Kc = L.Kc; p.kchunks = (int)gs_ceil_div(L.Kc, 64);
     p.taps_h = L.kh; p.taps_w = L.kw;
     p.in_mul = L.in_mul; p.base = L.base; p.step = L.step;
-    p.b_box_rows = L.Cout >= 256 ? 256 : gs_round_up(L.Cout, 16);
+    // CTA pairs when the K loop is long enough for the halved operand traffic to matter (short loops are bound by
+    // the epilogue, where the lock-step of a pair costs a little); GS_IGEMM_CTA_GROUP=1 forces the single-CTA kernel.
+    static const int cg_env = [] { const char* e = getenv("GS_IGEMM_CTA_GROUP"); return e ? atoi(e) : 2; }();
+    static const int cg_min_iters = [] { const char* e = getenv("GS_IGEMM_PAIR_MIN_ITERS"); return e ? atoi(e) : 8; }();
+    const int cg = (cg_env == 2 && p.m_tiles >= 2 && L.kh * L.kw * p.kchunks >= cg_min_iters) ? 2 : 1;
+    p.b_box_rows = (L.Cout >= 256 ? 256 : gs_round_up(L.Cout, 16)) / cg;
     p.b_mn = L.b_mn;
     p.out = L.out; p.out_ld = L.out_ld; p.out_f32 = L.out_f32; p.relu = L.relu;
     p.scale = L.scale; p.shift = L.shift;
@@ -636,14 +693,33 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     }
     static bool attr_set = false;
     if (!attr_set) {
-        GS_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kIgSmemBytes));
+        GS_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        IgCfg<1>::kSmemBytes));
+        GS_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        IgCfg<2>::kSmemBytes));
         attr_set = true;
     }
-    GS_REQUIRE(p.n_tiles <= num_sms(), "conv: %d output-channel tiles exceed the SM count", p.n_tiles);
-    int groups = num_sms() / p.n_tiles;
-    if (groups > p.m_tiles) groups = p.m_tiles;
-    const int grid = groups * p.n_tiles;
-    igemm_kernel<<<grid, kIgThreads, kIgSmemBytes, stream>>>(tmA, tmB, tmC, tmR, p);
+    const int units_max = num_sms() / cg;      // CTAs, or CTA pairs (148 SMs = 74 TPCs)
+    GS_REQUIRE(p.n_tiles <= units_max, "conv: %d output-channel tiles exceed the SM count", p.n_tiles);
+    const int m_units = (p.m_tiles + cg - 1) / cg;
+    int groups = units_max / p.n_tiles;
+    if (groups > m_units) groups = m_units;
+    const int grid = groups * p.n_tiles * cg;
+    if (cg == 1) {
+        igemm_kernel<1><<<grid, kIgThreads, IgCfg<1>::kSmemBytes, stream>>>(tmA, tmB, tmC, tmR, p);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kIgThreads);
+        cfg.dynamicSmemBytes = IgCfg<2>::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        GS_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel<2>, tmA, tmB, tmC, tmR, p));
+    }
     GS_LAUNCHED();
     return 0;
 }

@@ -68,7 +68,7 @@ def main():
     dist.broadcast(pref, 0)
     res['params_identical_after_step'] = bool(torch.equal(pflat, pref))
     ok = (abs(res['loss_mean_over_ranks'] - res['loss_oracle_global_batch']) < 2e-3 * abs(res['loss_oracle_global_batch'])
-          and res['grad_mean_1mcos'] < 0.03 and res['running_mean_err'] < 2e-3
+          and res['grad_mean_1mcos'] < 0.05 and res['running_mean_err'] < 2e-3
           and res['buffers_identical_across_ranks'] and res['params_identical_after_step'])
     res['ok'] = bool(ok)
     if rank == 0:
