@@ -13,6 +13,7 @@ from .core import (CONV_LAYERS, NORM_LAYERS, BatchNorm2d, DynamicBatchNorm2d, Dy
 from .backbone import BACKBONES, DynamicResLayer, DynamicResNet
 from .heads import HEADS, LOSSES, CrossEntropyLoss, DynamicFCNHead, build_loss
 from .psp_head import DynamicPPM, DynamicPSPHead
+from .aspp_head import DynamicASPPHead, DynamicASPPModule
 from .segmentor import (SEGMENTORS, DynamicEncoderDecoder, EncoderDecoder, build_backbone, build_head,
                         build_segmentor)
 from .model_space import (MODEL_SAMPLERS, ManipulateArchHook, ModelSpaceManager, broadcast_object,

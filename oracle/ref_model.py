@@ -456,6 +456,41 @@ class DynamicPSPHead(DynamicFCNHead):
         return self.conv_seg(out)
 
 
+class DynamicASPPHead(DynamicFCNHead):
+    """BASELINE config 3's DeepLabV3 head.  NOT in the reference tree: [EXT] mmseg ASPPHead /
+    ASPPModule (mmseg/models/decode_heads/aspp_head.py) restated with the reference's DynamicConvModule, the way
+    dynamic_psp_head.py:75-147 restates PSPHead:  cat[resize(image_pool(x)), aspp_d(x) for d in dilations] ->
+    3x3 bottleneck -> dropout -> conv_seg; 1x1 conv for dilation 1, else 3x3 with padding = dilation."""
+
+    def __init__(self, in_channels, channels, num_classes, dilations=(1, 6, 12, 18), dropout_ratio=0.1, conv_cfg=None,
+                 norm_cfg=None, act_cfg=dict(type='ReLU'), in_index=-1,
+                 loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0), ignore_index=255,
+                 align_corners=False, **_ignored):
+        nn.Module.__init__(self)
+        self.in_channels, self.channels, self.num_classes, self.in_index = in_channels, channels, num_classes, in_index
+        self.loss_weight = loss_decode.get('loss_weight', 1.0)
+        self.ignore_index, self.align_corners = ignore_index, align_corners
+        self.conv_seg = DynamicConv2d(channels, num_classes, kernel_size=1, padding=0)
+        self.dropout = nn.Dropout2d(dropout_ratio) if dropout_ratio > 0 else None
+        self.image_pool = nn.Sequential(nn.AdaptiveAvgPool2d(1),
+                                        DynamicConvModule(in_channels, channels, 1, conv_cfg=conv_cfg, norm_cfg=norm_cfg,
+                                                          act_cfg=act_cfg))
+        self.aspp_modules = nn.ModuleList(
+            DynamicConvModule(in_channels, channels, 1 if d == 1 else 3, dilation=d, padding=0 if d == 1 else d,
+                              conv_cfg=conv_cfg, norm_cfg=norm_cfg, act_cfg=act_cfg) for d in dilations)
+        self.bottleneck = DynamicConvModule((len(dilations) + 1) * channels, channels, 3, padding=1, conv_cfg=conv_cfg,
+                                            norm_cfg=norm_cfg, act_cfg=act_cfg)
+
+    def forward(self, inputs):
+        x = inputs[self.in_index]
+        outs = [F.interpolate(self.image_pool(x), size=x.size()[2:], mode='bilinear', align_corners=self.align_corners)]
+        outs.extend(m(x) for m in self.aspp_modules)
+        out = self.bottleneck(torch.cat(outs, dim=1))
+        if self.dropout is not None:
+            out = self.dropout(out)
+        return self.conv_seg(out)
+
+
 class DynamicEncoderDecoder(nn.Module, DynamicMixin):
     """gaiaseg/models/segmentors/dynamic_encoder_decoder.py:8-42 + [EXT] mmseg EncoderDecoder (inference restated
     in-tree at gaiaseg/models/segmentors/dynamic_distiller.py:252-262, 461-521)."""
@@ -507,6 +542,7 @@ class DynamicEncoderDecoder(nn.Module, DynamicMixin):
 
 
 _TYPES = dict(DynamicResNet=DynamicResNet, DynamicFCNHead=DynamicFCNHead, DynamicPSPHead=DynamicPSPHead,
+              DynamicASPPHead=DynamicASPPHead,
               DynamicEncoderDecoder=DynamicEncoderDecoder)
 
 

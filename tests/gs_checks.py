@@ -141,6 +141,12 @@ CONV_CASES = [
     ('3x3_ragged',     1, 17, 23, 64, 80, 3, 1, 1, 1, 64, 80),
     ('3x3_s2_ragged',  1, 19, 27, 64, 64, 3, 2, 1, 1, 64, 64),
     ('3x3_bigk',       1, 8, 16, 640, 512, 3, 1, 1, 1, 640, 512),
+    # ASPP branches of BASELINE config 3 (dilations 12 / 24 / 36 on a 64x128 map; prefix slice of a wider weight)
+    ('3x3_dil12',      1, 64, 128, 192, 96, 3, 1, 12, 12, 256, 96),
+    ('3x3_dil24',      1, 64, 128, 128, 64, 3, 1, 24, 24, 128, 64),
+    ('3x3_dil36',      2, 64, 128, 64, 64, 3, 1, 36, 36, 128, 64),
+    # odd number of 128-pixel tiles with a long K loop: the CTA-pair kernel ends on a phantom tile
+    ('3x3_oddtiles',   3, 8, 16, 320, 320, 3, 1, 1, 1, 320, 320),
 ]
 
 
@@ -436,7 +442,7 @@ def argmax_checks(gs):
 # ------------------------------------------------------------------------------------------------
 # model level
 # ------------------------------------------------------------------------------------------------
-def small_cfg(num_classes=19, deep_stem=False, os8=False, aux=False, dropout=0.0, sync=True, psp=False):
+def small_cfg(num_classes=19, deep_stem=False, os8=False, aux=False, dropout=0.0, sync=True, psp=False, aspp=False):
     norm = dict(type='DynSyncBN' if sync else 'DynBN', requires_grad=True)
     if sync:
         norm['group_size'] = 1
@@ -454,6 +460,11 @@ def small_cfg(num_classes=19, deep_stem=False, os8=False, aux=False, dropout=0.0
     if psp:   # the reference's in-tree training config: PSP decode head (+ FCN aux head)
         cfg['decode_head'] = dict(type='DynamicPSPHead', conv_cfg=dict(type='DynConv2d'), in_channels=320, in_index=3,
                                   channels=64, pool_scales=(1, 2, 3, 6), dropout_ratio=dropout, num_classes=num_classes,
+                                  norm_cfg=dict(type='SyncBN', requires_grad=True), align_corners=False,
+                                  loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0))
+    if aspp:  # BASELINE config 3: DeepLabV3 ASPP decode head (small dilations so that the 8x12 map sees every tap)
+        cfg['decode_head'] = dict(type='DynamicASPPHead', conv_cfg=dict(type='DynConv2d'), in_channels=320, in_index=3,
+                                  channels=64, dilations=(1, 2, 3, 5), dropout_ratio=dropout, num_classes=num_classes,
                                   norm_cfg=dict(type='SyncBN', requires_grad=True), align_corners=False,
                                   loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0))
     if aux:
@@ -526,7 +537,8 @@ def _oracle_train_pass(cfg, sd0, arch, img, lab, dtype, emulate):
 
 
 def model_checks(gs, variants=(('os32', {}), ('os8_deepstem_aux', dict(deep_stem=True, os8=True, aux=True)),
-                               ('psp_aux', dict(psp=True, aux=True, os8=True)))):
+                               ('psp_aux', dict(psp=True, aux=True, os8=True)),
+                               ('aspp_os8', dict(aspp=True, os8=True)))):
     """Whole segmentor, same sampled sub-net on both sides.
     vs the fp32 oracle (stated bf16 tolerance; activations are stored in bf16 between layers): loss 2e-2 relative,
        acc_seg within 1 point, eval-mode label maps >= 97 % pixel agreement (disagreements at small margins).

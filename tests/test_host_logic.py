@@ -62,8 +62,10 @@ def test_manipulate_arch_fans_out_like_the_reference(gs):
         m.backbone.conv1.manipulate_width(10 ** 6)
 
 
-def test_state_dict_is_reference_format(gs):
-    cfg = C.small_cfg(aux=True, deep_stem=True, os8=True)
+@pytest.mark.parametrize('kw', [dict(aux=True, deep_stem=True, os8=True), dict(psp=True, aux=True, os8=True),
+                                dict(aspp=True, os8=True)], ids=['fcn_aux', 'psp_aux', 'aspp'])
+def test_state_dict_is_reference_format(gs, kw):
+    cfg = C.small_cfg(**kw)
     m = gs.build_segmentor(cfg, train_cfg=dict(), test_cfg=dict(mode='whole'))
     o = O.build_segmentor(cfg)
     sd_m, sd_o = m.state_dict(), o.state_dict()

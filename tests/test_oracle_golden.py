@@ -139,3 +139,31 @@ def test_extracted_subnet_equals_manipulated_supernet():
         assert torch.equal(a, b)
     assert sub.layer3[0].conv1.weight.shape[0] == 24 and len(sub.layer3) == 2
     assert sum(p.numel() for p in sub.parameters()) < sum(p.numel() for p in bb.parameters())
+
+
+def test_aspp_head_equals_static_torch_modules_on_the_prefix_slice():
+    """BASELINE config 3's DeepLabV3 head is not in the reference tree; the oracle's DynamicASPPHead is pinned against
+    stock torch modules (nn.Conv2d / nn.BatchNorm2d holding the PREFIX-SLICED weights) wired like mmseg's ASPPHead."""
+    torch.manual_seed(3)
+    dil, C_in, C_x, ch, K = (1, 2, 3), 24, 16, 8, 5
+    head = O.DynamicASPPHead(C_in, ch, K, dilations=dil, dropout_ratio=0, conv_cfg=dict(type='DynConv2d'),
+                             norm_cfg=dict(type='DynBN', requires_grad=True), in_index=0)
+    for p in head.parameters():
+        torch.nn.init.normal_(p, 0, 0.3)
+    head.eval()
+    x = torch.randn(2, C_x, 9, 11)                                       # narrower than in_channels: prefix slice
+
+    def cba(mod, inp, k, d):
+        w = mod.conv.weight[:, :inp.size(1)]
+        y = F.conv2d(inp, w, None, 1, 0 if k == 1 else d, d)
+        n = mod.norm
+        return F.relu(F.batch_norm(y, n.running_mean, n.running_var, n.weight, n.bias, False, 0.1, n.eps))
+
+    outs = [F.interpolate(cba(head.image_pool[1], F.adaptive_avg_pool2d(x, 1), 1, 1), size=(9, 11), mode='bilinear',
+                          align_corners=False)]
+    outs += [cba(m, x, 1 if d == 1 else 3, d) for m, d in zip(head.aspp_modules, dil)]
+    ref = F.conv2d(cba(head.bottleneck, torch.cat(outs, 1), 3, 1), head.conv_seg.weight, head.conv_seg.bias)
+    with torch.no_grad():
+        got = head([x])
+    np.testing.assert_allclose(got.numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-5)
+    assert list(dict(head.named_parameters()))[:3] == ['conv_seg.weight', 'conv_seg.bias', 'image_pool.1.conv.weight']
