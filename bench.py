@@ -305,6 +305,9 @@ def main():
         torch.cuda.profiler.stop()
         print(json.dumps({'ncu_cycle': 'done', 'launches_per_cycle': None}))
         return
+    if args.kineto and rank != 0:      # the other ranks take part in the profiled cycle (SyncBN exchanges)
+        step_resident()
+        torch.cuda.synchronize()
     if args.kineto and rank == 0:
         from torch.profiler import ProfilerActivity, profile
         torch.cuda.synchronize()
@@ -320,6 +323,9 @@ def main():
         rows = sorted(({'kernel': k, 'ms': v[0] / 1e3, 'launches': v[1]} for k, v in agg.items()), key=lambda r: -r['ms'])
         os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
         json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'kineto_kernels.json'), 'w'), indent=0)
+    if args.host_profile and rank != 0:
+        step_resident()
+        torch.cuda.synchronize()
     if args.host_profile and rank == 0:
         import cProfile
         import pstats

@@ -83,7 +83,7 @@ PROTOTYPES = {
     'gs_ipc_open': (_I, [_P, _P]),
     'gs_ipc_close': (_I, [_P]),
     'gs_ipc_free': (_I, [_P]),
-    'gs_syncbn_allreduce': (_I, [_P, _I, _P, _I, _I, _P, _P]),
+    'gs_syncbn_allreduce': (_I, [_P, _I, _P, _I, _I, _P, _P, _P, _P]),
     'gs_sgd_flat': (_I, [_P, _P, _P, _L, _P, _I, _P, _P]),
 }
 

@@ -3,15 +3,18 @@
 // The reference's SyncBN issues, per BN layer and direction, an NCCL all_gather / all_reduce of a few KB from the
 // host (2 x ~140 layers per step: [EXT] torch.nn.SyncBatchNorm under gaiavision DynSyncBN,
 // configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:20-23): latency- and launch-bound.  Here every rank owns an
-// IPC-shared inbox; gs_syncbn_allreduce is ONE small kernel that
-//   1. stores the local packed sums into slot[seq % NSLOT][my rank] of EVERY rank's inbox (P2P st.global over NVLink),
-//   2. publishes a release flag carrying the sequence number,
-//   3. spins (acquire, bounded) until the flags of all ranks for this sequence number have arrived in its own inbox,
-//   4. sums the `world` contributions in rank order -> bit-identical result on every rank.
+// IPC-shared inbox; gs_syncbn_allreduce is ONE small kernel with a flag-in-data ("low latency") protocol:
+//   1. every fp64 value is split into two 32-bit halves, each stored together with the 32-bit sequence tag of this
+//      exchange as ONE 8-byte word (single-copy atomic) straight into slot[seq % NSLOT][my rank] of every PEER's inbox
+//      (P2P st.global over NVLink) -- no memory fence, no separate flag, so the cost is ONE one-way NVLink latency;
+//   2. the kernel then polls its own inbox until both words of a value carry the current tag and sums the `world`
+//      contributions in rank order (its own from registers) -> bit-identical result on every rank.
 // Sequence numbers come from a device-resident counter, so the kernel is CUDA-graph safe.  A rank can be at most
-// one exchange ahead of the slowest rank (it needs everybody's flag to finish), so NSLOT >= 2 slots never collide.
-// Different GPUs run their kernels concurrently by construction (one process per GPU); the bounded spin turns a
-// missing peer into a trapped kernel instead of a hung box.
+// one exchange ahead of the slowest rank (it needs everybody's data to finish), so NSLOT = 4 slots never collide,
+// and a slot's stale words carry an older tag.  Different GPUs run their kernels concurrently by construction (one
+// process per GPU); the bounded spin turns a missing peer into a trapped kernel instead of a hung box.
+// Optionally the same kernel first accumulates the BN parameter gradients from the LOCAL sums (dbeta += sum g,
+// dgamma += sum g*xhat) -- they are averaged later by the gradient all-reduce like every other parameter gradient.
 #include "../../include/gaiaseg_b200.h"
 #include "gs_host.h"
 
@@ -23,21 +26,19 @@ namespace gs {
 constexpr int kCommSlots = 4;
 constexpr int kCommMaxWorld = 8;
 constexpr int kCommSlotDoubles = 2 * 4096;   // 2*C doubles, C <= 4096
+constexpr int kCommThreads = 1024;
+constexpr int kCommPerThread = kCommSlotDoubles / kCommThreads;
 
 struct PeerPtrs {
-    double* p[kCommMaxWorld];
+    ulonglong2* p[kCommMaxWorld];
 };
 
-__host__ __device__ inline size_t comm_flag_offset_doubles(int world) {
-    return static_cast<size_t>(kCommSlots) * world * kCommSlotDoubles;
+__device__ __forceinline__ void st_u64_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+__device__ __forceinline__ ulonglong2 ld_v2_sys(const ulonglong2* p) {
+    ulonglong2 v;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -46,44 +47,71 @@ __device__ __forceinline__ unsigned long long gtimer() {
     return t;
 }
 
-__global__ void __launch_bounds__(512) syncbn_allreduce_kernel(double* __restrict__ stats, int n, PeerPtrs peers, int rank,
-                                                               int world, unsigned long long* seq_dev) {
-    __shared__ unsigned long long s_seq;
+__global__ void __launch_bounds__(kCommThreads) syncbn_allreduce_kernel(double* __restrict__ stats, int n, PeerPtrs peers,
+                                                                        int rank, int world, unsigned long long* seq_dev,
+                                                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int tid = threadIdx.x;
-    if (tid == 0) s_seq = *seq_dev + 1;
-    __syncthreads();
-    const unsigned long long seq = s_seq;
+    const unsigned long long seq = *seq_dev + 1;     // every thread reads the counter; thread 0 bumps it at the very end
+    const unsigned long long tag = (seq & 0xFFFFFFFFull) << 32;
     const int slot = static_cast<int>(seq % kCommSlots);
-    // 1. push the local contribution to every rank (own inbox included)
-    for (int r = 0; r < world; ++r) {
-        double* dst = peers.p[r] + (static_cast<size_t>(slot) * world + rank) * kCommSlotDoubles;
-        for (int i = tid; i < n; i += blockDim.x) dst[i] = stats[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    // 2. publish, 3. wait
-    if (tid < world) {
-        unsigned long long* flags = reinterpret_cast<unsigned long long*>(peers.p[tid] + comm_flag_offset_doubles(world));
-        st_release_sys(flags + slot * world + rank, seq);
-        const unsigned long long* mine =
-            reinterpret_cast<const unsigned long long*>(peers.p[rank] + comm_flag_offset_doubles(world)) + slot * world + tid;
-        const unsigned long long t0 = gtimer();
-        unsigned int spins = 0;
-        while (ld_acquire_sys(mine) < seq) {
-            if ((++spins & 1023u) == 0 && gtimer() - t0 > 10000000000ull) {
-                printf("gaiaseg_b200: SyncBN peer exchange timed out (rank %d waiting for rank %d, seq %llu)\n", rank, tid, seq);
-                __trap();
+    double mine[kCommPerThread];
+    // 1. push the local contribution to every peer
+#pragma unroll
+    for (int k = 0; k < kCommPerThread; ++k) {
+        const int i = tid + k * kCommThreads;
+        if (i < n) {
+            const double v = stats[i];
+            mine[k] = v;
+            const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+            const unsigned long long w0 = (b & 0xFFFFFFFFull) | tag, w1 = (b >> 32) | tag;
+            for (int r = 0; r < world; ++r) {
+                if (r == rank) continue;
+                unsigned long long* dst = reinterpret_cast<unsigned long long*>(
+                    peers.p[r] + (static_cast<size_t>(slot) * world + rank) * kCommSlotDoubles + i);
+                st_u64_sys(dst, w0);
+                st_u64_sys(dst + 1, w1);
             }
         }
     }
-    __syncthreads();
-    // 4. reduce in rank order
-    const double* inbox = peers.p[rank] + static_cast<size_t>(slot) * world * kCommSlotDoubles;
-    for (int i = tid; i < n; i += blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < world; ++r) s += __ldcg(inbox + static_cast<size_t>(r) * kCommSlotDoubles + i);
-        stats[i] = s;
+    // BN parameter gradients from the LOCAL sums (n = 2C: [sum g | sum g*xhat])
+    if (dbeta != nullptr || dgamma != nullptr) {
+        const int C = n >> 1;
+#pragma unroll
+        for (int k = 0; k < kCommPerThread; ++k) {
+            const int i = tid + k * kCommThreads;
+            if (i < n) {
+                if (i < C) { if (dbeta) dbeta[i] += static_cast<float>(mine[k]); }
+                else if (dgamma) dgamma[i - C] += static_cast<float>(mine[k]);
+            }
+        }
     }
+    // 2. poll the own inbox, reduce in rank order
+    const ulonglong2* inbox = peers.p[rank] + static_cast<size_t>(slot) * world * kCommSlotDoubles;
+    const unsigned long long t0 = gtimer();
+#pragma unroll
+    for (int k = 0; k < kCommPerThread; ++k) {
+        const int i = tid + k * kCommThreads;
+        if (i < n) {
+            double s = 0.0;
+            for (int r = 0; r < world; ++r) {
+                if (r == rank) { s += mine[k]; continue; }
+                const ulonglong2* src = inbox + static_cast<size_t>(r) * kCommSlotDoubles + i;
+                ulonglong2 w = ld_v2_sys(src);
+                unsigned int spins = 0;
+                while ((w.x & 0xFFFFFFFF00000000ull) != tag || (w.y & 0xFFFFFFFF00000000ull) != tag) {
+                    if ((++spins & 1023u) == 0 && gtimer() - t0 > 10000000000ull) {
+                        printf("gaiaseg_b200: SyncBN peer exchange timed out (rank %d waiting for rank %d, seq %llu)\n", rank,
+                               r, seq);
+                        __trap();
+                    }
+                    w = ld_v2_sys(src);
+                }
+                s += __longlong_as_double(static_cast<long long>((w.x & 0xFFFFFFFFull) | (w.y << 32)));
+            }
+            stats[i] = s;
+        }
+    }
+    __syncthreads();      // every thread has read *seq_dev long before, but keep the bump strictly last
     if (tid == 0) *seq_dev = seq;
 }
 
@@ -92,7 +120,7 @@ __global__ void __launch_bounds__(512) syncbn_allreduce_kernel(double* __restric
 using namespace gs;
 
 extern "C" int64_t gs_comm_inbox_bytes(int32_t world) {
-    return static_cast<int64_t>(comm_flag_offset_doubles(world)) * 8 + static_cast<int64_t>(kCommSlots) * world * 8;
+    return static_cast<int64_t>(kCommSlots) * world * kCommSlotDoubles * static_cast<int64_t>(sizeof(ulonglong2));
 }
 
 extern "C" int gs_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle_out_64) {
@@ -130,18 +158,22 @@ extern "C" int gs_ipc_free(void* dev_ptr) {
 }
 
 extern "C" int gs_syncbn_allreduce(double* stats, int32_t n, const void* const* peer_inboxes, int32_t rank, int32_t world,
-                                   void* seq_dev, void* stream) {
+                                   void* seq_dev, float* dgamma, float* dbeta, void* stream) {
     GS_REQUIRE(stats && peer_inboxes && seq_dev, "syncbn_allreduce: null pointer");
     GS_REQUIRE(world >= 1 && world <= kCommMaxWorld && rank >= 0 && rank < world, "syncbn_allreduce: bad rank %d / world %d",
                rank, world);
     GS_REQUIRE(n > 0 && n <= kCommSlotDoubles, "syncbn_allreduce: %d values exceed the slot size %d", n, kCommSlotDoubles);
+    GS_REQUIRE((dgamma == nullptr && dbeta == nullptr) || n % 2 == 0, "syncbn_allreduce: parameter gradients need n = 2C");
     PeerPtrs pp{};
     for (int r = 0; r < world; ++r) {
         GS_REQUIRE(peer_inboxes[r] != nullptr, "syncbn_allreduce: inbox of rank %d is not mapped", r);
-        pp.p[r] = reinterpret_cast<double*>(const_cast<void*>(peer_inboxes[r]));
+        pp.p[r] = reinterpret_cast<ulonglong2*>(const_cast<void*>(peer_inboxes[r]));
     }
-    syncbn_allreduce_kernel<<<1, 512, 0, static_cast<cudaStream_t>(stream)>>>(
-        stats, n, pp, rank, world, reinterpret_cast<unsigned long long*>(seq_dev));
+    int threads = ((n + 31) / 32) * 32;
+    if (threads > kCommThreads) threads = kCommThreads;
+    syncbn_allreduce_kernel<<<1, kCommThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        stats, n, pp, rank, world, reinterpret_cast<unsigned long long*>(seq_dev), dgamma, dbeta);
+    (void)threads;
     GS_LAUNCHED();
     return 0;
 }

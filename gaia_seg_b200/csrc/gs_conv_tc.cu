@@ -81,16 +81,8 @@ struct IgemmParams {
     const float* shift;
     const __nv_bfloat16* residual;
     long long res_ld;
+    // non-NULL: per-channel sum / sum^2 of the stored (bf16-rounded) output, fp64 [2 * Cout] (DynBN forward statistics)
     double* stats;
-    // stats_mode 1: sum / sum^2 of the stored output (DynBN forward statistics)
-    // stats_mode 2: the output is dz of a BN(+ReLU) layer -> sum g, sum g*xhat (BN backward reduction) with
-    //               g = dz * mask, xhat = (y - mean) * invstd; mask = [z > 0] if bwd_z else [fma(y, scale, shift) > 0]
-    int stats_mode;
-    int tw_shift;
-    const __nv_bfloat16* bwd_y; long long bwd_y_ld;
-    const __nv_bfloat16* bwd_z; long long bwd_z_ld;
-    const float* bwd_aff;   // [4][Cout]: mean, invstd, scale, shift
-    int bwd_relu;
 };
 
 template <int CG>
@@ -283,9 +275,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         int tr_t = 0;
         uint32_t ring = 0;                 // staging position of this half (2 slots, flattened over tiles)
         uint8_t* const hstage = staging + half * 2 * (128 * 128);
-        float st_s[4], st_q[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
+        // DynBN statistics of this lane's column pair in each of the half's two sub-tiles, packed (col, col+1) fp32x2
+        uint64_t st_s2[2] = {0ull, 0ull}, st_q2[2] = {0ull, 0ull};
+        const uint32_t hstage_u32 = smem_u32(hstage);
+        const uint32_t r7s = static_cast<uint32_t>(row & 7) << 4;
+        const uint32_t st_lane = (static_cast<uint32_t>(lane >> 2) << 4) | (static_cast<uint32_t>(lane & 3) << 2);
         for (int mu = mu0; mu < m_units; mu += groups) {
             const int mt = mu * CG + rank;
             const int img = mt / tiles_hw;
@@ -314,17 +308,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         tma_load_4d(hstage + ((ring + j - j_lo) & 1) * (128 * 128), &tmR, &res_bar[j], n0 + j * 64, w0,
                                     h0, img);
                     }
-                }
-            }
-
-            if (p.stats_mode == 2 && valid) {
-                // pull this tile's y (z) rows towards L2 while the MMA main loop of the tile is still running
-                const char* yp = reinterpret_cast<const char*>(p.bwd_y + pix * p.bwd_y_ld + n0 + half * 128);
-                const int bytes = (n_valid - half * 128) * 2;
-                for (int o = 0; o < bytes && o < 256; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + o));
-                if (p.bwd_relu && p.bwd_z != nullptr) {
-                    const char* zp = reinterpret_cast<const char*>(p.bwd_z + pix * p.bwd_z_ld + n0 + half * 128);
-                    for (int o = 0; o < bytes && o < 256; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(zp + o));
                 }
             }
 
@@ -390,8 +373,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     __syncwarp();
                     if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
                 }
-                for (int j = j_lo; j < j_hi; ++j) {
-                    uint8_t* sub = hstage + (ring & 1) * (128 * 128);
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = j_lo + jj;
+                    if (j >= j_hi) break;
+                    // shared-space addresses (32 bit): slot base is 1024-aligned, so the 128B-swizzle XOR of 16-byte chunk k
+                    // of this thread's row is  wr ^ (k << 4)
+                    const uint32_t sub_u32 = hstage_u32 + (ring & 1) * (128 * 128);
+                    const uint32_t wr = (sub_u32 + row * 128) ^ r7s;
                     if (res_tma) mbar_wait(&res_bar[j], res_phase);
                     tmem_ld_wait();
 #pragma unroll
@@ -402,21 +391,34 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cc == 0 ? raw0[i] : raw1[i]);
                             const int col0 = n0 + c * 32;
-                            if (p.scale != nullptr) {
+                            if (p.scale != nullptr || p.shift != nullptr) {
+                                if (col0 + 32 <= p.Cout) {       // whole chunk inside the active width: vector loads
 #pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    if (col0 + i < p.Cout) v[i] *= __ldg(p.scale + col0 + i);
-                            }
-                            if (p.shift != nullptr) {
+                                    for (int g4 = 0; g4 < 8; ++g4) {
+                                        if (p.scale != nullptr) {
+                                            const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + g4);
+                                            v[g4 * 4 + 0] *= s4.x; v[g4 * 4 + 1] *= s4.y;
+                                            v[g4 * 4 + 2] *= s4.z; v[g4 * 4 + 3] *= s4.w;
+                                        }
+                                        if (p.shift != nullptr) {
+                                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.shift + col0) + g4);
+                                            v[g4 * 4 + 0] += b4.x; v[g4 * 4 + 1] += b4.y;
+                                            v[g4 * 4 + 2] += b4.z; v[g4 * 4 + 3] += b4.w;
+                                        }
+                                    }
+                                } else {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    if (col0 + i < p.Cout) v[i] += __ldg(p.shift + col0 + i);
+                                    for (int i = 0; i < 32; ++i)
+                                        if (col0 + i < p.Cout) {
+                                            if (p.scale != nullptr) v[i] *= __ldg(p.scale + col0 + i);
+                                            if (p.shift != nullptr) v[i] += __ldg(p.shift + col0 + i);
+                                        }
+                                }
                             }
                             if (res_tma) {
 #pragma unroll
                                 for (int g8 = 0; g8 < 4; ++g8) {
-                                    const int chunk = (cc * 4 + g8) ^ (row & 7);
-                                    const uint4 u = *reinterpret_cast<const uint4*>(sub + row * 128 + chunk * 16);
+                                    const uint4 u = lds128(wr ^ ((cc * 4 + g8) << 4));
                                     v[g8 * 8 + 0] += bf16_lo(u.x); v[g8 * 8 + 1] += bf16_hi(u.x);
                                     v[g8 * 8 + 2] += bf16_lo(u.y); v[g8 * 8 + 3] += bf16_hi(u.y);
                                     v[g8 * 8 + 4] += bf16_lo(u.z); v[g8 * 8 + 5] += bf16_hi(u.z);
@@ -433,13 +435,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             }
 #pragma unroll
                             for (int g8 = 0; g8 < 4; ++g8) {
-                                const int chunk = (cc * 4 + g8) ^ (row & 7);
                                 uint4 u;
                                 u.x = pack_bf16x2(v[g8 * 8 + 0], v[g8 * 8 + 1]);
                                 u.y = pack_bf16x2(v[g8 * 8 + 2], v[g8 * 8 + 3]);
                                 u.z = pack_bf16x2(v[g8 * 8 + 4], v[g8 * 8 + 5]);
                                 u.w = pack_bf16x2(v[g8 * 8 + 6], v[g8 * 8 + 7]);
-                                *reinterpret_cast<uint4*>(sub + row * 128 + chunk * 16) = u;
+                                sts128(wr ^ ((cc * 4 + g8) << 4), u);
                             }
                         }
                     }
@@ -461,64 +462,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         // lane owns columns (2*lane, 2*lane+1) of this sub-tile, over the 32 rows its warp staged
                         const int cin = lane * 2;
                         if (j * 64 + cin < n_valid) {
-                            const int chunk = cin >> 3;
-                            const int word = (cin & 7) >> 1;
-                            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                            if (p.stats_mode == 1) {
-#pragma unroll 8
-                                for (int r = 0; r < 32; ++r) {
-                                    const int rr = q * 32 + r;
-                                    const uint32_t wv = *reinterpret_cast<const uint32_t*>(
-                                        sub + rr * 128 + ((chunk ^ (rr & 7)) << 4) + word * 4);
-                                    const float a = bf16_lo(wv), b = bf16_hi(wv);
-                                    s0 += a; q0 = fmaf(a, a, q0);
-                                    s1 += b; q1 = fmaf(b, b, q1);
-                                }
-                            } else {
-                                // BN-backward reduction fused into the dgrad that produced dz (no separate pass over dz)
-                                const int col = n0 + j * 64 + cin;
-                                const float mu0 = __ldg(p.bwd_aff + col), mu1 = __ldg(p.bwd_aff + col + 1);
-                                const float is0 = __ldg(p.bwd_aff + p.Cout + col), is1 = __ldg(p.bwd_aff + p.Cout + col + 1);
-                                const float sc0 = __ldg(p.bwd_aff + 2 * p.Cout + col), sc1 = __ldg(p.bwd_aff + 2 * p.Cout + col + 1);
-                                const float sh0 = __ldg(p.bwd_aff + 3 * p.Cout + col), sh1 = __ldg(p.bwd_aff + 3 * p.Cout + col + 1);
-                                // all 32 row loads of y (and z) are issued back to back (addresses of rows outside the
-                                // image are clamped, their dz is zero) so ONE memory latency is exposed per sub-tile
-                                uint32_t yv[32], zv[32];
+                            {
+                                // 32 conflict-free LDS.32 (row r: chunk (lane>>2) ^ (r & 7), word lane & 3) -> packed
+                                // fp32x2 accumulation (FADD2 / FFMA2) of both columns at once
+                                const uint32_t sb = sub_u32 + q * (32 * 128);
+                                uint64_t s2 = st_s2[jj], q2 = st_q2[jj];
 #pragma unroll
                                 for (int r = 0; r < 32; ++r) {
-                                    const int rr = q * 32 + r;
-                                    int hh = h0 + (rr >> p.tw_shift), ww = w0 + (rr & (p.TW - 1));
-                                    hh = hh < p.Ho ? hh : p.Ho - 1;
-                                    ww = ww < p.Wo ? ww : p.Wo - 1;
-                                    const int ii = img < p.N ? img : p.N - 1;
-                                    const long long px = (static_cast<long long>(ii) * p.Ho + hh) * p.Wo + ww;
-                                    yv[r] = __ldg(reinterpret_cast<const uint32_t*>(p.bwd_y + px * p.bwd_y_ld + col));
-                                    if (p.bwd_relu && p.bwd_z != nullptr)
-                                        zv[r] = __ldg(reinterpret_cast<const uint32_t*>(p.bwd_z + px * p.bwd_z_ld + col));
+                                    const uint32_t wv = lds32(sb + r * 128 + (st_lane ^ ((r & 7) << 4)));
+                                    const uint64_t pv = pack_f32x2(bf16_lo(wv), bf16_hi(wv));
+                                    s2 = add_f32x2(s2, pv);
+                                    q2 = fma_f32x2(pv, pv, q2);
                                 }
-#pragma unroll
-                                for (int r = 0; r < 32; ++r) {
-                                    const int rr = q * 32 + r;
-                                    const uint32_t wv = *reinterpret_cast<const uint32_t*>(
-                                        sub + rr * 128 + ((chunk ^ (rr & 7)) << 4) + word * 4);   // zero for rows outside
-                                    const float y0 = bf16_lo(yv[r]), y1 = bf16_hi(yv[r]);
-                                    bool dead0 = false, dead1 = false;
-                                    if (p.bwd_relu) {
-                                        if (p.bwd_z != nullptr) {
-                                            dead0 = !(bf16_lo(zv[r]) > 0.f);
-                                            dead1 = !(bf16_hi(zv[r]) > 0.f);
-                                        } else {
-                                            dead0 = !(fmaf(y0, sc0, sh0) > 0.f);
-                                            dead1 = !(fmaf(y1, sc1, sh1) > 0.f);
-                                        }
-                                    }
-                                    const float g0 = dead0 ? 0.f : bf16_lo(wv), g1 = dead1 ? 0.f : bf16_hi(wv);
-                                    s0 += g0; q0 = fmaf(g0, (y0 - mu0) * is0, q0);
-                                    s1 += g1; q1 = fmaf(g1, (y1 - mu1) * is1, q1);
-                                }
+                                st_s2[jj] = s2; st_q2[jj] = q2;
                             }
-                            st_s[(j - j_lo) * 2] += s0; st_q[(j - j_lo) * 2] += q0;
-                            st_s[(j - j_lo) * 2 + 1] += s1; st_q[(j - j_lo) * 2 + 1] += q1;
                         }
                     }
                     fence_proxy_async_smem();
@@ -527,7 +484,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     if (ep_tid == 0) tma_store_wait_read0();
                     named_bar_sync(1 + half, 128);
                     if (ep_tid == 0) {
-                        tma_store_4d(&tmC, sub, n0 + j * 64, w0, h0, img);
+                        tma_store_4d(&tmC, reinterpret_cast<const void*>(hstage + (ring & 1) * (128 * 128)), n0 + j * 64, w0,
+                                     h0, img);
                         tma_store_commit();
                         if (j == 0 && tr_t < 16) trace(146 + 4 * tr_t);
                     }
@@ -550,8 +508,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    red[q * 512 + (half * 2 + jj) * 64 + lane * 2 + e] = st_s[jj * 2 + e];
-                    red[q * 512 + 256 + (half * 2 + jj) * 64 + lane * 2 + e] = st_q[jj * 2 + e];
+                    red[q * 512 + (half * 2 + jj) * 64 + lane * 2 + e] = e ? f32x2_hi(st_s2[jj]) : f32x2_lo(st_s2[jj]);
+                    red[q * 512 + 256 + (half * 2 + jj) * 64 + lane * 2 + e] = e ? f32x2_hi(st_q2[jj]) : f32x2_lo(st_q2[jj]);
                 }
             named_bar_sync(3, 256);
             for (int c = ep_tid + half * 128; c < 256; c += 256) {
@@ -594,7 +552,7 @@ struct IgemmLaunch {
     int in_mul, base, step;
     void* out; long long out_ld; int out_f32;
     const float* scale; const float* shift; const void* residual; long long res_ld; int relu; double* stats;
-    const gs_bn_bwd_fuse* fuse;   // non-NULL: `stats` receives the BN-backward sums of the layer that produced the conv input
+    const gs_bn_bwd_fuse* fuse;   // reserved, must be NULL
 };
 
 static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
@@ -624,21 +582,12 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     p.scale = L.scale; p.shift = L.shift;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(L.residual); p.res_ld = L.res_ld;
     p.stats = L.stats;
-    p.stats_mode = L.stats ? 1 : 0;
-    for (p.tw_shift = 0; (1 << p.tw_shift) < p.TW; ++p.tw_shift) {}
-    if (L.fuse != nullptr) {
-        GS_REQUIRE(L.fuse->y && L.fuse->aff && L.fuse->sums, "dgrad fuse: null pointer");
-        GS_REQUIRE(L.fuse->y_ld % 8 == 0 && (!L.fuse->z || L.fuse->z_ld % 8 == 0), "dgrad fuse: pitches must be multiples of 8");
-        p.stats = L.fuse->sums;
-        p.stats_mode = 2;
-        p.bwd_y = reinterpret_cast<const __nv_bfloat16*>(L.fuse->y); p.bwd_y_ld = L.fuse->y_ld;
-        p.bwd_z = reinterpret_cast<const __nv_bfloat16*>(L.fuse->z); p.bwd_z_ld = L.fuse->z_ld;
-        p.bwd_aff = L.fuse->aff; p.bwd_relu = L.fuse->relu;
-    }
+    GS_REQUIRE(L.fuse == nullptr, "dgrad: the fused BN-backward reduction was removed (measured slower than gs_bn_bwd_reduce); "
+                                  "pass fuse = NULL");
     const bool tma_store_ok = !L.out_f32 && (L.out_ld % 8 == 0) && (L.Cout % 8 == 0) &&
                               ((reinterpret_cast<uintptr_t>(L.out) & 15) == 0);
     p.direct = tma_store_ok ? 0 : 1;
-    GS_REQUIRE(!(p.direct && (L.stats || L.fuse)), "conv: statistics need the bf16 TMA-store epilogue (Co %% 8 == 0)");
+    GS_REQUIRE(!(p.direct && L.stats), "conv: statistics need the bf16 TMA-store epilogue (Co %% 8 == 0)");
     if (L.residual) {
         GS_REQUIRE(L.res_ld % 8 == 0 && L.Cout % 8 == 0 && (reinterpret_cast<uintptr_t>(L.residual) & 15) == 0,
                    "conv: residual needs Co %% 8 == 0 and 16-byte alignment");

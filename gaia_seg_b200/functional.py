@@ -342,10 +342,8 @@ def conv_wgrad(conv, a, dy, g):
         _timed_call('wgrad', g, fn, ctypes.byref(g), a.data_ptr(), dy.data_ptr(), gw.data_ptr(), st)
 
 
-# Experimental (off): fusing the BN-backward reduction into the dgrad epilogue is implemented and parity-green, but the
-# epilogue's latency-exposed reads of y cost more (+17 ms dgrad per cycle) than the separate reduction pass saves (8 ms);
-# it needs a TMA prefetch of the y tile into shared memory, for which the 3-stage ring leaves no room.
-FUSE_BN_REDUCE = os.environ.get('GS_FUSE_BN_REDUCE', '0') == '1'
+# Round-1 experiment, removed from the kernel: BN-backward sums in the dgrad epilogue (include/gaiaseg_b200.h, gs_bn_bwd_fuse).
+FUSE_BN_REDUCE = False
 
 
 def _fusable(prev):
@@ -429,9 +427,9 @@ class PeerExchange:
         self.seq = torch.zeros(1, dtype=torch.int64, device=torch.device('cuda', torch.cuda.current_device()))
         dist.barrier(group=group)
 
-    def all_reduce(self, stats):
+    def all_reduce(self, stats, dgamma=None, dbeta=None):
         call('gs_syncbn_allreduce', stats.data_ptr(), stats.numel(), self.ptrs, self.rank, self.world, self.seq.data_ptr(),
-             _stream())
+             dgamma, dbeta, _stream())
 
     @classmethod
     def get(cls, group=None):
@@ -451,12 +449,15 @@ class PeerExchange:
         return inst
 
 
-def stats_all_reduce(stats, group=None):
-    """Sum the packed fp64 statistics over the SyncBN group (peer-memory kernel, NCCL as fallback)."""
+def stats_all_reduce(stats, group=None, dgamma=None, dbeta=None):
+    """Sum the packed fp64 statistics over the SyncBN group (peer-memory kernel, NCCL as fallback).  `dgamma` / `dbeta`
+    (device pointers or None): BN parameter gradients, incremented by the LOCAL sums before the exchange."""
     ex = PeerExchange.get(group)
     if ex:
-        ex.all_reduce(stats)
+        ex.all_reduce(stats, dgamma, dbeta)
     else:
+        if dgamma or dbeta:
+            call('gs_bn_bwd_param', stats.data_ptr(), stats.numel() // 2, dgamma, dbeta, 1, _stream())
         dist.all_reduce(stats, group=group)
 
 
@@ -516,10 +517,9 @@ def bn_backward(bn, dz, y, aff, count, zmask, relu, want_dres, pre_sums=None):
     dbet = _param_grad(bn.bias).data_ptr() if gb else None
     pg, world = _sync_group(bn)
     if world > 1:
-        if gw or gb:   # parameter gradients come from the LOCAL sums (the gradient all-reduce averages them later)
-            call('gs_bn_bwd_param', sums.data_ptr(), C, dgam, dbet, 1, st)
+        # parameter gradients come from the LOCAL sums (the gradient all-reduce averages them later): same kernel
+        stats_all_reduce(sums, pg, dgam, dbet)
         dgam = dbet = None
-        stats_all_reduce(sums, pg)
     dy = new_act(N, C, H, W, dev)
     dres = new_act(N, C, H, W, dev) if want_dres else None
     call('gs_bn_bwd_apply', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),

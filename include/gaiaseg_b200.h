@@ -76,11 +76,9 @@ int gs_conv2d_fwd(const gs_conv_geom* g, const void* x, const void* w_krsc, void
                   const float* shift, const void* residual, int32_t res_ld, int32_t flags, double* stats,
                   void* stream);
 
-/* Optional fusion for gs_conv2d_dgrad: dx is the gradient dz flowing into the BN(+ReLU) layer that PRODUCED the conv
- * input, so the dgrad epilogue can do that layer's BN-backward reduction while the tile is on chip:
- *   sums[0:Ci] += sum g, sums[Ci:2Ci] += sum g*xhat,  g = dx * mask, xhat = (y - mean) * invstd,
- *   mask = none (relu == 0) | [z > 0] (z != NULL) | [fma(y, scale, shift) > 0];  aff = [mean|invstd|scale|shift] ([4][Ci]).
- * Saves the separate gs_bn_bwd_reduce pass (one read of dz and one launch per layer). */
+/* RESERVED argument of gs_conv2d_dgrad (must be NULL).  Round 1 tried to do the BN-backward reduction of the layer that
+ * produced the conv input inside the dgrad epilogue (sums += sum g, sum g*xhat); the epilogue's reads of y cost more than
+ * the separate gs_bn_bwd_reduce pass saves, so the device code was removed.  The struct stays so that the ABI is stable. */
 typedef struct gs_bn_bwd_fuse {
     const void* y; int32_t y_ld;     /* bf16 conv output of the producer layer, same pixels / channels as dx */
     const void* z; int32_t z_ld;     /* bf16 layer output (mask source when a residual was added), or NULL */
@@ -90,7 +88,7 @@ typedef struct gs_bn_bwd_fuse {
 } gs_bn_bwd_fuse;
 
 /* dx = conv_transpose(dy, w[:Co,:Ci]) (+ residual).  replaces autograd of F.conv2d (cuDNN dgrad).
- * For stride > 1 `workspace` must hold gs_conv2d_dgrad_workspace_bytes(g) bytes.  `fuse` may be NULL. */
+ * For stride > 1 `workspace` must hold gs_conv2d_dgrad_workspace_bytes(g) bytes.  `fuse` must be NULL (reserved). */
 int64_t gs_conv2d_dgrad_workspace_bytes(const gs_conv_geom* g);
 int gs_conv2d_dgrad(const gs_conv_geom* g, const void* dy, const void* w_krsc, void* dx, const void* residual,
                     int32_t res_ld, void* workspace, const gs_bn_bwd_fuse* fuse, void* stream);
@@ -252,15 +250,18 @@ int gs_upsample_bilinear_f32(const float* src, int32_t N, int32_t h, int32_t w, 
  * (configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:20-23).  Every rank allocates an IPC-shareable inbox of
  * gs_comm_inbox_bytes(world) bytes (gs_ipc_alloc -> 64-byte handle), exchanges the handles out of band
  * (torch.distributed.all_gather_object) and maps the peers' inboxes (gs_ipc_open).  gs_syncbn_allreduce is ONE kernel:
- * push the n packed fp64 sums to every inbox (P2P stores), release-flag with a device-resident sequence number,
- * bounded acquire-spin for all ranks, sum in rank order (bit-identical on every rank), result in place. */
+ * every fp64 sum travels as two 8-byte words {32 data bits | 32-bit sequence tag} stored straight into every peer's
+ * inbox (P2P stores, no fence, no separate flag: one one-way NVLink latency); the kernel polls its own inbox until the
+ * words carry the tag of this exchange (device-resident counter: CUDA-graph safe; bounded spin) and sums in rank order
+ * (bit-identical on every rank), result in place.  dgamma / dbeta (fp32 [C], may be NULL; n = 2C) are first
+ * incremented by the LOCAL sums: the BN parameter gradients, averaged later by the gradient all-reduce. */
 int64_t gs_comm_inbox_bytes(int32_t world);
 int gs_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle_out_64);
 int gs_ipc_open(const void* handle_64, void** dev_ptr);
 int gs_ipc_close(void* dev_ptr);
 int gs_ipc_free(void* dev_ptr);
 int gs_syncbn_allreduce(double* stats, int32_t n, const void* const* peer_inboxes, int32_t rank, int32_t world,
-                        void* seq_dev, void* stream);
+                        void* seq_dev, float* dgamma, float* dbeta, void* stream);
 
 /* ---- optimizer ---------------------------------------------------------- */
 /* SGD(momentum, weight decay) over the FLAT fp32 master buffer (all parameters back to back, each padded
