@@ -32,7 +32,7 @@ namespace gs {
 constexpr int kIgABytes = 128 * 64 * 2;       // 128 pixels x 64 channels bf16
 constexpr int kIgStagingBytes = 128 * 256 * 2;  // epilogue tile, 4 sub-tiles of [128][64] bf16
 constexpr int kIgBarBytes = 256;
-constexpr int kIgThreads = 320;                // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kIgThreads = 576;                // TMA warp, MMA warp, 16 epilogue warps
 // CG = 1: one CTA per 128-pixel x 256-channel tile.  CG = 2: a CTA PAIR (cluster of two SMs of one TPC, tcgen05
 // cta_group::2) computes 256 pixels x 256 channels -- each CTA stages its own 128 pixels of A and only HALF of the weight
 // tile (the tensor cores of both SMs read both halves), i.e. 32 KB instead of 48 KB of shared-memory fill per K chunk,
@@ -119,7 +119,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 8 * CG);  // one arrive per epilogue warp (of both CTAs of a pair: leader's barrier)
+            mbar_init(&tempty_bar[i], 16 * CG);  // one arrive per epilogue warp (of both CTAs of a pair: leader's barrier)
         }
         for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
         fence_mbar_init();
@@ -254,72 +254,79 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
         }
     } else {
-        // =========================== epilogue (warps 2..9) ===========================
-        // Two warps per TMEM sub-partition: `half` 0 drains accumulator columns 0..127 (sub-tiles 0,1), half 1
-        // columns 128..255 (sub-tiles 2,3); each half is an independent 128-thread pipeline with its own named
-        // barrier, two staging slots and its own TMA-store thread.
-        // Per tile: four 64-column sub-tiles, each  TMEM -> registers -> affine / residual / ReLU -> bf16 -> swizzled
-        // staging buffer (ring of 4 x 16 KB) -> TMA store, software-pipelined so the store of sub-tile j overlaps
-        // the drain of j+1 (one named barrier per sub-tile).  DynBN statistics: every lane re-reads the 32 rows
-        // its own warp just staged (column pair = lane, conflict-free) and keeps sum / sum^2 in registers across
-        // ALL tiles of the current n-tile; fp64 atomics only when the n-tile changes or the kernel ends.
-        const int q = warp & 3;            // TMEM sub-partition of this warp
+        // =========================== epilogue (warps 2..17) ===========================
+        // 16 warps = 4 sub-tile groups x 4 TMEM sub-partitions: group `sub` owns accumulator columns [64 sub, 64 sub + 64)
+        // (one TMA-store box), warp quarter q its 32 rows.  All four sub-tiles of a tile drain CONCURRENTLY -- the
+        // per-tile epilogue is instruction-issue bound, so it is spread over all four schedulers (4 warps each) --
+        // each group through its own 16 KB staging slot, named barrier and TMA-store thread:
+        //   TMEM -> registers -> affine / residual / ReLU -> bf16 -> swizzled staging -> TMA store.
+        // DynBN statistics: every lane re-reads the 32 rows its own warp just staged (column pair = lane,
+        // conflict-free) and keeps sum / sum^2 in registers across ALL tiles of the CTA; fp64 atomics once at the end.
+        const int q = warp & 3;            // TMEM sub-partition of this warp (hardware rule: warp id % 4)
+        const int sub = (warp - 2) >> 2;   // sub-tile group 0..3
         const int row = q * 32 + lane;     // accumulator row == pixel within the tile
-        const int half = (warp - 2) >> 2;
-        const int ep_tid = threadIdx.x - 64 - half * 128;   // thread index inside the half (0 = its TMA thread)
+        const int g_tid = threadIdx.x - 64 - sub * 128;   // thread index inside the group (0 = its TMA thread)
         const int th = row / p.TW;
         const int tw = row - th * p.TW;
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t res_phase = 0;
         int tr_t = 0;
-        uint32_t ring = 0;                 // staging position of this half (2 slots, flattened over tiles)
-        uint8_t* const hstage = staging + half * 2 * (128 * 128);
-        // DynBN statistics of this lane's column pair in each of the half's two sub-tiles, packed (col, col+1) fp32x2
-        uint64_t st_s2[2] = {0ull, 0ull}, st_q2[2] = {0ull, 0ull};
-        const uint32_t hstage_u32 = smem_u32(hstage);
-        const uint32_t r7s = static_cast<uint32_t>(row & 7) << 4;
+        uint8_t* const slot = staging + sub * (128 * 128);
+        const uint32_t slot_u32 = smem_u32(slot);
+        // shared-space addresses (32 bit): the slot is 1024-aligned, so the 128B-swizzle XOR of 16-byte chunk k of this
+        // thread's row is  wr ^ (k << 4)
+        const uint32_t wr = (slot_u32 + row * 128) ^ (static_cast<uint32_t>(row & 7) << 4);
         const uint32_t st_lane = (static_cast<uint32_t>(lane >> 2) << 4) | (static_cast<uint32_t>(lane & 3) << 2);
+        const uint32_t st_base = slot_u32 + q * (32 * 128);
+        uint64_t st_s2 = 0ull, st_q2 = 0ull;   // statistics of this lane's column pair, packed (col, col + 1) fp32x2
+        const int n0 = nt * 256;
+        int n_valid = p.Cout - n0;
+        if (n_valid > 256) n_valid = 256;
+        const int nchunks = (n_valid + 31) >> 5;
+        const bool has_cols = sub * 64 < n_valid;          // does this group own any column of the n-tile?
+        const bool res_tma = (!p.direct) && (p.residual != nullptr);
         for (int mu = mu0; mu < m_units; mu += groups) {
             const int mt = mu * CG + rank;
             const int img = mt / tiles_hw;
             const int rem = mt - img * tiles_hw;
             const int h0 = (rem / p.tiles_w) * p.TH;
             const int w0 = (rem % p.tiles_w) * p.TW;
-            const int n0 = nt * 256;
-            int n_valid = p.Cout - n0;
-            if (n_valid > 256) n_valid = 256;
-            const int nchunks = (n_valid + 31) >> 5;
-            const int nsub = (n_valid + 63) >> 6;
-            const int j_lo = half * 2;
-            const int j_hi = nsub < j_lo + 2 ? nsub : j_lo + 2;   // this half's sub-tiles [j_lo, j_hi)
             const int h = h0 + th, w = w0 + tw;
             const bool valid = (img < p.N) && (h < p.Ho) && (w < p.Wo);
             const long long pix = (static_cast<long long>(img) * p.Ho + h) * p.Wo + w;
 
-            const bool res_tma = (!p.direct) && (p.residual != nullptr);
-            if (res_tma) {
-                // residual tile -> staging IN PLACE (overlaps the MMA main loop of this tile); the epilogue adds it
-                // at the very positions it overwrites.  All earlier stores must have finished reading the ring.
-                if (ep_tid == 0) {
+            if (!p.direct && has_cols) {
+                // the previous tile's store must have finished READING the slot before anybody refills it; with a
+                // residual the refill is the TMA load of the residual tile IN PLACE (it overlaps the MMA main loop of
+                // this tile; the epilogue adds it at the very positions it overwrites)
+                if (g_tid == 0) {
                     tma_store_wait_read0();
-                    for (int j = j_lo; j < j_hi; ++j) {
-                        mbar_arrive_expect_tx(&res_bar[j], 128 * 128);
-                        tma_load_4d(hstage + ((ring + j - j_lo) & 1) * (128 * 128), &tmR, &res_bar[j], n0 + j * 64, w0,
-                                    h0, img);
+                    if (res_tma) {
+                        mbar_arrive_expect_tx(&res_bar[sub], 128 * 128);
+                        tma_load_4d(slot, &tmR, &res_bar[sub], n0 + sub * 64, w0, h0, img);
                     }
                 }
+                if (!res_tma) named_bar_sync(1 + sub, 128);
             }
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after_sync();
-            if (ep_tid == 0 && half == 0 && tr_t < 16) trace(144 + 4 * tr_t);
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+            if (g_tid == 0 && sub == 0 && tr_t < 16) trace(144 + 4 * tr_t);
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + sub * 64;
 
-            if (p.direct) {
-                for (int c = half * 4; c < nchunks && c < half * 4 + 4; ++c) {
+            if (!has_cols) {
+                // nothing to drain for this group: still hand the accumulator back
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
+            } else if (p.direct) {
+#pragma unroll 1
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = sub * 2 + cc;
+                    if (c >= nchunks) break;
                     uint32_t raw[32];
-                    tmem_ld_32x32b_x32(t_addr + c * 32, raw);
+                    tmem_ld_32x32b_x32(t_addr + cc * 32, raw);
                     tmem_ld_wait();
                     float v[32];
 #pragma unroll
@@ -363,157 +370,133 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 __syncwarp();
                 if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
             } else {
-                uint32_t raw0[32], raw1[32];                 // both 32-column chunks of the current sub-tile
-                if (j_lo < j_hi) {
-                    tmem_ld_32x32b_x32(t_addr + j_lo * 64, raw0);
-                    if (j_lo * 2 + 1 < nchunks) tmem_ld_32x32b_x32(t_addr + j_lo * 64 + 32, raw1);
-                } else {
-                    // nothing to drain for this half: still hand the accumulator back
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
+                // the sub-tile drains in four 16-column groups through two alternating register sets: the TMEM load of
+                // group g+1 is in flight while group g is converted and staged (18 warps leave 96 registers per thread)
+                uint32_t ra[16], rb[16];
+                const int ngrp = min(4, (n_valid - sub * 64 + 15) >> 4);   // 16-column groups with active columns
+                tmem_ld_32x32b_x16(t_addr, ra);
+                if (res_tma) mbar_wait(&res_bar[sub], res_phase);
+                tmem_ld_wait();
+                auto stage_group = [&](const uint32_t (&raw)[16], int g) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+                    const int col0 = n0 + sub * 64 + g * 16;
+                    if (p.scale != nullptr || p.shift != nullptr) {
+                        if (col0 + 16 <= p.Cout) {       // whole group inside the active width: vector loads
+#pragma unroll
+                            for (int g4 = 0; g4 < 4; ++g4) {
+                                if (p.scale != nullptr) {
+                                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + g4);
+                                    v[g4 * 4 + 0] *= s4.x; v[g4 * 4 + 1] *= s4.y;
+                                    v[g4 * 4 + 2] *= s4.z; v[g4 * 4 + 3] *= s4.w;
+                                }
+                                if (p.shift != nullptr) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.shift + col0) + g4);
+                                    v[g4 * 4 + 0] += b4.x; v[g4 * 4 + 1] += b4.y;
+                                    v[g4 * 4 + 2] += b4.z; v[g4 * 4 + 3] += b4.w;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (col0 + i < p.Cout) {
+                                    if (p.scale != nullptr) v[i] *= __ldg(p.scale + col0 + i);
+                                    if (p.shift != nullptr) v[i] += __ldg(p.shift + col0 + i);
+                                }
+                        }
+                    }
+                    if (res_tma) {
+#pragma unroll
+                        for (int g8 = 0; g8 < 2; ++g8) {
+                            const uint4 u = lds128(wr ^ ((g * 2 + g8) << 4));
+                            v[g8 * 8 + 0] += bf16_lo(u.x); v[g8 * 8 + 1] += bf16_hi(u.x);
+                            v[g8 * 8 + 2] += bf16_lo(u.y); v[g8 * 8 + 3] += bf16_hi(u.y);
+                            v[g8 * 8 + 4] += bf16_lo(u.z); v[g8 * 8 + 5] += bf16_hi(u.z);
+                            v[g8 * 8 + 6] += bf16_lo(u.w); v[g8 * 8 + 7] += bf16_hi(u.w);
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    if (!valid) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = 0.f;  // keeps OOB pixels out of the statistics
+                    }
+#pragma unroll
+                    for (int g8 = 0; g8 < 2; ++g8) {
+                        uint4 u;
+                        u.x = pack_bf16x2(v[g8 * 8 + 0], v[g8 * 8 + 1]);
+                        u.y = pack_bf16x2(v[g8 * 8 + 2], v[g8 * 8 + 3]);
+                        u.z = pack_bf16x2(v[g8 * 8 + 4], v[g8 * 8 + 5]);
+                        u.w = pack_bf16x2(v[g8 * 8 + 6], v[g8 * 8 + 7]);
+                        sts128(wr ^ ((g * 2 + g8) << 4), u);
+                    }
+                };
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g < ngrp) {
+                        if (g + 1 < ngrp) {
+                            if (g & 1) tmem_ld_32x32b_x16(t_addr + (g + 1) * 16, ra);
+                            else tmem_ld_32x32b_x16(t_addr + (g + 1) * 16, rb);
+                        }
+                        if (g & 1) stage_group(rb, g);
+                        else stage_group(ra, g);
+                        if (g + 1 < ngrp) tmem_ld_wait();
+                        if (g == (ngrp > 1 ? ngrp - 2 : 0)) {
+                            // the last group of this warp's accumulator share is in registers -> hand the buffer back
+                            tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
+                            if (g_tid == 0 && sub == 0 && tr_t < 16) trace(145 + 4 * tr_t);
+                        }
+                    }
                 }
+                // make the staged rows visible to the TMA engine, then one thread of the group stores the box while
+                // every warp accumulates the statistics of the rows it staged
+                fence_proxy_async_smem();
+                named_bar_sync(1 + sub, 128);
+                if (g_tid == 0) {
+                    tma_store_4d(&tmC, slot, n0 + sub * 64, w0, h0, img);
+                    tma_store_commit();
+                    if (sub == 0 && tr_t < 16) trace(146 + 4 * tr_t);
+                }
+                if (p.stats != nullptr && sub * 64 + lane * 2 < n_valid) {
+                    // lane owns columns (2*lane, 2*lane+1) of the sub-tile over the 32 rows its warp staged: 32
+                    // conflict-free LDS.32 (row r: chunk (lane>>2) ^ (r & 7), word lane & 3) -> packed fp32x2
+                    // accumulation (FADD2 / FFMA2) of both columns at once
+                    uint64_t s2 = st_s2, q2 = st_q2;
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    const int j = j_lo + jj;
-                    if (j >= j_hi) break;
-                    // shared-space addresses (32 bit): slot base is 1024-aligned, so the 128B-swizzle XOR of 16-byte chunk k
-                    // of this thread's row is  wr ^ (k << 4)
-                    const uint32_t sub_u32 = hstage_u32 + (ring & 1) * (128 * 128);
-                    const uint32_t wr = (sub_u32 + row * 128) ^ r7s;
-                    if (res_tma) mbar_wait(&res_bar[j], res_phase);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int c = j * 2 + cc;
-                        if (c < nchunks) {
-                            float v[32];
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cc == 0 ? raw0[i] : raw1[i]);
-                            const int col0 = n0 + c * 32;
-                            if (p.scale != nullptr || p.shift != nullptr) {
-                                if (col0 + 32 <= p.Cout) {       // whole chunk inside the active width: vector loads
-#pragma unroll
-                                    for (int g4 = 0; g4 < 8; ++g4) {
-                                        if (p.scale != nullptr) {
-                                            const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + g4);
-                                            v[g4 * 4 + 0] *= s4.x; v[g4 * 4 + 1] *= s4.y;
-                                            v[g4 * 4 + 2] *= s4.z; v[g4 * 4 + 3] *= s4.w;
-                                        }
-                                        if (p.shift != nullptr) {
-                                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.shift + col0) + g4);
-                                            v[g4 * 4 + 0] += b4.x; v[g4 * 4 + 1] += b4.y;
-                                            v[g4 * 4 + 2] += b4.z; v[g4 * 4 + 3] += b4.w;
-                                        }
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i)
-                                        if (col0 + i < p.Cout) {
-                                            if (p.scale != nullptr) v[i] *= __ldg(p.scale + col0 + i);
-                                            if (p.shift != nullptr) v[i] += __ldg(p.shift + col0 + i);
-                                        }
-                                }
-                            }
-                            if (res_tma) {
-#pragma unroll
-                                for (int g8 = 0; g8 < 4; ++g8) {
-                                    const uint4 u = lds128(wr ^ ((cc * 4 + g8) << 4));
-                                    v[g8 * 8 + 0] += bf16_lo(u.x); v[g8 * 8 + 1] += bf16_hi(u.x);
-                                    v[g8 * 8 + 2] += bf16_lo(u.y); v[g8 * 8 + 3] += bf16_hi(u.y);
-                                    v[g8 * 8 + 4] += bf16_lo(u.z); v[g8 * 8 + 5] += bf16_hi(u.z);
-                                    v[g8 * 8 + 6] += bf16_lo(u.w); v[g8 * 8 + 7] += bf16_hi(u.w);
-                                }
-                            }
-                            if (p.relu) {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                            }
-                            if (!valid) {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] = 0.f;  // keeps OOB pixels out of the statistics
-                            }
-#pragma unroll
-                            for (int g8 = 0; g8 < 4; ++g8) {
-                                uint4 u;
-                                u.x = pack_bf16x2(v[g8 * 8 + 0], v[g8 * 8 + 1]);
-                                u.y = pack_bf16x2(v[g8 * 8 + 2], v[g8 * 8 + 3]);
-                                u.z = pack_bf16x2(v[g8 * 8 + 4], v[g8 * 8 + 5]);
-                                u.w = pack_bf16x2(v[g8 * 8 + 6], v[g8 * 8 + 7]);
-                                sts128(wr ^ ((cc * 4 + g8) << 4), u);
-                            }
-                        }
+                    for (int r = 0; r < 32; ++r) {
+                        const uint32_t wv = lds32(st_base + r * 128 + (st_lane ^ ((r & 7) << 4)));
+                        const uint64_t pv = pack_f32x2(bf16_lo(wv), bf16_hi(wv));
+                        s2 = add_f32x2(s2, pv);
+                        q2 = fma_f32x2(pv, pv, q2);
                     }
-                    if (j == j_hi - 1) {
-                        // this warp's share of the accumulator is drained -> hand it back to the MMA warp
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
-                        if (ep_tid == 0 && half == 0 && tr_t < 16) trace(145 + 4 * tr_t);
-                    } else {
-                        // prefetch the next sub-tile's accumulators: the TMEM latency hides behind statistics,
-                        // fence, barrier and the TMA-store issue below
-                        const int c2 = (j + 1) * 2;
-                        tmem_ld_32x32b_x32(t_addr + c2 * 32, raw0);
-                        if (c2 + 1 < nchunks) tmem_ld_32x32b_x32(t_addr + (c2 + 1) * 32, raw1);
-                    }
-                    __syncwarp();
-                    if (p.stats != nullptr) {
-                        // lane owns columns (2*lane, 2*lane+1) of this sub-tile, over the 32 rows its warp staged
-                        const int cin = lane * 2;
-                        if (j * 64 + cin < n_valid) {
-                            {
-                                // 32 conflict-free LDS.32 (row r: chunk (lane>>2) ^ (r & 7), word lane & 3) -> packed
-                                // fp32x2 accumulation (FADD2 / FFMA2) of both columns at once
-                                const uint32_t sb = sub_u32 + q * (32 * 128);
-                                uint64_t s2 = st_s2[jj], q2 = st_q2[jj];
-#pragma unroll
-                                for (int r = 0; r < 32; ++r) {
-                                    const uint32_t wv = lds32(sb + r * 128 + (st_lane ^ ((r & 7) << 4)));
-                                    const uint64_t pv = pack_f32x2(bf16_lo(wv), bf16_hi(wv));
-                                    s2 = add_f32x2(s2, pv);
-                                    q2 = fma_f32x2(pv, pv, q2);
-                                }
-                                st_s2[jj] = s2; st_q2[jj] = q2;
-                            }
-                        }
-                    }
-                    fence_proxy_async_smem();
-                    // the OTHER slot of this half was stored one group ago: that store must have finished reading
-                    // shared memory before anybody passes the barrier and overwrites it with the next sub-tile
-                    if (ep_tid == 0) tma_store_wait_read0();
-                    named_bar_sync(1 + half, 128);
-                    if (ep_tid == 0) {
-                        tma_store_4d(&tmC, reinterpret_cast<const void*>(hstage + (ring & 1) * (128 * 128)), n0 + j * 64, w0,
-                                     h0, img);
-                        tma_store_commit();
-                        if (j == 0 && tr_t < 16) trace(146 + 4 * tr_t);
-                    }
-                    ++ring;
+                    st_s2 = s2; st_q2 = q2;
                 }
                 if (res_tma) res_phase ^= 1;
             }
-            if (ep_tid == 0 && half == 0 && tr_t < 16) trace(147 + 4 * tr_t);
+            if (g_tid == 0 && sub == 0 && tr_t < 16) trace(147 + 4 * tr_t);
             ++tr_t;
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-        if (!p.direct && ep_tid == 0) tma_store_wait_all0();
+        if (!p.direct && g_tid == 0) tma_store_wait_all0();
         if (p.stats != nullptr) {
             // one flush per kernel: the 4 row-quarters are summed through the now idle staging buffer, then one column
             // per thread goes out with two fp64 atomics
-            named_bar_sync(3, 256);
+            named_bar_sync(5, 512);
             float* red = reinterpret_cast<float*>(staging);        // [4 quarters][512]: sums 0..255, squares 256..511
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    red[q * 512 + (half * 2 + jj) * 64 + lane * 2 + e] = e ? f32x2_hi(st_s2[jj]) : f32x2_lo(st_s2[jj]);
-                    red[q * 512 + 256 + (half * 2 + jj) * 64 + lane * 2 + e] = e ? f32x2_hi(st_q2[jj]) : f32x2_lo(st_q2[jj]);
-                }
-            named_bar_sync(3, 256);
-            for (int c = ep_tid + half * 128; c < 256; c += 256) {
-                const int col = nt * 256 + c;
+            red[q * 512 + sub * 64 + lane * 2] = f32x2_lo(st_s2);
+            red[q * 512 + sub * 64 + lane * 2 + 1] = f32x2_hi(st_s2);
+            red[q * 512 + 256 + sub * 64 + lane * 2] = f32x2_lo(st_q2);
+            red[q * 512 + 256 + sub * 64 + lane * 2 + 1] = f32x2_hi(st_q2);
+            named_bar_sync(5, 512);
+            const int c = threadIdx.x - 64;
+            if (c < 256) {
+                const int col = n0 + c;
                 if (col < p.Cout) {
                     const float su = red[c] + red[512 + c] + red[1024 + c] + red[1536 + c];
                     const float sq = red[256 + c] + red[768 + c] + red[1280 + c] + red[1792 + c];
