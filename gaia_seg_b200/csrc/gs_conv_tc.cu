@@ -684,13 +684,18 @@ __global__ void zero_insert_kernel(const uint4* __restrict__ dy, long long dy_ld
 //   M = 128 output channels (A = dY, MN-major), N <= 256 input channels (B = X, MN-major),
 //   K = pixels, 64 per pipeline stage.  grid.x = co_tiles * ci_tiles * taps, grid.y = split-K.
 // ------------------------------------------------------------------------------------------------
-constexpr int kWgStages = 4;
 constexpr int kWgBoxBytes = 64 * 64 * 2;           // [64 pixels][64 channels] bf16
 constexpr int kWgABytes = 2 * kWgBoxBytes;
-constexpr int kWgBBytes = 4 * kWgBoxBytes;
-constexpr int kWgStageBytes = kWgABytes + kWgBBytes;
-constexpr int kWgSmemBytes = 1024 + kWgStages * kWgStageBytes + 256;
 constexpr int kWgThreads = 192;
+// CG = 2: a CTA pair (cta_group::2, M = 256 output channels): each CTA stages its own 128 output channels of dY and HALF
+// of the X tile -- 32 KB instead of 48 KB of L2 -> SM traffic per 64-pixel chunk, which is what bounds the main loop.
+template <int CG>
+struct WgCfg {
+    static constexpr int kStages = CG == 1 ? 4 : 6;
+    static constexpr int kBBytes = (4 / CG) * kWgBoxBytes;
+    static constexpr int kStageBytes = kWgABytes + kBBytes;
+    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+};
 
 struct WgradParams {
     int N, Ho, Wo, TH, TW, tiles_h, tiles_w, chunks_total, splitk;
@@ -706,11 +711,14 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                  : "memory");
 }
 
+template <int CG>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
              const __grid_constant__ WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kWgStages = WgCfg<CG>::kStages;
+    constexpr int kWgStageBytes = WgCfg<CG>::kStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kWgStages;
@@ -720,18 +728,22 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    // work item
-    int t = blockIdx.x;
+    // work item (CG 2: the two CTAs of a pair take output-channel tiles 2*cot and 2*cot + 1; a pair with an odd tile
+    // count ends on a phantom tile: its dY loads are out of bounds = zero and its epilogue stores nothing)
+    const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+    int t = blockIdx.x / CG;
     const int tap = t % (p.kh * p.kw); t /= (p.kh * p.kw);
     const int cit = t % p.ci_tiles;
     const int cot = t / p.ci_tiles;
     const int r = tap / p.kw, s = tap - r * p.kw;
-    const int co0 = cot * 128, ci0 = cit * 256;
+    const int co0 = (cot * CG + rank) * 128, ci0 = cit * 256;
     int ci_valid = p.Ci - ci0; if (ci_valid > 256) ci_valid = 256;
     int co_valid = p.Co - co0; if (co_valid > 128) co_valid = 128;
-    const int a_boxes = (co_valid + 63) >> 6;
-    const int b_boxes = (ci_valid + 63) >> 6;
     const uint32_t umma_n = (ci_valid + 15) & ~15;
+    const int n_half = static_cast<int>(umma_n) / CG;          // this CTA's share of the X tile (input channels)
+    const int cb0 = ci0 + rank * (CG == 2 ? n_half : 0);
+    const int a_boxes = CG == 2 ? 2 : (co_valid + 63) >> 6;   // pair: both CTAs always load 2 boxes (equal byte counts)
+    const int b_boxes = ((CG == 2 ? n_half : ci_valid) + 63) >> 6;
     const int per = (p.chunks_total + p.splitk - 1) / p.splitk;
     const int c_begin = blockIdx.y * per;
     int c_end = c_begin + per; if (c_end > p.chunks_total) c_end = p.chunks_total;
@@ -744,9 +756,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         mbar_init(tfull_bar, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr, 256);
+    if (warp == 1) {
+        if (CG == 2) tmem_alloc_pair(tmem_ptr, 256);
+        else tmem_alloc(tmem_ptr, 256);
+    }
     tc_fence_before_sync();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
     const bool has_work = c_begin < c_end;
@@ -754,7 +770,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     if (warp == 0) {
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t tx = (a_boxes + b_boxes) * kWgBoxBytes;
+            const uint32_t tx = CG * (a_boxes + b_boxes) * kWgBoxBytes;   // pair: the leader's barrier counts both CTAs
             for (int c = c_begin; c < c_end; ++c) {
                 const int img = c / tiles_hw;
                 const int rem = c - img * tiles_hw;
@@ -765,18 +781,26 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* a_dst = smem + stage * kWgStageBytes;
                 uint8_t* b_dst = a_dst + kWgABytes;
-                mbar_arrive_expect_tx(&full_bar[stage], tx);
-                for (int j = 0; j < a_boxes; ++j)
-                    tma_load_4d(a_dst + j * kWgBoxBytes, &tmDY, &full_bar[stage], co0 + j * 64, wo0, ho0, img);
-                for (int j = 0; j < b_boxes; ++j)
-                    tma_load_4d(b_dst + j * kWgBoxBytes, &tmX, &full_bar[stage], ci0 + j * 64, iw, ih, img);
+                if (CG == 1) {
+                    mbar_arrive_expect_tx(&full_bar[stage], tx);
+                    for (int j = 0; j < a_boxes; ++j)
+                        tma_load_4d(a_dst + j * kWgBoxBytes, &tmDY, &full_bar[stage], co0 + j * 64, wo0, ho0, img);
+                    for (int j = 0; j < b_boxes; ++j)
+                        tma_load_4d(b_dst + j * kWgBoxBytes, &tmX, &full_bar[stage], ci0 + j * 64, iw, ih, img);
+                } else {
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
+                    for (int j = 0; j < a_boxes; ++j)
+                        tma_load_4d_pair(a_dst + j * kWgBoxBytes, &tmDY, &full_bar[stage], co0 + j * 64, wo0, ho0, img);
+                    for (int j = 0; j < b_boxes; ++j)
+                        tma_load_4d_pair(b_dst + j * kWgBoxBytes, &tmX, &full_bar[stage], cb0 + j * 64, iw, ih, img);
+                }
                 if (++stage == kWgStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (elect_one() && has_work) {
+        if (rank == 0 && elect_one() && has_work) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t idesc = make_idesc_bf16(128, umma_n, true, true);
+            const uint32_t idesc = make_idesc_bf16(128 * CG, umma_n, true, true);
             uint32_t accumulate = 0;
             for (int c = c_begin; c < c_end; ++c) {
                 mbar_wait(&full_bar[stage], phase);
@@ -787,13 +811,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
                 for (int k = 0; k < 4; ++k) {
                     const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 2048, kWgBoxBytes, 1024);
                     const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 2048, kWgBoxBytes, 1024);
-                    umma_bf16_ss(tmem_base, adesc, bdesc, idesc, accumulate);
+                    if (CG == 2) umma_bf16_ss_pair(tmem_base, adesc, bdesc, idesc, accumulate);
+                    else umma_bf16_ss(tmem_base, adesc, bdesc, idesc, accumulate);
                     accumulate = 1;
                 }
-                umma_commit(&empty_bar[stage]);
+                if (CG == 2) umma_commit_pair(&empty_bar[stage]);
+                else umma_commit(&empty_bar[stage]);
                 if (++stage == kWgStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(tfull_bar);
+            if (CG == 2) umma_commit_pair(tfull_bar);
+            else umma_commit(tfull_bar);
         }
     } else if (has_work) {
         const int q = warp & 3;
@@ -828,8 +855,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         }
     }
     tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 256);
+    if (CG == 2) cluster_sync_all();
+    else __syncthreads();
+    if (warp == 1) {
+        if (CG == 2) tmem_dealloc_pair(tmem_base, 256);
+        else tmem_dealloc(tmem_base, 256);
+    }
 }
 
 static int launch_wgrad(const gs_conv_geom* g, const void* x, const void* dy, float* dw, cudaStream_t stream) {
@@ -847,9 +878,14 @@ static int launch_wgrad(const gs_conv_geom* g, const void* x, const void* dy, fl
     p.kh = g->kh; p.kw = g->kw; p.stride = g->stride; p.pad = g->pad; p.dil = g->dil;
     p.dw = dw; p.Ci_max = g->Ci_max;
     p.row_stride = static_cast<long long>(g->kh) * g->kw * g->Ci_max;
-    const int items = p.co_tiles * p.ci_tiles * g->kh * g->kw;
+    static const int cg_env = [] { const char* e = getenv("GS_WGRAD_CTA_GROUP"); return e ? atoi(e) : 2; }();
+    // pairs pay off only for the big layers (measured: >= ~2.5e10 MACs; smaller launches are bound by the split-K
+    // atomics and the short per-CTA pixel range, where the lock-step of a pair costs a little)
+    const double macs = (double)g->N * g->Ho * g->Wo * g->Co * g->Ci * g->kh * g->kw;
+    const int cg = (cg_env == 2 && p.co_tiles >= 2 && macs >= 2.5e10) ? 2 : 1;
+    const int items = (int)gs_ceil_div(p.co_tiles, cg) * p.ci_tiles * g->kh * g->kw;   // CTAs or CTA pairs
     static const int waves_x2 = getenv("GS_WGRAD_HALF_WAVES") ? atoi(getenv("GS_WGRAD_HALF_WAVES")) : 4;
-    int splitk = (int)gs_ceil_div((long long)waves_x2 * num_sms() / 2, items);
+    int splitk = (int)gs_ceil_div((long long)waves_x2 * (num_sms() / cg) / 2, items);
     if (splitk > p.chunks_total) splitk = p.chunks_total;
     if (splitk < 1) splitk = 1;
     // keep at least 8 pixel-chunks (512 pixels) per CTA so the fp32 atomics stay a small tail
@@ -876,11 +912,26 @@ static int launch_wgrad(const gs_conv_geom* g, const void* x, const void* dy, fl
     }
     static bool attr_set = false;
     if (!attr_set) {
-        GS_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+        GS_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<1>::kSmemBytes));
+        GS_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<2>::kSmemBytes));
         attr_set = true;
     }
-    dim3 grid(items, splitk);
-    wgrad_kernel<<<grid, kWgThreads, kWgSmemBytes, stream>>>(tmDY, tmX, p);
+    if (cg == 1) {
+        dim3 grid(items, splitk);
+        wgrad_kernel<1><<<grid, kWgThreads, WgCfg<1>::kSmemBytes, stream>>>(tmDY, tmX, p);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(items * 2, splitk);
+        cfg.blockDim = dim3(kWgThreads);
+        cfg.dynamicSmemBytes = WgCfg<2>::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        GS_CUDA_OK(cudaLaunchKernelEx(&cfg, wgrad_kernel<2>, tmDY, tmX, p));
+    }
     GS_LAUNCHED();
     return 0;
 }
