@@ -599,6 +599,56 @@ def _bias(conv, Co):
     return None if conv.bias is None else conv.bias[:Co]
 
 
+# ------------------------------------------------------------------------------------------------
+# weight gradients on a side stream
+# ------------------------------------------------------------------------------------------------
+# wgrad(L) needs only dy(L) and the saved input of layer L; nothing on the backward chain (dgrad(L) -> BN backward of
+# L-1 -> ...) waits for it.  It is therefore enqueued on a second stream, where the tensor-core kernel overlaps the
+# memory-bound BN-backward kernels of the following layers (they co-reside on the SMs: wgrad takes the shared memory,
+# the BN blocks only registers).  ONE join per backward pass, installed as an autograd final callback; the operands
+# are kept alive until then.  In a captured iteration the fork / join become parallel branches of the graph.
+WGRAD_STREAM = os.environ.get('GS_WGRAD_STREAM', '1') == '1'
+_side_streams = {}
+_side_state = {'pending': [], 'main': None, 'queued': False}
+
+
+def _side_stream(device):
+    st = _side_streams.get(device.index)
+    if st is None:
+        st = _side_streams[device.index] = torch.cuda.Stream(device=device)
+    return st
+
+
+def wgrad_join():
+    """Make the stream the backward pass ran on wait for the side-stream weight gradients (idempotent)."""
+    stt = _side_state
+    if stt['pending']:
+        dev = stt['pending'][0][1].device
+        (stt['main'] or torch.cuda.current_stream(dev)).wait_stream(_side_stream(dev))
+        stt['pending'].clear()
+    stt['queued'], stt['main'] = False, None
+
+
+def _wgrad_async(conv, a, dy, geom):
+    if not WGRAD_STREAM or PROFILE is not None or _lib.PROFILE_CALLS is not None:
+        conv_wgrad(conv, a, dy, geom)
+        return
+    stt = _side_state
+    main = torch.cuda.current_stream(dy.device)
+    if not stt['queued']:
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(wgrad_join)
+        except RuntimeError:          # not inside a backward pass: keep the plain stream order
+            conv_wgrad(conv, a, dy, geom)
+            return
+        stt['queued'], stt['main'] = True, main
+    side = _side_stream(dy.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        conv_wgrad(conv, a, dy, geom)
+    stt['pending'].append((a, dy))
+
+
 def cba_backward(rec, dz, need_dx=True, dx_add=None, pre_sums=None, fuse_prev=None):
     """Returns (dx, dres, sums_prev): gradient w.r.t. the conv input (None unless need_dx), w.r.t. the residual, and --
     when `fuse_prev` names the layer that produced the conv input -- that layer's BN-backward sums, computed by this
@@ -626,7 +676,7 @@ def cba_backward(rec, dz, need_dx=True, dx_add=None, pre_sums=None, fuse_prev=No
         if conv.bias is not None and conv.bias.requires_grad:
             s = bn_stats(dy)
             call('gs_bn_bwd_param', s.data_ptr(), C, None, _param_grad(conv.bias).data_ptr(), 1, st)
-    conv_wgrad(conv, rec.a, dy, rec.geom)
+    _wgrad_async(conv, rec.a, dy, rec.geom)
     dx, sums_prev = None, None
     if need_dx:
         if is_image_conv(conv):
