@@ -884,7 +884,7 @@ static int launch_wgrad(const gs_conv_geom* g, const void* x, const void* dy, fl
     const double macs = (double)g->N * g->Ho * g->Wo * g->Co * g->Ci * g->kh * g->kw;
     const int cg = (cg_env == 2 && p.co_tiles >= 2 && macs >= 2.5e10) ? 2 : 1;
     const int items = (int)gs_ceil_div(p.co_tiles, cg) * p.ci_tiles * g->kh * g->kw;   // CTAs or CTA pairs
-    static const int waves_x2 = getenv("GS_WGRAD_HALF_WAVES") ? atoi(getenv("GS_WGRAD_HALF_WAVES")) : 4;
+    static const int waves_x2 = getenv("GS_WGRAD_HALF_WAVES") ? atoi(getenv("GS_WGRAD_HALF_WAVES")) : 2;   // one wave: fewer split-K atomics; wgrad runs beside the BN kernels anyway
     int splitk = (int)gs_ceil_div((long long)waves_x2 * (num_sms() / cg) / 2, items);
     if (splitk > p.chunks_total) splitk = p.chunks_total;
     if (splitk < 1) splitk = 1;

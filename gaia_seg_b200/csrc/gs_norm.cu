@@ -434,7 +434,7 @@ using namespace gs;
 // Grid policy.  Every block of a REDUCING kernel ends with 2*C same-address fp64 atomics, and the L2 atomic units
 // serialise those (~8-17 ns per op and address, measured): the number of blocks is the dominant cost for these
 // 10-20 us kernels, so reductions use at most 2 blocks per SM with deep unrolling (>= 64 KB of loads in flight per SM).
-// Streaming (apply) kernels use up to 4 blocks per SM and at least 8 pixels per thread row so the per-channel
+// Streaming (apply) kernels use up to 3 blocks per SM and at least 12 pixels per thread row so the per-channel
 // prologue is amortised.
 static inline int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -446,7 +446,7 @@ static inline int reduce_grid(const ColMap& m, long long P) {
     return colmap_grid(m, P, ppt, 148 * per_sm);
 }
 static inline int stream_grid(const ColMap& m, long long P) {
-    static const int bps = env_int("GS_BN_STREAM_BLOCKS_PER_SM", 4), ppt = env_int("GS_BN_STREAM_PPT", 8);
+    static const int bps = env_int("GS_BN_STREAM_BLOCKS_PER_SM", 3), ppt = env_int("GS_BN_STREAM_PPT", 12);
     return colmap_grid(m, P, ppt, 148 * bps);
 }
 
