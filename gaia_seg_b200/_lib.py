@@ -84,6 +84,8 @@ PROTOTYPES = {
     'gs_ipc_close': (_I, [_P]),
     'gs_ipc_free': (_I, [_P]),
     'gs_syncbn_allreduce': (_I, [_P, _I, _P, _I, _I, _P, _P, _P, _P]),
+    'gs_comm_flags_bytes': (_L, []),
+    'gs_grad_allreduce': (_I, [_P, _L, _L, _P, _I, _I, _P, _P]),
     'gs_sgd_flat': (_I, [_P, _P, _P, _L, _P, _I, _P, _P]),
 }
 

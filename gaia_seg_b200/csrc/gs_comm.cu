@@ -115,9 +115,115 @@ __global__ void __launch_bounds__(kCommThreads) syncbn_allreduce_kernel(double* 
     if (tid == 0) *seq_dev = seq;
 }
 
+// ------------------------------------------------------------------------------------------------
+// gradient all-reduce over peer memory (replaces the NCCL all-reduce of the flat gradient buffer)
+// ------------------------------------------------------------------------------------------------
+// Every rank's flat fp32 gradient buffer is IPC-mapped by all peers.  Two-shot all-reduce of a range in three
+// stream-ordered launches (all capturable in a CUDA graph, sequence counter in device memory):
+//   1. barrier "ready":  my gradients of the range are complete (stream order) -> flag to every peer, wait for theirs;
+//   2. reduce + push:    rank r owns the r-th shard of the range: s = sum over ranks (fixed order, P2P 16-byte loads)
+//                        and stores s into EVERY rank's buffer (P2P stores) -- each element is touched by one rank only;
+//   3. barrier "done":   all shards have landed everywhere (and nobody reads my buffer any more).
+// Traffic per rank: (world-1)/world of the range read and written over NVLink, i.e. what a ring all-reduce moves, but
+// with every link busy at once (NVSwitch) and no host-side NCCL call.
+struct GradPtrs {
+    float* g[kCommMaxWorld];
+};
+struct FlagPtrs {
+    unsigned long long* f[kCommMaxWorld];   // per rank: [2 flag sets][kCommMaxWorld]
+};
+
+__global__ void peer_barrier_kernel(FlagPtrs flags, int rank, int world, unsigned long long* seq_dev, int set, int bump) {
+    const int tid = threadIdx.x;
+    const unsigned long long seq = *seq_dev + (bump ? 1ull : 0ull);
+    __syncthreads();
+    if (tid < world && tid != rank) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags.f[tid] + set * kCommMaxWorld + rank), "l"(seq) : "memory");
+        const unsigned long long* mine = flags.f[rank] + set * kCommMaxWorld + tid;
+        const unsigned long long t0 = gtimer();
+        unsigned int spins = 0;
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+            if ((++spins & 1023u) == 0 && gtimer() - t0 > 10000000000ull) {
+                printf("gaiaseg_b200: gradient all-reduce barrier timed out (rank %d waiting for rank %d, seq %llu)\n", rank,
+                       tid, seq);
+                __trap();
+            }
+        } while (v < seq);
+    }
+    __syncthreads();
+    if (tid == 0 && bump) *seq_dev = seq;
+}
+
+__device__ __forceinline__ float4 ld_f4_sys(const float4* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_f4_sys(float4* p, const float4& v) {
+    asm volatile("st.volatile.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(256) grad_reduce_push_kernel(GradPtrs ptrs, long long lo4, long long hi4, int world) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = lo4 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < hi4; i += stride) {
+        float4 v[kCommMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kCommMaxWorld; ++r)
+            if (r < world) v[r] = ld_f4_sys(reinterpret_cast<const float4*>(ptrs.g[r]) + i);
+        float4 s = v[0];
+#pragma unroll
+        for (int r = 1; r < kCommMaxWorld; ++r)
+            if (r < world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+#pragma unroll
+        for (int r = 0; r < kCommMaxWorld; ++r)
+            if (r < world) st_f4_sys(reinterpret_cast<float4*>(ptrs.g[r]) + i, s);
+    }
+    __threadfence_system();
+}
+
 }  // namespace gs
 
 using namespace gs;
+
+extern "C" int64_t gs_comm_flags_bytes(void) { return 2 * kCommMaxWorld * 8; }
+
+extern "C" int gs_grad_allreduce(const void* const* peer_grads, int64_t offset, int64_t count, const void* const* peer_flags,
+                                 int32_t rank, int32_t world, void* seq_dev, void* stream) {
+    GS_REQUIRE(peer_grads && peer_flags && seq_dev, "grad_allreduce: null pointer");
+    GS_REQUIRE(world >= 1 && world <= kCommMaxWorld && rank >= 0 && rank < world, "grad_allreduce: bad rank %d / world %d", rank,
+               world);
+    GS_REQUIRE(offset >= 0 && count >= 0 && offset % 4 == 0 && count % 4 == 0,
+               "grad_allreduce: offset / count must be multiples of 4 elements");
+    if (count == 0 || world == 1) return 0;
+    GradPtrs gp{};
+    FlagPtrs fp{};
+    for (int r = 0; r < world; ++r) {
+        GS_REQUIRE(peer_grads[r] && peer_flags[r], "grad_allreduce: buffers of rank %d are not mapped", r);
+        GS_REQUIRE((reinterpret_cast<uintptr_t>(peer_grads[r]) & 15) == 0, "grad_allreduce: gradient buffer not 16-byte aligned");
+        gp.g[r] = reinterpret_cast<float*>(const_cast<void*>(peer_grads[r]));
+        fp.f[r] = reinterpret_cast<unsigned long long*>(const_cast<void*>(peer_flags[r]));
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long* seq = reinterpret_cast<unsigned long long*>(seq_dev);
+    const long long n4 = count / 4, o4 = offset / 4;
+    const long long per = (n4 + world - 1) / world;
+    long long lo4 = o4 + per * rank, hi4 = lo4 + per;
+    if (lo4 > o4 + n4) lo4 = o4 + n4;
+    if (hi4 > o4 + n4) hi4 = o4 + n4;
+    peer_barrier_kernel<<<1, 32, 0, st>>>(fp, rank, world, seq, 0, 1);
+    if (hi4 > lo4) {
+        long long blocks = (hi4 - lo4 + 256 * 4 - 1) / (256 * 4);
+        const long long cap = static_cast<long long>(num_sms()) * 4;
+        if (blocks > cap) blocks = cap;
+        grad_reduce_push_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(gp, lo4, hi4, world);
+    }
+    peer_barrier_kernel<<<1, 32, 0, st>>>(fp, rank, world, seq, 1, 0);
+    GS_LAUNCHED();
+    return 0;
+}
 
 extern "C" int64_t gs_comm_inbox_bytes(int32_t world) {
     return static_cast<int64_t>(kCommSlots) * world * kCommSlotDoubles * static_cast<int64_t>(sizeof(ulonglong2));

@@ -449,6 +449,66 @@ class PeerExchange:
         return inst
 
 
+class _RawCuda:
+    """A raw device allocation presented through __cuda_array_interface__ (zero-copy torch.as_tensor)."""
+
+    def __init__(self, ptr, n, typestr='<f4'):
+        self.__cuda_array_interface__ = {'shape': (n,), 'typestr': typestr, 'data': (ptr, False), 'version': 2}
+
+
+class PeerGrad:
+    """Flat fp32 gradient buffer in IPC-shareable memory + the peer-memory all-reduce over it (gs_grad_allreduce):
+    every rank maps every other rank's buffer, a range is summed in three capturable launches (no NCCL call)."""
+
+    def __init__(self, numel, device, group=None):
+        lib = _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise GsError('PeerGrad: at most 8 ranks (one NVSwitch domain)')
+        self.numel = numel
+
+        def alloc(nbytes):
+            ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            _lib.check(lib.gs_ipc_alloc(nbytes, ctypes.byref(ptr), handle), 'gs_ipc_alloc')
+            return ptr.value, bytes(handle.raw)
+
+        gptr, gh = alloc(numel * 4)
+        fptr, fh = alloc(int(lib.gs_comm_flags_bytes()))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (gh, fh), group=group)
+        self.gptrs, self.fptrs = (ctypes.c_void_p * 8)(), (ctypes.c_void_p * 8)()
+        for r, (hg, hf) in enumerate(handles):
+            if r == self.rank:
+                self.gptrs[r], self.fptrs[r] = gptr, fptr
+            else:
+                pg, pf = ctypes.c_void_p(), ctypes.c_void_p()
+                _lib.check(lib.gs_ipc_open(ctypes.create_string_buffer(hg, 64), ctypes.byref(pg)), 'gs_ipc_open')
+                _lib.check(lib.gs_ipc_open(ctypes.create_string_buffer(hf, 64), ctypes.byref(pf)), 'gs_ipc_open')
+                self.gptrs[r], self.fptrs[r] = pg.value, pf.value
+        self.tensor = torch.as_tensor(_RawCuda(gptr, numel), device=device)     # zero-initialised by gs_ipc_alloc
+        self.seq = torch.zeros(1, dtype=torch.int64, device=device)
+        dist.barrier(group=group)
+
+    def all_reduce(self, offset=0, count=None):
+        count = self.numel - offset if count is None else count
+        call('gs_grad_allreduce', self.gptrs, offset, count, self.fptrs, self.rank, self.world, self.seq.data_ptr(), _stream())
+
+    @classmethod
+    def create(cls, numel, device, group=None):
+        """PeerGrad, or None when the job is single-rank / peer access is disabled or unavailable (then NCCL is used)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        if os.environ.get('GS_GRAD_PEER', '1') == '0' or not PeerExchange.get(group):
+            return None
+        try:
+            return cls(numel, device, group)
+        except Exception as e:
+            import warnings
+            warnings.warn(f'gaia_seg_b200: peer-memory gradient buffer unavailable ({e}); using NCCL all_reduce')
+            return None
+
+
 def stats_all_reduce(stats, group=None, dgamma=None, dbeta=None):
     """Sum the packed fp64 statistics over the SyncBN group (peer-memory kernel, NCCL as fallback).  `dgamma` / `dbeta`
     (device pointers or None): BN parameter gradients, incremented by the LOCAL sums before the exchange."""

@@ -161,7 +161,10 @@ class FlatParams:
             total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         self.total = total
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        # several ranks: the gradient buffer lives in IPC-shareable memory so that the all-reduce can run over NVLink
+        # peer memory (functional.PeerGrad); the ranks must construct FlatParams collectively
+        self.peer_grad = F_gs.PeerGrad.create(total, dev)
+        self.flat_g = self.peer_grad.tensor if self.peer_grad else torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_shadow = torch.empty(total, dtype=torch.bfloat16, device=dev)
         self.params, self.offsets = params, offs
         for p, o in zip(params, offs):
@@ -197,6 +200,9 @@ class FlatParams:
         optimizer's grad_scale).  One call per bucket over NVLink; no per-parameter hooks."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return 1
+        if self.peer_grad is not None and group is None:
+            self.peer_grad.all_reduce()          # three capturable launches over NVLink peer memory
+            return self.peer_grad.world
         n = bucket_bytes // 4
         for s in range(0, self.total, n):
             dist.all_reduce(self.flat_g[s:s + n], group=group)
@@ -375,7 +381,9 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         steps0 = self.opt._steps
-        tail_eager = w > 1     # the graph then holds forward + backward (+ the peer-memory SyncBN exchanges) only
+        # several ranks without the peer-memory gradient buffer: the graph holds forward + backward (+ the peer-memory
+        # SyncBN exchanges) only, the NCCL all-reduce and the optimizer launch stay eager
+        tail_eager = w > 1 and self.opt.flat.peer_grad is None
         mod = self._module()
         F_gs._touched_bns = []
         try:

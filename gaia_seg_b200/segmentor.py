@@ -149,8 +149,14 @@ class EncoderDecoder(nn.Module):
         vals.append(loss)
         stacked = torch.stack([v.detach().float() for v in vals])
         if reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            stacked = stacked / dist.get_world_size()
-            dist.all_reduce(stacked)
+            ex = F_gs.PeerExchange.get(None)
+            if ex:      # capturable peer-memory exchange (the same kernel as the SyncBN statistics)
+                s64 = stacked.double()
+                ex.all_reduce(s64)
+                stacked = (s64 / dist.get_world_size()).float()
+            else:
+                stacked = stacked / dist.get_world_size()
+                dist.all_reduce(stacked)
         return loss, LogVars(names, stacked)
 
     def train_step(self, data_batch, optimizer=None, **kwargs):

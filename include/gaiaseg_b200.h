@@ -263,6 +263,16 @@ int gs_ipc_free(void* dev_ptr);
 int gs_syncbn_allreduce(double* stats, int32_t n, const void* const* peer_inboxes, int32_t rank, int32_t world,
                         void* seq_dev, float* dgamma, float* dbeta, void* stream);
 
+/* Gradient all-reduce (sum) of grad[offset : offset + count] over peer memory: replaces the bucketed NCCL all-reduce
+ * MMDistributedDataParallel issues during backward (gaiaseg/apis/train.py:88-95).  peer_grads[r] = rank r's flat fp32
+ * gradient buffer (gs_ipc_alloc'ed, mapped by everybody), peer_flags[r] = rank r's gs_comm_flags_bytes() flag area
+ * (zero-initialised).  Three stream-ordered launches: barrier "ready" -> every rank sums its shard of the range over all
+ * ranks (P2P loads, fixed order) and stores the result into every rank's buffer (P2P stores) -> barrier "done".
+ * CUDA-graph safe (device-resident sequence counter), bounded spins.  offset / count in elements, multiples of 4. */
+int64_t gs_comm_flags_bytes(void);
+int gs_grad_allreduce(const void* const* peer_grads, int64_t offset, int64_t count, const void* const* peer_flags,
+                      int32_t rank, int32_t world, void* seq_dev, void* stream);
+
 /* ---- optimizer ---------------------------------------------------------- */
 /* SGD(momentum, weight decay) over the FLAT fp32 master buffer (all parameters back to back, each padded
  * to a multiple of 64 elements) + refresh of the flat bf16 shadow at the same indices:
