@@ -680,33 +680,57 @@ def _side_stream(device):
 
 
 def wgrad_join():
-    """Make the stream the backward pass ran on wait for the side-stream weight gradients (idempotent)."""
+    """Make the stream the backward pass ran on wait for the side-stream work (idempotent)."""
     stt = _side_state
     if stt['pending']:
-        dev = stt['pending'][0][1].device
+        dev = stt['pending'][0][0]
         (stt['main'] or torch.cuda.current_stream(dev)).wait_stream(_side_stream(dev))
         stt['pending'].clear()
     stt['queued'], stt['main'] = False, None
+
+
+def side_stream_run(fn, device, keep=()):
+    """Run `fn()` on the side stream, ordered after everything enqueued so far on the current stream; the current
+    stream re-joins at the end of the running backward pass.  Outside a backward pass `fn` simply runs in stream order.
+    `keep`: objects that must stay alive until the join (operands of the side-stream kernels)."""
+    stt = _side_state
+    main = torch.cuda.current_stream(device)
+    if not stt['queued']:
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(wgrad_join)
+        except RuntimeError:          # not inside a backward pass: keep the plain stream order
+            fn()
+            return False
+        stt['queued'], stt['main'] = True, main
+    side = _side_stream(device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        fn()
+    stt['pending'].append((device, keep))
+    return True
 
 
 def _wgrad_async(conv, a, dy, geom):
     if not WGRAD_STREAM or PROFILE is not None or _lib.PROFILE_CALLS is not None:
         conv_wgrad(conv, a, dy, geom)
         return
-    stt = _side_state
-    main = torch.cuda.current_stream(dy.device)
-    if not stt['queued']:
-        try:
-            torch.autograd.Variable._execution_engine.queue_callback(wgrad_join)
-        except RuntimeError:          # not inside a backward pass: keep the plain stream order
-            conv_wgrad(conv, a, dy, geom)
-            return
-        stt['queued'], stt['main'] = True, main
-    side = _side_stream(dy.device)
-    side.wait_stream(main)
-    with torch.cuda.stream(side):
-        conv_wgrad(conv, a, dy, geom)
-    stt['pending'].append((a, dy))
+    side_stream_run(lambda: conv_wgrad(conv, a, dy, geom), dy.device, keep=(a, dy))
+
+
+# Gradient chunks: set by runner.FlatParams when the gradient buffer is peer-mapped.  Called with the flat offset of the
+# first parameter of a res stage once that stage's backward has been enqueued: every gradient at or beyond that offset
+# is final (later layers ran their backward earlier), so its all-reduce can start on the side stream while the earlier
+# stages are still in their backward pass.
+grad_chunk_hook = None
+
+
+def _stage_grads_done(blocks):
+    if grad_chunk_hook is None or PROFILE is not None or _lib.PROFILE_CALLS is not None:
+        return
+    offs = [getattr(p, '_gs_flat_off', None) for p in blocks[0].parameters()]
+    offs = [o for o in offs if o is not None]
+    if offs:
+        grad_chunk_hook(min(offs))
 
 
 def cba_backward(rec, dz, need_dx=True, dx_add=None, pre_sums=None, fuse_prev=None):
@@ -826,6 +850,7 @@ class StageFn(torch.autograd.Function):
             x, r = _bottleneck_forward(x, blk, save)
             recs.append(r)
         ctx.recs = recs
+        ctx.blocks = blocks
         return x
 
     @staticmethod
@@ -837,6 +862,7 @@ class StageFn(torch.autograd.Function):
             prev_r3 = recs[b - 1][2] if b > 0 else None
             need = ctx.needs_input_grad[0] or b > 0
             d, carry = _bottleneck_backward(recs[b], d, need, pre_sums=carry, prev_r3=prev_r3)
+        _stage_grads_done(ctx.blocks)
         return d, None, None
 
 

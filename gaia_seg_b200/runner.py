@@ -179,6 +179,7 @@ class FlatParams:
             vp.copy_(p.data)
             p.data = vp
             p.grad = vg
+            p._gs_flat_off = o
         self.convs = []
         off_of = {id(p): o for p, o in zip(params, offs)}
         for m in model.modules():
@@ -192,8 +193,25 @@ class FlatParams:
             F_gs.conv_shadows(m)
         self.image_convs = [m for m in self.convs if F_gs.is_image_conv(m)]
 
+        # overlapped all-reduce: gradients at offsets >= _reduced_from have already been summed over the ranks by a
+        # side-stream chunk during the backward pass (functional.grad_chunk_hook)
+        self._reduced_from = total
+        if self.peer_grad is not None and os.environ.get('GS_GRAD_OVERLAP', '1') != '0':
+            F_gs.grad_chunk_hook = self._reduce_chunk
+
+    def _reduce_chunk(self, off):
+        """All-reduce [off, _reduced_from) on the side stream (every gradient in that range is final)."""
+        hi = self._reduced_from
+        if off >= hi:
+            return
+        pg = self.peer_grad
+        if F_gs.side_stream_run(lambda: pg.all_reduce(off, hi - off), self.flat_g.device):
+            self._reduced_from = off
+
     def zero_grad(self):
+        """Contract of one iteration: zero_grad() -> ONE backward pass -> all_reduce_grads() -> optimizer step."""
         self.flat_g.zero_()
+        self._reduced_from = self.total
 
     def all_reduce_grads(self, group=None, bucket_bytes=64 << 20):
         """Sum the flat gradient over the data-parallel group in NCCL buckets (the mean is folded into the
@@ -201,7 +219,11 @@ class FlatParams:
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return 1
         if self.peer_grad is not None and group is None:
-            self.peer_grad.all_reduce()          # three capturable launches over NVLink peer memory
+            # three capturable launches over NVLink peer memory; the chunks beyond _reduced_from were done during backward
+            F_gs.wgrad_join()
+            if self._reduced_from > 0:
+                self.peer_grad.all_reduce(0, self._reduced_from)
+            self._reduced_from = self.total
             return self.peer_grad.world
         n = bucket_bytes // 4
         for s in range(0, self.total, n):
