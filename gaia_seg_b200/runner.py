@@ -343,7 +343,7 @@ class GraphedTrainStep:
         """arch_key: hashable id of the currently applied sub-net (e.g. json.dumps(meta['arch'], sort_keys=True))."""
         first = self.stream is None
         if first:
-            self.stream = torch.cuda.Stream()
+            self.stream = torch.cuda.Stream(priority=int(os.environ.get("GS_MAIN_STREAM_PRIORITY", "-1")))
         cur = torch.cuda.current_stream()
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
@@ -554,6 +554,8 @@ class OptimizerHook(Hook):
             raise NotImplementedError('grad_clip is not used by the GAIA-seg recipe')
 
     def after_train_iter(self, runner):
+        if getattr(runner, '_step_done', False):     # GraphedTrainStep already ran backward + all-reduce + step
+            return
         opt = runner.optimizer
         opt.zero_grad()
         runner.outputs['loss'].backward()
@@ -599,11 +601,15 @@ class TextLoggerHook(Hook):
 
 
 class IterBasedRunner:
-    """mmcv IterBasedRunner for the single ('train', 1) workflow of the reference config."""
+    """mmcv IterBasedRunner for the single ('train', 1) workflow of the reference config.  `graph_replay` (default on,
+    `runner=dict(type='IterBasedRunner', graph_replay=False)` to disable): iterations run through GraphedTrainStep, so
+    sub-nets that recur (the anchors of the sampler, the single arch of a finetune) are replayed as CUDA graphs."""
 
-    def __init__(self, model, optimizer=None, work_dir=None, logger=None, meta=None, max_iters=None, **kw):
+    def __init__(self, model, optimizer=None, work_dir=None, logger=None, meta=None, max_iters=None, graph_replay=True,
+                 **kw):
         self.model, self.optimizer, self.work_dir, self.logger, self.meta = model, optimizer, work_dir, logger, meta
         self.max_iters = max_iters
+        self.graph_replay, self._graphed, self._step_done = graph_replay, None, False
         self.iter = 0
         self.hooks = []
         self.outputs = None
@@ -634,6 +640,15 @@ class IterBasedRunner:
         for h in self.hooks:
             getattr(h, name, lambda r: None)(self)
 
+    def _arch_key(self):
+        """Identity of the sub-net the ManipulateArchHook applied for this iteration (graph cache key)."""
+        import json
+        for h in self.hooks:
+            meta = getattr(h, 'last_meta', None)
+            if meta is not None:
+                return json.dumps(meta.get('arch', meta), sort_keys=True, default=str)
+        return 'fixed-arch'
+
     def load_checkpoint(self, filename, map_location='cpu', strict=False):
         return load_checkpoint(self.model, filename, map_location, strict)
 
@@ -658,7 +673,14 @@ class IterBasedRunner:
                 data_batch = next(it)
             self.call_hook('before_train_iter')
             data_batch = scatter_batch(data_batch)
-            self.outputs = self.model.train_step(data_batch, self.optimizer)
+            if self.graph_replay and isinstance(self.optimizer, GsSGD):
+                if self._graphed is None:
+                    self._graphed = GraphedTrainStep(self.model, self.optimizer)
+                self.outputs = self._graphed(self._arch_key(), data_batch)
+                self._step_done = True
+            else:
+                self.outputs = self.model.train_step(data_batch, self.optimizer)
+                self._step_done = False
             self.call_hook('after_train_iter')
             self.iter += 1
         self.call_hook('after_run')
