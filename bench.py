@@ -434,8 +434,20 @@ def main():
         ig_ms = agg.get('fwd', [0, 0, 0])[1] + agg.get('dgrad', [0, 0, 0])[1]
         ig_n = agg.get('fwd', [0, 0, 0])[2] + agg.get('dgrad', [0, 0, 0])[2]
         ach = ig_f / (ig_ms * 1e-3) / 1e12 if ig_ms > 0 else 0.0
+        # DRAM bytes per conv launch (dram__bytes_read.sum + dram__bytes_write.sum) come from the committed ncu capture
+        # of the same kernels (bench.py cannot run under ncu itself): newest profiles/r*_igemm_dram_traffic.json
+        traffic, traffic_src = None, None
+        import glob
+        cand = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_igemm_dram_traffic.json')))
+        if cand:
+            try:
+                traffic = float(json.load(open(cand[-1]))['dram_bytes_per_launch'])
+                traffic_src = os.path.relpath(cand[-1], ROOT)
+            except Exception:
+                traffic = None
         roof = {'bound': 'tensor', 'kernel': 'gs::igemm_kernel (conv fwd + dgrad)', 'achieved': ach, 'peak': peak_tf,
-                'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': traffic, 'traffic_source': traffic_src,
+                'peak_source': peak_src,
                 'launches': ig_n, 'avg_launch_ms': ig_ms / max(ig_n, 1), 'flops_per_launch': ig_f / max(ig_n, 1)}
         breakdown = {k: {'tflops': v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0, 'ms': v[1], 'launches': v[2],
                          'share_of_step': v[1] / cyc_ms} for k, v in agg.items()}
