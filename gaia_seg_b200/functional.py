@@ -342,18 +342,8 @@ def conv_wgrad(conv, a, dy, g):
         _timed_call('wgrad', g, fn, ctypes.byref(g), a.data_ptr(), dy.data_ptr(), gw.data_ptr(), st)
 
 
-# Round-1 experiment, removed from the kernel: BN-backward sums in the dgrad epilogue (include/gaiaseg_b200.h, gs_bn_bwd_fuse).
-FUSE_BN_REDUCE = False
-
-
-def _fusable(prev):
-    """Can the BN-backward reduction of layer `prev` ride in the epilogue of the dgrad that produces its dz?"""
-    return FUSE_BN_REDUCE and prev is not None and prev.mode == 'bn_batch' and CONV_IMPL == 'tc' and PROFILE is None
-
-
-def conv_dgrad(conv, dy, g, x_shape, add=None, fuse_prev=None):
-    """dx = conv_transpose(dy, W[:Co, :Ci]) (+ add).  With `fuse_prev` (the LayerRec of the conv+BN layer that produced
-    this conv's input) the dgrad epilogue also accumulates that layer's BN-backward sums; returns (dx, sums | None)."""
+def conv_dgrad(conv, dy, g, x_shape, add=None):
+    """dx = conv_transpose(dy, W[:Co, :Ci]) (+ add): the residual gradient `add` is summed in the dgrad epilogue."""
     krsc = conv_shadows(conv)
     N, Ci, H, W = x_shape
     dx = new_act(N, Ci, H, W, dy.device)
@@ -364,26 +354,17 @@ def conv_dgrad(conv, dy, g, x_shape, add=None, fuse_prev=None):
         add = as_act(add)
         add_ld = act_ld(add)
     st = _stream()
-    sums = None
     if CONV_IMPL == 'tc':
         ws = None
         nbytes = _lib.load().gs_conv2d_dgrad_workspace_bytes(ctypes.byref(g))
         if nbytes > 0:
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dy.device)
-        fuse = None
-        if _fusable(fuse_prev):
-            pr = fuse_prev
-            sums = zeros_f64(2 * Ci, dy.device)
-            zm = pr.z if (pr.relu and pr.has_res) else None
-            fs = _lib.BnBwdFuse(pr.y.data_ptr(), act_ld(pr.y), _ptr(zm), act_ld(zm) if zm is not None else 0,
-                                pr.aff.data_ptr(), 1 if pr.relu else 0, sums.data_ptr())
-            fuse = ctypes.byref(fs)
         _timed_call('dgrad', g, 'gs_conv2d_dgrad', ctypes.byref(g), dy.data_ptr(), krsc.data_ptr(), dx.data_ptr(),
-                    _ptr(add), add_ld, _ptr(ws), fuse, st)
+                    _ptr(add), add_ld, _ptr(ws), None, st)
     else:
         _timed_call('dgrad', g, 'gs_conv2d_dgrad_simt', ctypes.byref(g), dy.data_ptr(), krsc.data_ptr(), dx.data_ptr(),
                     _ptr(add), add_ld, st)
-    return dx, sums
+    return dx
 
 
 # ------------------------------------------------------------------------------------------------
@@ -558,19 +539,16 @@ def bn_train_apply(bn, y, stats, C, residual=None, relu=False):
     return z, aff, count
 
 
-def bn_backward(bn, dz, y, aff, count, zmask, relu, want_dres, pre_sums=None):
-    """Per-channel sums (own kernel, or already produced by the dgrad epilogue that wrote dz: `pre_sums`), all-reduce
-    over the SyncBN group, then ONE kernel for dy (+ dres, + parameter grads)."""
+def bn_backward(bn, dz, y, aff, count, zmask, relu, want_dres):
+    """Per-channel sums (one reduction kernel), all-reduce over the SyncBN group, then ONE kernel for dy (+ dres,
+    + parameter grads)."""
     N, C, H, W = dz.shape
     P, dev, st = N * H * W, dz.device, _stream()
     mean, invstd, scale, shift = aff[0], aff[1], aff[2], aff[3]
     zl = act_ld(zmask) if zmask is not None else 0
-    if pre_sums is not None:
-        sums = pre_sums
-    else:
-        sums = zeros_f64(2 * C, dev)
-        call('gs_bn_bwd_reduce', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),
-             invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, P, C, sums.data_ptr(), st)
+    sums = zeros_f64(2 * C, dev)
+    call('gs_bn_bwd_reduce', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),
+         invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, P, C, sums.data_ptr(), st)
     gw = bn.weight is not None and bn.weight.requires_grad
     gb = bn.bias is not None and bn.bias.requires_grad
     dgam = _param_grad(bn.weight).data_ptr() if gw else None
@@ -733,10 +711,9 @@ def _stage_grads_done(blocks):
         grad_chunk_hook(min(offs))
 
 
-def cba_backward(rec, dz, need_dx=True, dx_add=None, pre_sums=None, fuse_prev=None):
-    """Returns (dx, dres, sums_prev): gradient w.r.t. the conv input (None unless need_dx), w.r.t. the residual, and --
-    when `fuse_prev` names the layer that produced the conv input -- that layer's BN-backward sums, computed by this
-    layer's dgrad epilogue.  `pre_sums`: this layer's own sums if an earlier dgrad already produced them."""
+def cba_backward(rec, dz, need_dx=True, dx_add=None):
+    """Returns (dx, dres): gradient w.r.t. the conv input (None unless need_dx; `dx_add` is summed in the dgrad
+    epilogue) and w.r.t. the residual."""
     dz = as_act(dz)
     conv, bn, C = rec.conv, rec.bn, rec.Co
     N, _, Ho, Wo = dz.shape
@@ -746,8 +723,7 @@ def cba_backward(rec, dz, need_dx=True, dx_add=None, pre_sums=None, fuse_prev=No
     zmask = rec.z if rec.relu else None
     if rec.mode == 'bn_batch':
         # without a residual the ReLU mask is recomputed from y (one tensor read less than reading z)
-        dy, dres = bn_backward(bn, dz, rec.y, rec.aff, rec.count, zmask if rec.has_res else None, rec.relu, rec.has_res,
-                               pre_sums=pre_sums)
+        dy, dres = bn_backward(bn, dz, rec.y, rec.aff, rec.count, zmask if rec.has_res else None, rec.relu, rec.has_res)
     else:
         dres = new_act(N, C, Ho, Wo, dev) if rec.has_res else None
         scale = rec.aff[0] if rec.mode == 'affine' else None
@@ -761,12 +737,12 @@ def cba_backward(rec, dz, need_dx=True, dx_add=None, pre_sums=None, fuse_prev=No
             s = bn_stats(dy)
             call('gs_bn_bwd_param', s.data_ptr(), C, None, _param_grad(conv.bias).data_ptr(), 1, st)
     _wgrad_async(conv, rec.a, dy, rec.geom)
-    dx, sums_prev = None, None
+    dx = None
     if need_dx:
         if is_image_conv(conv):
             raise GsError('gradient w.r.t. the input image is not provided by the hot path')
-        dx, sums_prev = conv_dgrad(conv, dy, rec.geom, rec.x_shape, add=dx_add, fuse_prev=fuse_prev)
-    return dx, dres, sums_prev
+        dx = conv_dgrad(conv, dy, rec.geom, rec.x_shape, add=dx_add)
+    return dx, dres
 
 
 # ------------------------------------------------------------------------------------------------
@@ -785,7 +761,7 @@ class ConvBnActFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dz):
-        dx, dres, _ = cba_backward(ctx.rec, dz, need_dx=ctx.needs_input_grad[0])
+        dx, dres = cba_backward(ctx.rec, dz, need_dx=ctx.needs_input_grad[0])
         ctx.rec = None
         return dx, dres, None, None, None, None, None
 
@@ -806,7 +782,7 @@ class BottleneckFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         recs, ctx.recs = ctx.recs, None
-        dx, _ = _bottleneck_backward(recs, dout, ctx.needs_input_grad[0])
+        dx = _bottleneck_backward(recs, dout, ctx.needs_input_grad[0])
         return dx, None, None
 
 
@@ -821,26 +797,26 @@ def _bottleneck_forward(x, block, save):
     return z3, (r1, r2, r3, rd)
 
 
-def _bottleneck_backward(recs, dout, need_dx=True, pre_sums=None, prev_r3=None):
-    """Hand-written backward of one bottleneck.  Every dgrad also reduces the BN-backward sums of the layer below it
-    (conv3 -> bn2, conv2 -> bn1, conv1 -> bn3 of the PREVIOUS block when `prev_r3` is given), so only the first BN
-    reached from outside runs a reduction kernel of its own.  Returns (dx, sums for prev_r3)."""
+def _bottleneck_backward(recs, dout, need_dx=True):
+    """Hand-written backward of one bottleneck: the residual gradient (through the downsample branch when there is one)
+    is added inside conv1's dgrad epilogue.  Returns dx."""
     r1, r2, r3, rd = recs
-    d2, dres, s2 = cba_backward(r3, dout, pre_sums=pre_sums, fuse_prev=r2)
-    d1, _, s1 = cba_backward(r2, d2, pre_sums=s2, fuse_prev=r1)
+    d2, dres = cba_backward(r3, dout)
+    d1, _ = cba_backward(r2, d2)
     add = dres
     if rd is not None:
-        add, _, _ = cba_backward(rd, dres)
+        add, _ = cba_backward(rd, dres)
     if not need_dx:
-        cba_backward(r1, d1, need_dx=False, pre_sums=s1)
-        return None, None
-    dx, _, carry = cba_backward(r1, d1, dx_add=add, pre_sums=s1, fuse_prev=prev_r3)
-    return dx, carry
+        cba_backward(r1, d1, need_dx=False)
+        return None
+    dx, _ = cba_backward(r1, d1, dx_add=add)
+    return dx
 
 
 class StageFn(torch.autograd.Function):
-    """DynamicResLayer.forward (the first `depth` blocks of a stage) as ONE autograd node, so that the backward can
-    chain the fused BN reductions across block boundaries."""
+    """DynamicResLayer.forward (the first `depth` blocks of a stage) as ONE autograd node: ~10x fewer autograd nodes
+    than one per layer, and the end of its backward is where the gradients of the stage (and of everything after it)
+    are final -> start of their all-reduce chunk."""
 
     @staticmethod
     def forward(ctx, x, weight, blocks):
@@ -856,12 +832,9 @@ class StageFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         recs, ctx.recs = ctx.recs, None
-        carry = None
         d = dout
         for b in range(len(recs) - 1, -1, -1):
-            prev_r3 = recs[b - 1][2] if b > 0 else None
-            need = ctx.needs_input_grad[0] or b > 0
-            d, carry = _bottleneck_backward(recs[b], d, need, pre_sums=carry, prev_r3=prev_r3)
+            d = _bottleneck_backward(recs[b], d, ctx.needs_input_grad[0] or b > 0)
         _stage_grads_done(ctx.blocks)
         return d, None, None
 
@@ -986,7 +959,7 @@ class ConvSegFn(torch.autograd.Function):
         dy = new_act(N, K, h, w, dl.device, BF16, ld=Kp)
         call('gs_cast_f32_bf16', dl.data_ptr(), act_ld(dl), dy.data_ptr(), Kp, P, K, st)
         conv_wgrad(conv, ctx.a, dy, ctx.g)
-        dx = conv_dgrad(conv, dy, ctx.g, ctx.xs)[0] if ctx.needs_input_grad[0] else None
+        dx = conv_dgrad(conv, dy, ctx.g, ctx.xs) if ctx.needs_input_grad[0] else None
         ctx.a = None
         return dx, None, None, None, None
 

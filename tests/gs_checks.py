@@ -189,7 +189,7 @@ def conv_case_checks(case, gs, impl=None):
         st_ref = torch.cat([yr.sum((0, 2, 3)), (yr * yr).sum((0, 2, 3))])
         out.append(check_f32(stats, st_ref, tag + '.stats', 1e-4))
         dya = Fg.as_act(dy.to(dev))
-        dx, _ = Fg.conv_dgrad(conv, dya, geom, tuple(x.shape))
+        dx = Fg.conv_dgrad(conv, dya, geom, tuple(x.shape))
         torch.cuda.synchronize()
         out.append(check_bf16(dx.float(), xd.grad, tag + '.dgrad'))
         conv.weight.grad = None

@@ -50,7 +50,7 @@ def main():
             'fwd_stats': lambda: Fg.conv_forward(x, conv, Co, want_stats=True),
             'fwd_plain': lambda: Fg.conv_forward(x, conv, Co),
             'fwd_relu_res': lambda: Fg.conv_forward(x, conv, Co, relu=True, residual=y),
-            'dgrad': lambda: Fg.conv_dgrad(conv, dy, g, tuple(x.shape))[0],
+            'dgrad': lambda: Fg.conv_dgrad(conv, dy, g, tuple(x.shape)),
             'dgrad_add': lambda: Fg.conv_dgrad(conv, dy, g, tuple(x.shape), add=res),
             'wgrad': lambda: Fg.conv_wgrad(conv, a, dy, g),
         }
