@@ -38,6 +38,7 @@ sandwich = True
 max_net, min_net, sample_subnet_num = MAX, MIN, 2
 train_sampler = None          # built from (max_net, min_net, random_subnet) because sandwich = True
 val_sampler = dict(type='anchor', anchors=[R50, R101])
+flops_sampler = dict(type='anchor', anchors=[MAX, MIN, R50, R101])   # tools/count_flops.py
 
 data = dict(samples_per_gpu=2, workers_per_gpu=2,
             train=dict(type='SyntheticSegDataset', size=(512, 1024), num_classes=19, length=256),

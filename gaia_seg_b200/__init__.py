@@ -20,6 +20,7 @@ from .model_space import (MODEL_SAMPLERS, ManipulateArchHook, ModelSpaceManager,
                           build_model_sampler, fold_dict, sandwich_sampler_cfg, unfold_dict)
 from .runner import (Config, FlatParams, GraphedTrainStep, GsDataParallel, GsSGD, IterBasedRunner, build_optimizer, build_runner,
                      get_dist_info, init_dist, load_checkpoint, reserve_activation_pool, save_checkpoint, scatter_batch)
+from .complexity import conv_macs, get_model_complexity_info
 from .apis import (DATASETS, CrossArchEvalHook, DistCrossArchEvalHook, SyntheticSegDataset, build_dataloader,
                    build_dataset, multi_gpu_test, set_random_seed, single_gpu_test, train_segmentor)
 

@@ -197,3 +197,61 @@ def test_model_space_manager_roundtrip(gs, tmp_path):
     from gaia_seg_b200.model_space import eval_rule
     ms.ms_manager.apply_rule(eval_rule("lambda m: m['overhead.flops'] >= 2e9"))
     assert len(ms.pack()) == 3
+
+
+@pytest.mark.parametrize('kw', [dict(aux=True, deep_stem=True, os8=True), dict(psp=True, aux=True, os8=True),
+                                dict(aspp=True, os8=True), dict()], ids=['fcn_os8', 'psp', 'aspp', 'fcn_os32'])
+def test_analytic_complexity_equals_hooked_conv_macs_of_the_oracle(gs, kw):
+    """tools/count_flops.py replacement: shapes propagated analytically must give the conv MACs a hook-based counter
+    measures on the oracle's real forward pass, for every head type and several sub-nets."""
+    from gaia_seg_b200.complexity import conv_macs, get_model_complexity_info
+    cfg = C.small_cfg(**kw)
+    m = gs.build_segmentor(cfg, train_cfg=dict(), test_cfg=dict(mode='whole'))
+    o = O.build_segmentor(cfg)
+    o.eval()
+    H, W = 64, 96
+    for name in ('max', 'min', 'mid'):
+        arch = {'backbone': dict(C.SMALL_ARCHS[name]['backbone'])}
+        if kw.get('deep_stem'):
+            w = arch['backbone']['stem']['width']
+            arch['backbone'] = dict(arch['backbone'], stem={'width': [w // 2, w // 2, w]})
+        m.manipulate_arch(arch)
+        o.manipulate_arch(arch)
+        macs = [0]
+
+        def hook(mod, inp, out):
+            kh, kw_ = mod.kernel_size
+            macs[0] += out.numel() // out.shape[0] * inp[0].shape[1] * kh * kw_
+
+        hs = [c.register_forward_hook(hook) for c in o.modules() if isinstance(c, torch.nn.Conv2d)]
+        with torch.no_grad():
+            feats = o.backbone(torch.zeros(1, 3, H, W))
+            bb_macs = macs[0]
+            o.decode_head(feats)
+        for h in hs:
+            h.remove()
+        assert conv_macs(m, (3, H, W), only_backbone=True) == bb_macs
+        assert conv_macs(m, (3, H, W)) == macs[0]
+        flops, params = get_model_complexity_info(m, (3, H, W))
+        assert flops > macs[0] and 0 < params <= sum(p.numel() for p in m.parameters())
+    # the MAX sub-net uses every backbone / decode-head parameter
+    m.manipulate_arch(C.SMALL_ARCHS['max'] if not kw.get('deep_stem') else
+                      {'backbone': dict(C.SMALL_ARCHS['max']['backbone'], stem={'width': [16, 16, 32]})})
+    _, params = get_model_complexity_info(m, (3, H, W))
+    full = sum(p.numel() for n, p in m.named_parameters() if not n.startswith('auxiliary_head'))
+    assert params == full
+
+
+def test_analytic_macs_reproduce_the_survey_figures(gs):
+    """conv MACs per 512x1024 image of the BASELINE supernet (backbone + FCN head): OS32 MAX 176.6 G /
+    MIN 27.1 G (plain 7x7 stem); OS8 V1c MAX 938.3 G / MIN 237.1 G plus the deep stem (+2.5 G at full width)."""
+    import bench
+    from gaia_seg_b200.complexity import conv_macs
+    want = {('os32', 'MAX'): 176.6, ('os32', 'MIN'): 27.1, ('os8', 'MAX'): 938.3 + 2.5, ('os8', 'MIN'): 237.1 + 0.4}
+    for v in ('os32', 'os8'):
+        m = gs.build_segmentor(bench.supernet_cfg(v), train_cfg=dict(), test_cfg=dict(mode='whole'))
+        MAX, MIN, _ = bench.sampler_cfg(v)
+        for a in (MAX, MIN):
+            m.manipulate_arch(gs.fold_dict(a)['arch'])
+            got = conv_macs(m, (3, 512, 1024)) / 1e9
+            assert abs(got - want[(v, a['name'])]) <= 0.15, (v, a['name'], got)
