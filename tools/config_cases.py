@@ -122,9 +122,9 @@ def config3(dev):
                                     '2x3x512x1024, 19 classes'}
     for name, arch in (('R101', R101), ('MAX', MAX)):
         model.manipulate_arch(arch)
-        # KNOWN ISSUE (round 1): capturing the FULL-SIZE ASPP model fails with cudaErrorStreamCaptureIsolation in the
-        # autograd engine's end-of-backward stream sync (the small ASPP model of tests/ captures fine, tools/graph_repro.py):
-        # config 3 is therefore timed eagerly (runner: `runner=dict(type='IterBasedRunner', graph_replay=False)`)
+        # open item (round 1): inside THIS script the capture of config 3 trips cudaErrorStreamCaptureIsolation in the autograd
+        # engine's end-of-backward stream sync; the same model / sub-net / size captures fine on its own
+        # (tools/graph_fullsize.py), so config 3 is timed eagerly here
         step = train_fn(model, opt, data, key=name, graph=False)
         ms = timed(step, 5, 3)
         out = step()
