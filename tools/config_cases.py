@@ -125,7 +125,7 @@ def config3(dev):
         # open item (round 1): inside THIS script the capture of config 3 trips cudaErrorStreamCaptureIsolation in the autograd
         # engine's end-of-backward stream sync; the same model / sub-net / size captures fine on its own
         # (tools/graph_fullsize.py), so config 3 is timed eagerly here
-        step = train_fn(model, opt, data, key=name, graph=False)
+        step = train_fn(model, opt, data, key=name, graph=os.environ.get('CONFIG3_GRAPH', '0') == '1')
         ms = timed(step, 5, 3)
         out = step()
         res[name] = dict(ms_per_step=round(ms, 2), imgs_per_s=round(2e3 / ms, 1), loss=float(out['loss']),
@@ -210,14 +210,12 @@ def main():
     which = [int(a) for a in sys.argv[1:]] or [1, 3, 4, 5]
     gs._lib.require_device()
     dev = torch.device('cuda', 0)
-    gs.reserve_activation_pool(48, dev)
     out = []
     for c in which:
         r = {1: config1, 3: config3, 4: config4, 5: config5}[c](dev)
         print(json.dumps({k: v for k, v in r.items() if k != 'subnets'}), flush=True)
         out.append(r)
         torch.cuda.empty_cache()
-        gs.reserve_activation_pool(48, dev)
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'config_cases.json'), 'w'), indent=1)
 
