@@ -23,11 +23,13 @@ for name in sys.argv[1:] or ['psp', 'aspp']:
     try:
         cfg = bench.supernet_cfg('os8')
         cfg['decode_head'] = heads[name]
+        if os.environ.get('SEED'):
+            gs.set_random_seed(int(os.environ['SEED']))
         model = gs.build_segmentor(cfg, train_cfg=dict(), test_cfg=dict(mode='whole')).to(dev).train()
         opt = gs.GsSGD(model, lr=0.01, momentum=0.9, weight_decay=5e-4)
         model.manipulate_arch(MIN)
         data = batch(2, 512, 1024, 19, dev, 3)
-        st = gs.GraphedTrainStep(model, opt, graph_after=2, max_graphs=2, pool_gb=8)
+        st = gs.GraphedTrainStep(model, opt, graph_after=2, max_graphs=2, pool_gb=float(os.environ.get('POOL', '8')))
         for it in range(5):
             out = st('min', data)
         torch.cuda.synchronize()
