@@ -695,20 +695,24 @@ def _wgrad_async(conv, a, dy, geom):
     side_stream_run(lambda: conv_wgrad(conv, a, dy, geom), dy.device, keep=(a, dy))
 
 
-# Gradient chunks: set by runner.FlatParams when the gradient buffer is peer-mapped.  Called with the flat offset of the
-# first parameter of a res stage once that stage's backward has been enqueued: every gradient at or beyond that offset
-# is final (later layers ran their backward earlier), so its all-reduce can start on the side stream while the earlier
-# stages are still in their backward pass.
-grad_chunk_hook = None
-
-
+# Gradient chunks: runner.FlatParams tags every parameter it owns with its flat offset and (when the gradient buffer is
+# peer-mapped and overlap is enabled) a weak reference to itself.  Once a res stage's backward has been enqueued, every
+# gradient at or beyond the offset of the stage's first parameter is final (later layers ran their backward earlier), so
+# the owner can start the all-reduce of that range on the side stream while the earlier stages are still in backward.
 def _stage_grads_done(blocks):
-    if grad_chunk_hook is None or PROFILE is not None or _lib.PROFILE_CALLS is not None:
+    if PROFILE is not None or _lib.PROFILE_CALLS is not None:
         return
-    offs = [getattr(p, '_gs_flat_off', None) for p in blocks[0].parameters()]
-    offs = [o for o in offs if o is not None]
-    if offs:
-        grad_chunk_hook(min(offs))
+    owner, off = None, None
+    for p in blocks[0].parameters():
+        ref = getattr(p, '_gs_flat_owner', None)
+        o = getattr(p, '_gs_flat_off', None)
+        if ref is None or o is None:
+            continue
+        if owner is None:
+            owner = ref()
+        off = o if off is None else min(off, o)
+    if owner is not None and off is not None:
+        owner._reduce_chunk(off)
 
 
 def cba_backward(rec, dz, need_dx=True, dx_add=None):

@@ -194,10 +194,13 @@ class FlatParams:
         self.image_convs = [m for m in self.convs if F_gs.is_image_conv(m)]
 
         # overlapped all-reduce: gradients at offsets >= _reduced_from have already been summed over the ranks by a
-        # side-stream chunk during the backward pass (functional.grad_chunk_hook)
+        # side-stream chunk during the backward pass (functional._stage_grads_done)
         self._reduced_from = total
         if self.peer_grad is not None and os.environ.get('GS_GRAD_OVERLAP', '1') != '0':
-            F_gs.grad_chunk_hook = self._reduce_chunk
+            import weakref
+            ref = weakref.ref(self)
+            for p in params:
+                p._gs_flat_owner = ref
 
     def _reduce_chunk(self, off):
         """All-reduce [off, _reduced_from) on the side stream (every gradient in that range is final)."""
