@@ -255,3 +255,27 @@ def test_analytic_macs_reproduce_the_survey_figures(gs):
             m.manipulate_arch(gs.fold_dict(a)['arch'])
             got = conv_macs(m, (3, 512, 1024)) / 1e9
             assert abs(got - want[(v, a['name'])]) <= 0.15, (v, a['name'], got)
+
+
+def test_stage_gradient_chunk_reaches_the_owning_flat_buffer(gs):
+    """The overlapped gradient all-reduce is driven from StageFn.backward: the first block's parameters carry their
+    flat offset and a weak reference to the FlatParams that owns them; the owner is asked to reduce from the SMALLEST
+    offset of the stage (host logic only -- no device needed)."""
+    import weakref
+    from gaia_seg_b200 import functional as Fg
+
+    class Owner:
+        def __init__(self):
+            self.calls = []
+
+        def _reduce_chunk(self, off):
+            self.calls.append(off)
+
+    blk = torch.nn.Sequential(torch.nn.Conv2d(4, 4, 1), torch.nn.BatchNorm2d(4))
+    Fg._stage_grads_done([blk])                     # untagged parameters (single GPU): nothing happens
+    owner = Owner()
+    for i, p in enumerate(blk.parameters()):
+        p._gs_flat_off = 640 - 64 * i
+        p._gs_flat_owner = weakref.ref(owner)
+    Fg._stage_grads_done([blk, torch.nn.Sequential()])
+    assert owner.calls == [640 - 64 * (len(list(blk.parameters())) - 1)]
