@@ -226,6 +226,8 @@ class CrossArchEvalHook(Hook):
                 res = self.dataloader.dataset.evaluate(results, **self.eval_kwargs)
                 self.results[anchor_id] = res
                 print(f'[eval iter {runner.iter + 1}] {anchor_id}: {res}', flush=True)
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()        # rank 0 alone ran dataset.evaluate: re-align before the next training iteration
         runner.model.train()
 
 

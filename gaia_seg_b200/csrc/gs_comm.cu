@@ -19,6 +19,7 @@
 #include "gs_host.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace gs {
@@ -49,7 +50,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
 
 __global__ void __launch_bounds__(kCommThreads) syncbn_allreduce_kernel(double* __restrict__ stats, int n, PeerPtrs peers,
                                                                         int rank, int world, unsigned long long* seq_dev,
-                                                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                        unsigned long long timeout_ns) {
     const int tid = threadIdx.x;
     const unsigned long long seq = *seq_dev + 1;     // every thread reads the counter; thread 0 bumps it at the very end
     const unsigned long long tag = (seq & 0xFFFFFFFFull) << 32;
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(kCommThreads) syncbn_allreduce_kernel(double* 
                 ulonglong2 w = ld_v2_sys(src);
                 unsigned int spins = 0;
                 while ((w.x & 0xFFFFFFFF00000000ull) != tag || (w.y & 0xFFFFFFFF00000000ull) != tag) {
-                    if ((++spins & 1023u) == 0 && gtimer() - t0 > 10000000000ull) {
+                    if ((++spins & 1023u) == 0 && gtimer() - t0 > timeout_ns) {
                         printf("gaiaseg_b200: SyncBN peer exchange timed out (rank %d waiting for rank %d, seq %llu)\n", rank,
                                r, seq);
                         __trap();
@@ -133,7 +135,8 @@ struct FlagPtrs {
     unsigned long long* f[kCommMaxWorld];   // per rank: [2 flag sets][kCommMaxWorld]
 };
 
-__global__ void peer_barrier_kernel(FlagPtrs flags, int rank, int world, unsigned long long* seq_dev, int set, int bump) {
+__global__ void peer_barrier_kernel(FlagPtrs flags, int rank, int world, unsigned long long* seq_dev, int set, int bump,
+                                    unsigned long long timeout_ns) {
     const int tid = threadIdx.x;
     const unsigned long long seq = *seq_dev + (bump ? 1ull : 0ull);
     __syncthreads();
@@ -146,7 +149,7 @@ __global__ void peer_barrier_kernel(FlagPtrs flags, int rank, int world, unsigne
         unsigned long long v;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-            if ((++spins & 1023u) == 0 && gtimer() - t0 > 10000000000ull) {
+            if ((++spins & 1023u) == 0 && gtimer() - t0 > timeout_ns) {
                 printf("gaiaseg_b200: gradient all-reduce barrier timed out (rank %d waiting for rank %d, seq %llu)\n", rank,
                        tid, seq);
                 __trap();
@@ -184,6 +187,19 @@ __global__ void __launch_bounds__(256) grad_reduce_push_kernel(GradPtrs ptrs, lo
     __threadfence_system();
 }
 
+// Spin budget of the peer kernels.  A rank may legitimately wait for a peer that is busy with rank-local host work
+// (checkpoint write, dataset.evaluate, a stalled DataLoader): the default matches NCCL's watchdog scale (10 minutes),
+// GS_COMM_TIMEOUT_S overrides it (tests and benchmarks use a short budget so that a bug traps instead of hanging a box).
+static unsigned long long comm_timeout_ns() {
+    static const unsigned long long v = [] {
+        const char* e = getenv("GS_COMM_TIMEOUT_S");
+        double s = e ? atof(e) : 600.0;
+        if (!(s > 0.0)) s = 600.0;
+        return static_cast<unsigned long long>(s * 1e9);
+    }();
+    return v;
+}
+
 }  // namespace gs
 
 using namespace gs;
@@ -213,14 +229,14 @@ extern "C" int gs_grad_allreduce(const void* const* peer_grads, int64_t offset, 
     long long lo4 = o4 + per * rank, hi4 = lo4 + per;
     if (lo4 > o4 + n4) lo4 = o4 + n4;
     if (hi4 > o4 + n4) hi4 = o4 + n4;
-    peer_barrier_kernel<<<1, 32, 0, st>>>(fp, rank, world, seq, 0, 1);
+    peer_barrier_kernel<<<1, 32, 0, st>>>(fp, rank, world, seq, 0, 1, comm_timeout_ns());
     if (hi4 > lo4) {
         long long blocks = (hi4 - lo4 + 256 * 4 - 1) / (256 * 4);
         const long long cap = static_cast<long long>(num_sms()) * 4;
         if (blocks > cap) blocks = cap;
         grad_reduce_push_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(gp, lo4, hi4, world);
     }
-    peer_barrier_kernel<<<1, 32, 0, st>>>(fp, rank, world, seq, 1, 0);
+    peer_barrier_kernel<<<1, 32, 0, st>>>(fp, rank, world, seq, 1, 0, comm_timeout_ns());
     GS_LAUNCHED();
     return 0;
 }
@@ -278,7 +294,7 @@ extern "C" int gs_syncbn_allreduce(double* stats, int32_t n, const void* const* 
     int threads = ((n + 31) / 32) * 32;
     if (threads > kCommThreads) threads = kCommThreads;
     syncbn_allreduce_kernel<<<1, kCommThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        stats, n, pp, rank, world, reinterpret_cast<unsigned long long*>(seq_dev), dgamma, dbeta);
+        stats, n, pp, rank, world, reinterpret_cast<unsigned long long*>(seq_dev), dgamma, dbeta, comm_timeout_ns());
     (void)threads;
     GS_LAUNCHED();
     return 0;

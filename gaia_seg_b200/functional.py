@@ -376,37 +376,85 @@ def bn_batch_mode(bn):
     return bn.training or not bn.track_running_stats or bn.running_mean is None
 
 
+def _all_agree(ok, group=None):
+    """Collective AND over the group: the peer-memory path is taken only when EVERY rank could set it up -- a rank that
+    fell back to NCCL alone while its peers spin in the peer kernels would hang the job."""
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=torch.device('cuda', torch.cuda.current_device()))
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()))
+
+
+def _ipc_alloc(nbytes):
+    lib = _lib.load()
+    ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+    _lib.check(lib.gs_ipc_alloc(nbytes, ctypes.byref(ptr), handle), 'gs_ipc_alloc')
+    return ptr.value, bytes(handle.raw)
+
+
+def _ipc_open(handle):
+    p = ctypes.c_void_p()
+    _lib.check(_lib.load().gs_ipc_open(ctypes.create_string_buffer(handle, 64), ctypes.byref(p)), 'gs_ipc_open')
+    return p.value
+
+
+def _peer_map(sizes, group, what):
+    """Allocate one IPC-shareable buffer per entry of `sizes` on every rank and map every peer's buffers.  Returns
+    (own_ptrs, tables) with tables[i] = (c_void_p * 8) of buffer i on every rank, or None when ANY rank failed (agreed
+    collectively; everything that was allocated / opened is released again)."""
+    import warnings
+    lib = _lib.load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    own, handles, err = [], [], None
+    try:
+        for nbytes in sizes:
+            ptr, h = _ipc_alloc(nbytes)
+            own.append(ptr)
+            handles.append(h)
+    except Exception as e:   # noqa: BLE001  (no P2P / IPC on this system)
+        err = e
+    if not _all_agree(err is None, group):
+        for ptr in own:
+            lib.gs_ipc_free(ptr)
+        warnings.warn(f'gaia_seg_b200: {what}: IPC allocation failed on at least one rank ({err}); ALL ranks use NCCL')
+        return None
+    gathered = [None] * world
+    dist.all_gather_object(gathered, handles, group=group)
+    tables = [(ctypes.c_void_p * 8)() for _ in sizes]
+    opened = []
+    try:
+        for r, hs in enumerate(gathered):
+            for i, h in enumerate(hs):
+                if r == rank:
+                    tables[i][r] = own[i]
+                else:
+                    tables[i][r] = _ipc_open(h)
+                    opened.append(tables[i][r])
+    except Exception as e:   # noqa: BLE001
+        err = e
+    if not _all_agree(err is None, group):
+        for ptr in opened:
+            lib.gs_ipc_close(ptr)
+        dist.barrier(group=group)          # nobody frees while a peer still has the buffer mapped
+        for ptr in own:
+            lib.gs_ipc_free(ptr)
+        warnings.warn(f'gaia_seg_b200: {what}: peer mapping failed on at least one rank ({err}); ALL ranks use NCCL')
+        return None
+    dist.barrier(group=group)
+    return own, tables
+
+
 class PeerExchange:
     """NVLink peer-memory all-reduce of the packed SyncBN sums (gs_syncbn_allreduce): one small kernel per layer and
     direction instead of a host-launched NCCL collective.  Set up once per process group: every rank allocates an
-    IPC-shareable inbox, the 64-byte handles travel through torch.distributed, peers map each other's inbox."""
+    IPC-shareable inbox, the 64-byte handles travel through torch.distributed, peers map each other's inbox.  Whether
+    the peer path or the NCCL fallback is used is agreed COLLECTIVELY (all ranks or none)."""
     _instances = {}
 
-    def __init__(self, group=None):
-        lib = _lib.load()
+    def __init__(self, group, own, table):
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        if self.world > 8:
-            raise GsError('PeerExchange: at most 8 ranks (one NVSwitch domain)')
-        nbytes = lib.gs_comm_inbox_bytes(self.world)
-        ptr = ctypes.c_void_p()
-        handle = ctypes.create_string_buffer(64)
-        _lib.check(lib.gs_ipc_alloc(nbytes, ctypes.byref(ptr), handle), 'gs_ipc_alloc')
-        self.own = ptr.value
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle.raw), group=group)
-        self.ptrs = (ctypes.c_void_p * 8)()
-        self.opened = []
-        for r, h in enumerate(handles):
-            if r == self.rank:
-                self.ptrs[r] = self.own
-            else:
-                p = ctypes.c_void_p()
-                _lib.check(lib.gs_ipc_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)), 'gs_ipc_open')
-                self.ptrs[r] = p.value
-                self.opened.append(p.value)
+        self.own, self.ptrs = own, table
         self.seq = torch.zeros(1, dtype=torch.int64, device=torch.device('cuda', torch.cuda.current_device()))
-        dist.barrier(group=group)
 
     def all_reduce(self, stats, dgamma=None, dbeta=None):
         call('gs_syncbn_allreduce', stats.data_ptr(), stats.numel(), self.ptrs, self.rank, self.world, self.seq.data_ptr(),
@@ -417,15 +465,13 @@ class PeerExchange:
         key = id(group) if group is not None else 0
         inst = cls._instances.get(key)
         if inst is None:
-            if os.environ.get('GS_SYNCBN_PEER', '1') == '0':
+            world = dist.get_world_size(group)
+            want = os.environ.get('GS_SYNCBN_PEER', '1') != '0' and world <= 8
+            if not _all_agree(want, group):
                 inst = False
             else:
-                try:
-                    inst = cls(group)
-                except Exception as e:   # IPC unavailable (e.g. no P2P): fall back to NCCL, loudly
-                    import warnings
-                    warnings.warn(f'gaia_seg_b200: NVLink peer exchange unavailable ({e}); SyncBN falls back to NCCL all_reduce')
-                    inst = False
+                m = _peer_map([_lib.load().gs_comm_inbox_bytes(world)], group, 'SyncBN peer exchange')
+                inst = cls(group, m[0][0], m[1][0]) if m is not None else False
             cls._instances[key] = inst
         return inst
 
@@ -441,35 +487,13 @@ class PeerGrad:
     """Flat fp32 gradient buffer in IPC-shareable memory + the peer-memory all-reduce over it (gs_grad_allreduce):
     every rank maps every other rank's buffer, a range is summed in three capturable launches (no NCCL call)."""
 
-    def __init__(self, numel, device, group=None):
-        lib = _lib.load()
+    def __init__(self, numel, device, group, own, tables):
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        if self.world > 8:
-            raise GsError('PeerGrad: at most 8 ranks (one NVSwitch domain)')
         self.numel = numel
-
-        def alloc(nbytes):
-            ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
-            _lib.check(lib.gs_ipc_alloc(nbytes, ctypes.byref(ptr), handle), 'gs_ipc_alloc')
-            return ptr.value, bytes(handle.raw)
-
-        gptr, gh = alloc(numel * 4)
-        fptr, fh = alloc(int(lib.gs_comm_flags_bytes()))
-        handles = [None] * self.world
-        dist.all_gather_object(handles, (gh, fh), group=group)
-        self.gptrs, self.fptrs = (ctypes.c_void_p * 8)(), (ctypes.c_void_p * 8)()
-        for r, (hg, hf) in enumerate(handles):
-            if r == self.rank:
-                self.gptrs[r], self.fptrs[r] = gptr, fptr
-            else:
-                pg, pf = ctypes.c_void_p(), ctypes.c_void_p()
-                _lib.check(lib.gs_ipc_open(ctypes.create_string_buffer(hg, 64), ctypes.byref(pg)), 'gs_ipc_open')
-                _lib.check(lib.gs_ipc_open(ctypes.create_string_buffer(hf, 64), ctypes.byref(pf)), 'gs_ipc_open')
-                self.gptrs[r], self.fptrs[r] = pg.value, pf.value
-        self.tensor = torch.as_tensor(_RawCuda(gptr, numel), device=device)     # zero-initialised by gs_ipc_alloc
+        self.gptrs, self.fptrs = tables
+        self.tensor = torch.as_tensor(_RawCuda(own[0], numel), device=device)     # zero-initialised by gs_ipc_alloc
         self.seq = torch.zeros(1, dtype=torch.int64, device=device)
-        dist.barrier(group=group)
 
     def all_reduce(self, offset=0, count=None):
         count = self.numel - offset if count is None else count
@@ -477,17 +501,15 @@ class PeerGrad:
 
     @classmethod
     def create(cls, numel, device, group=None):
-        """PeerGrad, or None when the job is single-rank / peer access is disabled or unavailable (then NCCL is used)."""
+        """PeerGrad, or None when the job is single-rank / peer access is disabled or unavailable on ANY rank (then
+        NCCL is used by all of them).  Collective: every rank must call it."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
-        if os.environ.get('GS_GRAD_PEER', '1') == '0' or not PeerExchange.get(group):
+        want = os.environ.get('GS_GRAD_PEER', '1') != '0' and bool(PeerExchange.get(group))
+        if not _all_agree(want, group):
             return None
-        try:
-            return cls(numel, device, group)
-        except Exception as e:
-            import warnings
-            warnings.warn(f'gaia_seg_b200: peer-memory gradient buffer unavailable ({e}); using NCCL all_reduce')
-            return None
+        m = _peer_map([numel * 4, int(_lib.load().gs_comm_flags_bytes())], group, 'peer-memory gradient buffer')
+        return cls(numel, device, group, m[0], m[1]) if m is not None else None
 
 
 def stats_all_reduce(stats, group=None, dgamma=None, dbeta=None):
@@ -502,11 +524,40 @@ def stats_all_reduce(stats, group=None, dgamma=None, dbeta=None):
         dist.all_reduce(stats, group=group)
 
 
+# `group_size` of DynSyncBN (configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:20-23 passes group_size=1): gaiavision is
+# not in the reference tree, so its meaning is an OPEN QUESTION (DESIGN.md "open questions").  Two readings, selectable:
+#   GS_SYNCBN_GROUP_SIZE=world (default)  the argument is accepted and ignored: statistics over the whole DP world -- what
+#                                         north_star prescribes ("SyncBN per-channel sum/sumsq across the 8 GPUs");
+#   GS_SYNCBN_GROUP_SIZE=ranks            group_size = ranks per synchronisation group (the linklink / SenseTime SyncBN
+#                                         convention): 1 -> per-GPU statistics (no exchange), k -> groups of k consecutive ranks.
+GROUP_SIZE_MODE = os.environ.get('GS_SYNCBN_GROUP_SIZE', 'world')
+_subgroups = {}
+
+
+def _rank_subgroup(k):
+    """Process group of the k consecutive ranks containing this rank (all ranks create all groups, once)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if k not in _subgroups:
+        mine = None
+        for lo in range(0, world, k):
+            pg = dist.new_group(list(range(lo, min(lo + k, world))))
+            if lo <= rank < lo + k:
+                mine = pg
+        _subgroups[k] = mine
+    return _subgroups[k]
+
+
 def _sync_group(bn):
     """(process_group, world) when `bn` synchronises statistics across ranks, else (None, 1)."""
     if not getattr(bn, 'sync', False) or not dist.is_available() or not dist.is_initialized():
         return None, 1
     pg = getattr(bn, 'process_group', None)
+    if pg is None and GROUP_SIZE_MODE == 'ranks':
+        k = getattr(bn, 'group_size', None)
+        if k is not None and k < dist.get_world_size():
+            if k <= 1:
+                return None, 1
+            pg = _rank_subgroup(int(k))
     world = dist.get_world_size(pg)
     return pg, world
 
@@ -670,7 +721,8 @@ def wgrad_join():
 def side_stream_run(fn, device, keep=()):
     """Run `fn()` on the side stream, ordered after everything enqueued so far on the current stream; the current
     stream re-joins at the end of the running backward pass.  Outside a backward pass `fn` simply runs in stream order.
-    `keep`: objects that must stay alive until the join (operands of the side-stream kernels)."""
+    `keep`: objects that must stay alive until the join (operands of the side-stream kernels).
+    Returns True: `fn` HAS run (been enqueued) in either case -- callers that track "this range is done" rely on it."""
     stt = _side_state
     main = torch.cuda.current_stream(device)
     if not stt['queued']:
@@ -678,7 +730,7 @@ def side_stream_run(fn, device, keep=()):
             torch.autograd.Variable._execution_engine.queue_callback(wgrad_join)
         except RuntimeError:          # not inside a backward pass: keep the plain stream order
             fn()
-            return False
+            return True
         stt['queued'], stt['main'] = True, main
     side = _side_stream(device)
     side.wait_stream(main)
@@ -688,6 +740,15 @@ def side_stream_run(fn, device, keep=()):
     return True
 
 
+def reset_side_state():
+    """Called at zero_grad(): a backward pass that raised before its final callback ran must not leave the
+    'callback queued' flag set (the next backward would then never re-join the side stream)."""
+    stt = _side_state
+    if stt['pending']:
+        wgrad_join()
+    stt['queued'], stt['main'] = False, None
+
+
 def _wgrad_async(conv, a, dy, geom):
     if not WGRAD_STREAM or PROFILE is not None or _lib.PROFILE_CALLS is not None:
         conv_wgrad(conv, a, dy, geom)
@@ -695,24 +756,22 @@ def _wgrad_async(conv, a, dy, geom):
     side_stream_run(lambda: conv_wgrad(conv, a, dy, geom), dy.device, keep=(a, dy))
 
 
-# Gradient chunks: runner.FlatParams tags every parameter it owns with its flat offset and (when the gradient buffer is
-# peer-mapped and overlap is enabled) a weak reference to itself.  Once a res stage's backward has been enqueued, every
-# gradient at or beyond the offset of the stage's first parameter is final (later layers ran their backward earlier), so
-# the owner can start the all-reduce of that range on the side stream while the earlier stages are still in backward.
+# Gradient chunks (overlapped all-reduce).  runner.FlatParams builds a PLAN from the model structure: every flat range is
+# tagged with the res stage whose backward, once enqueued, makes the range final BY DATA DEPENDENCY:
+#   * the parameters of backbone stage k           -> final when StageFn.backward of stage k has been enqueued;
+#   * a head reading feature `in_index` = stage k  -> final when the backward of stage k has been enqueued (that node
+#     consumes the head's input gradient, so the whole head ran before it -- no reliance on autograd's queue priority);
+#   * everything else (stem, necks, ...)           -> reduced by all_reduce_grads() after the backward pass.
+# The first block of a planned stage carries (weakref(owner), stage index); StageFn.backward reports it here.
 def _stage_grads_done(blocks):
     if PROFILE is not None or _lib.PROFILE_CALLS is not None:
         return
-    owner, off = None, None
-    for p in blocks[0].parameters():
-        ref = getattr(p, '_gs_flat_owner', None)
-        o = getattr(p, '_gs_flat_off', None)
-        if ref is None or o is None:
-            continue
-        if owner is None:
-            owner = ref()
-        off = o if off is None else min(off, o)
-    if owner is not None and off is not None:
-        owner._reduce_chunk(off)
+    tag = getattr(blocks[0], '_gs_grad_stage', None)
+    if tag is None:
+        return
+    owner = tag[0]()
+    if owner is not None:
+        owner._reduce_stage(tag[1])
 
 
 def cba_backward(rec, dz, need_dx=True, dx_add=None):
@@ -843,12 +902,23 @@ class StageFn(torch.autograd.Function):
         return d, None, None
 
 
+def _grad_anchor(modules):
+    """A parameter that requires grad among `modules` (autograd builds the node iff an input needs a gradient: with a
+    frozen first block and an input without grad -- frozen_stages / frozen_layers -- the later trainable blocks would
+    otherwise silently train nothing); falls back to the first conv weight."""
+    for m in modules:
+        for p in m.parameters():
+            if p.requires_grad:
+                return p
+    return modules[0].conv1.weight
+
+
 def res_stage(x, blocks):
-    return StageFn.apply(x, blocks[0].conv1.weight, blocks)
+    return StageFn.apply(x, _grad_anchor(blocks), blocks)
 
 
 def bottleneck(x, block):
-    return BottleneckFn.apply(x, block.conv1.weight, block)
+    return BottleneckFn.apply(x, _grad_anchor([block]), block)
 
 
 class MaxPoolFn(torch.autograd.Function):
@@ -912,6 +982,11 @@ def cat_channels(xs):
     return CatFn.apply(*xs)
 
 
+# parity tests inject the Bernoulli draw here: callable(N, C, keep, device) -> fp32 [N, C] mask with values in
+# {0, 1/keep}; None = torch's generator (the product behaviour)
+DROPOUT_MASK_FN = None
+
+
 class Dropout2dFn(torch.autograd.Function):
     """nn.Dropout2d (fcn_head.py:248-253): the per-(n, c) Bernoulli mask comes from torch's generator (a
     [N, C] tensor -- control-plane sized); applying it to the feature map is the kernel."""
@@ -921,7 +996,10 @@ class Dropout2dFn(torch.autograd.Function):
         x = as_act(x)
         N, C, H, W = x.shape
         keep = 1.0 - p
-        mask = torch.bernoulli(torch.full((N, C), keep, dtype=torch.float32, device=x.device)).div_(keep)
+        if DROPOUT_MASK_FN is not None:
+            mask = DROPOUT_MASK_FN(N, C, keep, x.device).to(device=x.device, dtype=torch.float32).contiguous()
+        else:
+            mask = torch.bernoulli(torch.full((N, C), keep, dtype=torch.float32, device=x.device)).div_(keep)
         y = new_act(N, C, H, W, x.device)
         call('gs_scale_nc', x.data_ptr(), act_ld(x), mask.data_ptr(), y.data_ptr(), C, N, H * W, C, _stream())
         ctx.mask = mask

@@ -6,9 +6,11 @@ format (max-width OIHW fp32 state_dict + meta).
 B200-first choices:
   * all parameters live in ONE flat fp32 master buffer (+ one flat gradient buffer, one flat momentum buffer,
     one flat bf16 forward-shadow buffer at the same offsets) -> the optimizer is ONE kernel launch, the
-    gradient exchange is ONE bucketed NCCL all-reduce over NVLink of the flat buffer instead of DDP's
-    reducer hooks + `find_unused_parameters` graph walk (gaiaseg/apis/train.py:88-95);
-  * SyncBN statistics are packed (sum, sumsq) all-reduces issued by the layers themselves.
+    gradient exchange is a hand-written two-shot all-reduce over NVLink PEER MEMORY of ranges of the flat buffer
+    (gs_grad_allreduce; per res stage on a side stream during backward, blocks outside the sampled depth never travel;
+    bucketed NCCL only as the collectively agreed fallback) instead of DDP's reducer hooks + `find_unused_parameters`
+    graph walk (gaiaseg/apis/train.py:88-95);
+  * SyncBN statistics are packed (sum, sumsq) exchanges over peer memory issued by the layers themselves.
 """
 import importlib.util
 import math
@@ -193,45 +195,154 @@ class FlatParams:
             F_gs.conv_shadows(m)
         self.image_convs = [m for m in self.convs if F_gs.is_image_conv(m)]
 
-        # overlapped all-reduce: gradients at offsets >= _reduced_from have already been summed over the ranks by a
-        # side-stream chunk during the backward pass (functional._stage_grads_done)
-        self._reduced_from = total
-        if self.peer_grad is not None and os.environ.get('GS_GRAD_OVERLAP', '1') != '0':
-            import weakref
-            ref = weakref.ref(self)
-            for p in params:
-                p._gs_flat_owner = ref
+        # gradient exchange plan: which flat ranges become final when (see functional._stage_grads_done), and which
+        # ranges belong to blocks a depth-truncated sub-net never runs (all-zero on every rank -> not exchanged at all)
+        self._sizes = {o: (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN for p, o in zip(params, offs)}
+        self._off_of = off_of
+        self._stage_blocks = {}      # stage index (1-based) -> (layer module, [(lo, hi) per block])
+        self._stage_extra = {}       # stage index -> [(lo, hi)] of heads whose input feature that stage produces
+        self._done = []              # ranges already exchanged (or known to be all-zero) in this iteration
+        self._overlap = self.peer_grad is not None and os.environ.get('GS_GRAD_OVERLAP', '1') != '0'
+        self._check = os.environ.get('GS_GRAD_OVERLAP_CHECK', '0') == '1'
+        self._snapshots = []
+        self._plan(model)
 
-    def _reduce_chunk(self, off):
-        """All-reduce [off, _reduced_from) on the side stream (every gradient in that range is final)."""
-        hi = self._reduced_from
-        if off >= hi:
+    # -- plan -----------------------------------------------------------------------------------
+    def _ranges_of(self, module):
+        """Merged flat ranges [(lo, hi)] covering the trainable parameters of `module`."""
+        offs = sorted(self._off_of[id(p)] for p in module.parameters() if id(p) in self._off_of)
+        out = []
+        for o in offs:
+            hi = o + self._sizes[o]
+            if out and out[-1][1] == o:
+                out[-1][1] = hi
+            else:
+                out.append([o, hi])
+        return [tuple(r) for r in out]
+
+    def _plan(self, model):
+        import weakref
+        backbone = getattr(model, 'backbone', None)
+        names = getattr(backbone, 'res_layers', None)
+        if backbone is None or not names:
             return
+        ref = weakref.ref(self)
+        for k, name in enumerate(names, start=1):
+            layer = getattr(backbone, name)
+            blocks = []
+            for blk in layer:
+                r = self._ranges_of(blk)
+                if len(r) != 1:          # a block's parameters are not one contiguous range: leave the stage unplanned
+                    blocks = None
+                    break
+                blocks.append(r[0])
+            if not blocks:
+                continue
+            self._stage_blocks[k] = (weakref.ref(layer), blocks)
+            if self._overlap:
+                layer[0]._gs_grad_stage = (ref, k)
+        out_idx = list(getattr(backbone, 'out_indices', range(len(names))))
+        heads = []
+        for attr in ('decode_head', 'auxiliary_head'):
+            h = getattr(model, attr, None)
+            if h is None:
+                continue
+            heads += list(h) if isinstance(h, nn.ModuleList) else [h]
+        for h in heads:
+            idx = getattr(h, 'in_index', None)
+            if not isinstance(idx, int):
+                continue
+            try:
+                k = out_idx[idx] + 1
+            except IndexError:
+                continue
+            if k in self._stage_blocks:
+                self._stage_extra.setdefault(k, []).extend(self._ranges_of(h))
+
+    @staticmethod
+    def _merge(ranges):
+        out = []
+        for lo, hi in sorted(r for r in ranges if r[1] > r[0]):
+            if out and lo <= out[-1][1]:
+                out[-1][1] = max(out[-1][1], hi)
+            else:
+                out.append([lo, hi])
+        return [tuple(r) for r in out]
+
+    def _inactive_ranges(self):
+        """Flat ranges of blocks beyond the sampled depth of every planned stage (the reference's DDP
+        all-reduces the zeros of the whole max-width model, gaiaseg/apis/train.py:88-95; here they never travel)."""
+        out = []
+        for k, (lref, blocks) in self._stage_blocks.items():
+            layer = lref()
+            d = getattr(layer, 'depth_state', len(blocks)) if layer is not None else len(blocks)
+            if d < len(blocks):
+                out.append((blocks[d][0], blocks[-1][1]))
+        return out
+
+    def _pending_ranges(self):
+        """What is left to exchange after the backward pass: [0, total) minus the per-stage chunks already done minus
+        the blocks outside the sampled depth."""
+        out, cur = [], 0
+        for lo, hi in self._merge(self._done + self._inactive_ranges()) + [(self.total, self.total)]:
+            if lo > cur:
+                out.append((cur, lo))
+            cur = max(cur, hi)
+        return out
+
+    def _reduce_stage(self, k):
+        """Backward of res stage k has been enqueued: exchange its active blocks and the heads it feeds on the side
+        stream (their gradients are final by data dependency)."""
+        if not self._overlap or k not in self._stage_blocks:
+            return
+        lref, blocks = self._stage_blocks[k]
+        layer = lref()
+        d = getattr(layer, 'depth_state', len(blocks)) if layer is not None else len(blocks)
+        todo = self._merge([(blocks[0][0], blocks[min(d, len(blocks)) - 1][1])] + self._stage_extra.get(k, []))
         pg = self.peer_grad
-        if F_gs.side_stream_run(lambda: pg.all_reduce(off, hi - off), self.flat_g.device):
-            self._reduced_from = off
+        for lo, hi in todo:
+            F_gs.side_stream_run(lambda lo=lo, hi=hi: pg.all_reduce(lo, hi - lo), self.flat_g.device)
+            self._done.append((lo, hi))
+            if self._check:
+                self._snapshots.append((lo, hi, None))
 
     def zero_grad(self):
         """Contract of one iteration: zero_grad() -> ONE backward pass -> all_reduce_grads() -> optimizer step."""
+        F_gs.reset_side_state()
         self.flat_g.zero_()
-        self._reduced_from = self.total
+        self._done = []
+        self._snapshots = []
 
     def all_reduce_grads(self, group=None, bucket_bytes=64 << 20):
-        """Sum the flat gradient over the data-parallel group in NCCL buckets (the mean is folded into the
-        optimizer's grad_scale).  One call per bucket over NVLink; no per-parameter hooks."""
+        """Sum the flat gradient over the data-parallel group (the mean is folded into the optimizer's grad_scale).
+        Peer-memory path: everything the per-stage chunks have not exchanged yet, minus the blocks outside the sampled
+        depth (zero everywhere).  NCCL path (fallback): bucketed all_reduce of the whole buffer."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return 1
         if self.peer_grad is not None and group is None:
-            # three capturable launches over NVLink peer memory; the chunks beyond _reduced_from were done during backward
             F_gs.wgrad_join()
-            if self._reduced_from > 0:
-                self.peer_grad.all_reduce(0, self._reduced_from)
-            self._reduced_from = self.total
+            if self._check and self._snapshots:
+                self._verify_chunks()
+            for lo, hi in self._pending_ranges():
+                self.peer_grad.all_reduce(lo, hi - lo)
+            self._done = []
             return self.peer_grad.world
         n = bucket_bytes // 4
         for s in range(0, self.total, n):
             dist.all_reduce(self.flat_g[s:s + n], group=group)
         return dist.get_world_size(group)
+
+    def _verify_chunks(self):
+        """GS_GRAD_OVERLAP_CHECK=1 (debug): a range that was exchanged during the backward pass must be identical on
+        every rank afterwards -- a gradient accumulated into it AFTER its exchange would be rank-local and break that."""
+        for lo, hi, _ in self._snapshots:
+            mine = self.flat_g[lo:hi]
+            ref = mine.clone()
+            dist.broadcast(ref, 0)
+            if not torch.equal(mine, ref):
+                raise F_gs.GsError(f'overlapped gradient all-reduce: range [{lo}, {hi}) was modified after its exchange '
+                                   f'(a late local gradient); set GS_GRAD_OVERLAP=0 and report the model structure')
+        self._snapshots = []
 
 
 class GsSGD(torch.optim.Optimizer):
@@ -273,20 +384,58 @@ class GsSGD(torch.optim.Optimizer):
         if not torch.cuda.is_current_stream_capturing():
             self.sync_hyper()
         call('gs_sgd_flat', f.flat_p.data_ptr(), f.flat_g.data_ptr(), self.momentum_buf.data_ptr(), f.total,
-             self._hyper_dev.data_ptr(), 1 if self._steps == 0 else 0, f.flat_shadow.data_ptr(), F_gs._stream())
+             self._hyper_dev.data_ptr(), 0, f.flat_shadow.data_ptr(), F_gs._stream())   # buf starts at zero: mom * 0 + d == d
         for m in f.image_convs:
             F_gs.refresh_image_shadow(m)
         self._steps += 1
 
+    def _logical(self, flat, p, off):
+        """View of `flat` at a parameter's offset with the parameter's logical (OIHW) shape."""
+        v = flat[off:off + p.numel()]
+        if p.dim() == 4:
+            Co, Ci, kh, kw = p.shape
+            return v.view(Co, kh, kw, Ci).permute(0, 3, 1, 2)
+        return v.view(p.shape)
+
     def state_dict(self):
-        return dict(momentum_buf=self.momentum_buf, steps=self._steps,
-                    param_groups=[{k: v for k, v in g.items() if k != 'params'} for g in self.param_groups])
+        """torch.optim.SGD layout (what an mmcv / reference checkpoint carries): state[i]['momentum_buffer'] with the
+        parameter's logical OIHW shape + param_groups with `params` indices, so checkpoints written here resume in the
+        reference and vice versa.  (No state before the first step, like torch.)"""
+        n = len(self.flat.params)
+        state = {}
+        if self._steps > 0:
+            for i, (p, off) in enumerate(zip(self.flat.params, self.flat.offsets)):
+                state[i] = {'momentum_buffer': self._logical(self.momentum_buf, p, off).detach().clone().contiguous()}
+        groups = []
+        for g in self.param_groups:
+            d = {k: v for k, v in g.items() if k != 'params'}
+            d.update(dampening=0, nesterov=False, params=list(range(n)))
+            groups.append(d)
+        return dict(state=state, param_groups=groups)
 
     def load_state_dict(self, sd):
-        self.momentum_buf.copy_(sd['momentum_buf'])
-        self._steps = sd['steps']
-        for g, s in zip(self.param_groups, sd['param_groups']):
-            g.update(s)
+        """Accepts the torch.optim.SGD layout (reference checkpoints) and the round-1 private layout (flat buffer)."""
+        if 'momentum_buf' in sd:                      # round-1 layout
+            self.momentum_buf.copy_(sd['momentum_buf'])
+            self._steps = int(sd.get('steps', 1))
+        else:
+            state = sd.get('state', {})
+            if len(sd['param_groups']) != 1 or len(sd['param_groups'][0]['params']) != len(self.flat.params):
+                raise ValueError('optimizer state: expected ONE param group over %d parameters' % len(self.flat.params))
+            self.momentum_buf.zero_()                 # parameters without state (never had a gradient) start from zero
+            with torch.no_grad():
+                for i, (p, off) in enumerate(zip(self.flat.params, self.flat.offsets)):
+                    st = state.get(i, state.get(str(i)))
+                    if st is None or st.get('momentum_buffer') is None:
+                        continue
+                    mb = st['momentum_buffer']
+                    if tuple(mb.shape) != tuple(p.shape):
+                        raise ValueError(f'momentum buffer {i}: shape {tuple(mb.shape)} vs parameter {tuple(p.shape)}')
+                    self._logical(self.momentum_buf, p, off).copy_(mb)
+            self._steps = 1 if state else 0
+        for g, s_ in zip(self.param_groups, sd['param_groups']):
+            g.update({k: v for k, v in s_.items() if k not in ('params', 'dampening', 'nesterov')})
+        self._hyper_last = None
 
 
 def reserve_activation_pool(gigabytes=32.0, device=None):
@@ -480,13 +629,22 @@ def _unwrap(model):
     return model.module if hasattr(model, 'module') and isinstance(model.module, nn.Module) else model
 
 
+def _to_cpu(obj):
+    if torch.is_tensor(obj):
+        return obj.detach().cpu()
+    if isinstance(obj, dict):
+        return {k: _to_cpu(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_to_cpu(v) for v in obj)
+    return obj
+
+
 def save_checkpoint(model, filename, optimizer=None, meta=None):
     model = _unwrap(model)
     sd = OrderedDict((k, v.detach().cpu().contiguous()) for k, v in model.state_dict().items())
     ckpt = dict(meta=dict(meta or {}, time=time.asctime()), state_dict=sd)
     if optimizer is not None:
-        ckpt['optimizer'] = {k: (v.detach().cpu() if torch.is_tensor(v) else v)
-                             for k, v in optimizer.state_dict().items()}
+        ckpt['optimizer'] = _to_cpu(optimizer.state_dict())
     os.makedirs(osp.dirname(osp.abspath(filename)), exist_ok=True)
     torch.save(ckpt, filename)
 
@@ -581,6 +739,10 @@ class CheckpointHook(Hook):
             if osp.lexists(latest):
                 os.remove(latest)
             os.symlink(osp.basename(path), latest)
+        if self.every_n_iters(runner, self.interval) and dist.is_available() and dist.is_initialized():
+            # rank 0 alone wrote the file: re-align the ranks on the host BEFORE they enqueue the next iteration -- the
+            # peer-memory exchange kernels spin on the device with a bounded budget (GS_COMM_TIMEOUT_S)
+            dist.barrier()
 
 
 class TextLoggerHook(Hook):
@@ -667,12 +829,22 @@ class IterBasedRunner:
         loader = data_loaders[0] if isinstance(data_loaders, (list, tuple)) else data_loaders
         self.model.train()
         self.call_hook('before_run')
-        it = iter(loader)
+        epoch = 0
+
+        def new_iter():
+            # mmcv IterLoader: every pass over the dataset reshuffles (DistributedSampler.set_epoch)
+            sampler = getattr(loader, 'sampler', None)
+            if hasattr(sampler, 'set_epoch'):
+                sampler.set_epoch(epoch)
+            return iter(loader)
+
+        it = new_iter()
         while self.iter < self.max_iters:
             try:
                 data_batch = next(it)
             except StopIteration:
-                it = iter(loader)
+                epoch += 1
+                it = new_iter()
                 data_batch = next(it)
             self.call_hook('before_train_iter')
             data_batch = scatter_batch(data_batch)

@@ -257,25 +257,81 @@ def test_analytic_macs_reproduce_the_survey_figures(gs):
             assert abs(got - want[(v, a['name'])]) <= 0.15, (v, a['name'], got)
 
 
-def test_stage_gradient_chunk_reaches_the_owning_flat_buffer(gs):
-    """The overlapped gradient all-reduce is driven from StageFn.backward: the first block's parameters carry their
-    flat offset and a weak reference to the FlatParams that owns them; the owner is asked to reduce from the SMALLEST
-    offset of the stage (host logic only -- no device needed)."""
-    import weakref
+def test_gradient_exchange_plan_follows_data_dependencies(gs):
+    """The overlapped gradient all-reduce is planned from the model structure (runner.FlatParams._plan): the active
+    blocks of res stage k and the heads reading that stage's feature are exchanged when StageFn.backward of stage k has
+    been enqueued (final by data dependency); blocks beyond the sampled depth are never exchanged (zero on every rank);
+    the rest goes after the backward pass.  Host logic only -- the flat offsets are computed as FlatParams does."""
+    import gs_checks as C
     from gaia_seg_b200 import functional as Fg
+    from gaia_seg_b200.runner import FlatParams, _ALIGN
+    model = gs.build_segmentor(C.small_cfg(aux=True), train_cfg=dict(), test_cfg=dict(mode='whole'))
+    fp = FlatParams.__new__(FlatParams)
+    params = [p for p in model.parameters() if p.requires_grad]
+    offs, total = [], 0
+    for p in params:
+        offs.append(total)
+        total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+    fp.total = total
+    fp._sizes = {o: (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN for p, o in zip(params, offs)}
+    fp._off_of = {id(p): o for p, o in zip(params, offs)}
+    fp._stage_blocks, fp._stage_extra, fp._done, fp._snapshots = {}, {}, [], []
+    fp._overlap, fp._check = True, False
+    fp._plan(model)
+    assert sorted(fp._stage_blocks) == [1, 2, 3, 4]
+    # blocks of a stage are contiguous and ordered; stages ascend in the flat buffer
+    prev_hi = 0
+    for k in (1, 2, 3, 4):
+        blocks = fp._stage_blocks[k][1]
+        assert len(blocks) == len(getattr(model.backbone, f'layer{k}'))
+        assert blocks[0][0] >= prev_hi
+        for a, b in zip(blocks, blocks[1:]):
+            assert a[1] == b[0]
+        prev_hi = blocks[-1][1]
+    # decode head reads feature 3 (stage 4), the auxiliary head feature 2 (stage 3)
+    assert fp._stage_extra[4] == fp._ranges_of(model.decode_head)
+    assert fp._stage_extra[3] == fp._ranges_of(model.auxiliary_head)
+    # MIN sub-net: depths [1, 1, 2, 1] of [2, 2, 3, 2] -> the tail blocks are inactive
+    model.manipulate_arch(C.SMALL_ARCHS['min'])
+    inactive = fp._inactive_ranges()
+    want = []
+    for k, d in zip((1, 2, 3, 4), (1, 1, 2, 1)):
+        blocks = fp._stage_blocks[k][1]
+        want.append((blocks[d][0], blocks[-1][1]))
+    assert sorted(inactive) == sorted(want)
+    # StageFn.backward -> _stage_grads_done -> owner._reduce_stage(k): record what would be exchanged
+    calls = []
+    Fg_side, fp.peer_grad = Fg.side_stream_run, None
+    fp.flat_g = torch.zeros(1)
 
-    class Owner:
-        def __init__(self):
-            self.calls = []
+    class _PG:
+        world = 2
 
-        def _reduce_chunk(self, off):
-            self.calls.append(off)
+        def all_reduce(self, lo, n):
+            calls.append((lo, lo + n))
 
-    blk = torch.nn.Sequential(torch.nn.Conv2d(4, 4, 1), torch.nn.BatchNorm2d(4))
-    Fg._stage_grads_done([blk])                     # untagged parameters (single GPU): nothing happens
-    owner = Owner()
-    for i, p in enumerate(blk.parameters()):
-        p._gs_flat_off = 640 - 64 * i
-        p._gs_flat_owner = weakref.ref(owner)
-    Fg._stage_grads_done([blk, torch.nn.Sequential()])
-    assert owner.calls == [640 - 64 * (len(list(blk.parameters())) - 1)]
+    fp.peer_grad = _PG()
+    Fg.side_stream_run = lambda fn, device, keep=(): (fn(), True)[1]
+    try:
+        for k in (4, 3, 2, 1):
+            layer = getattr(model.backbone, f'layer{k}')
+            Fg._stage_grads_done([layer[i] for i in range(layer.depth_state)])
+    finally:
+        Fg.side_stream_run = Fg_side
+    b4, b3 = fp._stage_blocks[4][1], fp._stage_blocks[3][1]
+    # stage 4: its ONE active block, then (not merged: the inactive block 1 lies between) the decode head it feeds
+    assert calls[0] == b4[0] and calls[1] == fp._ranges_of(model.decode_head)[0]
+    assert (b3[0][0], b3[1][1]) in calls and fp._ranges_of(model.auxiliary_head)[0] in calls
+    # after the backward pass: only the stem is left; nothing overlaps, nothing inactive is exchanged, all active covered
+    rest = fp._pending_ranges()
+    stem_hi = fp._stage_blocks[1][1][0][0]
+    assert rest == [(0, stem_hi)]
+    covered = FlatParams._merge(calls + rest + inactive)
+    assert covered == [(0, total)]
+    for a in calls + rest:
+        for b in inactive:
+            assert a[1] <= b[0] or b[1] <= a[0]
+    # an untagged stage (single GPU, or a model without a plan): nothing happens
+    calls.clear()
+    Fg._stage_grads_done([torch.nn.Sequential(torch.nn.Conv2d(4, 4, 1))])
+    assert calls == []

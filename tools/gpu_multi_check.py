@@ -70,6 +70,11 @@ def main():
     ok = (abs(res['loss_mean_over_ranks'] - res['loss_oracle_global_batch']) < 2e-3 * abs(res['loss_oracle_global_batch'])
           and res['grad_mean_1mcos'] < 0.05 and res['running_mean_err'] < 2e-3
           and res['buffers_identical_across_ranks'] and res['params_identical_after_step'])
+    # CUDA vs CUDA: collectives bit-exact against ordered sums, N ranks vs ONE rank on the concatenated batch (tight),
+    # overlapped vs plain vs NCCL all-reduce (tools/multi_rank_parity.py)
+    from tools.multi_rank_parity import run as cuda_vs_cuda
+    res['vs_1rank'] = cuda_vs_cuda(gs)
+    ok = ok and res['vs_1rank']['ok']
     res['ok'] = bool(ok)
     if rank == 0:
         print(json.dumps(res))

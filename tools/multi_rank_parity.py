@@ -1,0 +1,244 @@
+"""Multi-rank correctness of the data-parallel exchanges, CUDA vs CUDA (no oracle needed, so bench.py may run it):
+
+  1. collectives bit-exact: gs_syncbn_allreduce and gs_grad_allreduce (several sizes / ragged ranges) against the sum
+     in rank order of all_gather'ed inputs -- catches a mis-ordered or dropped shard definitively;
+  2. N ranks x 2 images vs ONE rank on the concatenated 2N-image batch (same kernels, SyncBN == global-batch BN,
+     gaiaseg/apis/train.py:88-95 + pspnet_ar50to101v2_gsync.py:20-23): loss, every parameter gradient, running stats;
+  3. overlapped (per-stage chunks on the side stream) vs non-overlapped vs NCCL all-reduce of the same gradients;
+  4. buffers and parameters bit-identical on every rank after an optimizer step (broadcast_buffers=False relies on it).
+
+`run(gs)` must be called by every rank of an initialised NCCL process group; returns a dict (identical keys on all ranks,
+`ok` computed on rank 0's view + all-reduced)."""
+import math
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def small_cfg():
+    norm = dict(type='DynSyncBN', requires_grad=True, group_size=1)
+    bb = dict(type='DynamicResNet', in_channels=3, stem_width=[16, 16, 32], body_depth=[2, 2, 3, 2],
+              body_width=[32, 48, 64, 80], num_stages=4, out_indices=(0, 1, 2, 3), conv_cfg=dict(type='DynConv2d'),
+              norm_cfg=norm, style='pytorch', deep_stem=True, strides=(1, 2, 1, 1), dilations=(1, 1, 2, 4),
+              contract_dilation=True)
+    head = dict(type='DynamicFCNHead', conv_cfg=dict(type='DynConv2d'), in_channels=320, in_index=3, channels=64,
+                num_convs=2, concat_input=True, dropout_ratio=0.0, num_classes=19,
+                norm_cfg=dict(type='SyncBN', requires_grad=True), align_corners=False,
+                loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0))
+    aux = dict(head, in_channels=256, in_index=2, channels=32, num_convs=1, concat_input=False,
+               loss_decode=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=0.4))
+    return dict(type='DynamicEncoderDecoder', backbone=bb, decode_head=head, auxiliary_head=aux)
+
+
+ARCH = {'backbone': {'stem': {'width': [8, 8, 16]}, 'body': {'width': [16, 48, 48, 80], 'depth': [2, 1, 3, 1]}}}
+
+
+def _randomize(model, seed):
+    """Same recipe as tests/gs_checks.randomize: non-identity BN, bf16-representable conv weights; CPU generator so every
+    rank starts from identical parameters."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 4:
+                fan = p.shape[1] * p.shape[2] * p.shape[3]
+                v = (torch.randn(p.shape, generator=g) * math.sqrt(2.0 / fan)).to(torch.bfloat16).float()
+            elif n.endswith('conv_seg.bias'):
+                v = torch.randn(p.shape, generator=g) * 0.01
+            elif n.endswith('.weight'):
+                v = torch.rand(p.shape, generator=g) + 0.5
+            else:
+                v = torch.randn(p.shape, generator=g) * 0.1
+            p.copy_(v.to(p.device))
+
+
+def _model(gs, seed, dev):
+    m = gs.build_segmentor(small_cfg(), train_cfg=dict(), test_cfg=dict(mode='whole'))
+    _randomize(m, seed)
+    m = m.to(dev)
+    m.manipulate_arch(ARCH)
+    m.train()
+    return m
+
+
+def _batch(world, seed=21):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(2 * world, 3, 64, 96, generator=g).to(torch.bfloat16).float()
+    lab = torch.randint(0, 19, (2 * world, 1, 64, 96), generator=g)
+    lab[torch.rand(2 * world, 1, 64, 96, generator=g) < 0.1] = 255
+    return img, lab
+
+
+def _gather(t):
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t.contiguous())
+    return out
+
+
+def collectives_exact(gs, opt, dev):
+    """gs_syncbn_allreduce / gs_grad_allreduce == sum in rank order, bit for bit."""
+    Fg = gs.functional
+    rank, world = dist.get_rank(), dist.get_world_size()
+    res = {}
+    ex = Fg.PeerExchange.get(None)
+    ok = bool(ex)
+    if ex:
+        for n in (2, 38, 2 * 96, 2 * 1280, 8192):
+            g = torch.Generator().manual_seed(1000 * n + rank)
+            mine = (torch.randn(n, generator=g, dtype=torch.float64) * 10 ** (rank % 3)).to(dev)
+            parts = _gather(mine)
+            ref = torch.zeros_like(mine)
+            for r in range(world):
+                ref = ref + parts[r]
+            got = mine.clone()
+            ex.all_reduce(got)
+            torch.cuda.synchronize()
+            ok &= bool(torch.equal(got, ref))
+    res['syncbn_allreduce_bit_exact'] = ok
+    pg = opt.flat.peer_grad
+    ok = pg is not None
+    if pg is not None:
+        total = opt.flat.total
+        flat = opt.flat.flat_g
+        for (off, cnt) in ((0, total), (64, 4), (128, 4 * (world + 1) + 4), (total // 2 // 4 * 4, 1028), (total - 68, 68)):
+            g = torch.Generator().manual_seed(77 + off + rank)
+            flat.copy_(torch.randn(total, generator=g).to(dev))
+            torch.cuda.synchronize()
+            dist.barrier()
+            parts = _gather(flat.clone())
+            ref = parts[0].clone()
+            for r in range(1, world):
+                ref = ref + parts[r]
+            before = flat.clone()
+            pg.all_reduce(off, cnt)
+            torch.cuda.synchronize()
+            dist.barrier()
+            ok &= bool(torch.equal(flat[off:off + cnt], ref[off:off + cnt]))
+            ok &= bool(torch.equal(flat[:off], before[:off])) and bool(torch.equal(flat[off + cnt:], before[off + cnt:]))
+        flat.zero_()
+    res['grad_allreduce_bit_exact'] = ok
+    return res
+
+
+def run(gs, seed=5):
+    Fg = gs.functional
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    res = {'world': world}
+    gmN = _model(gs, seed, dev)
+    opt = gs.GsSGD(gmN, lr=0.01, momentum=0.9, weight_decay=5e-4)         # collective: maps the peer gradient buffers
+    res['peer_syncbn'] = bool(Fg.PeerExchange.get(None))
+    res['peer_grad'] = opt.flat.peer_grad is not None
+    res.update(collectives_exact(gs, opt, dev))
+
+    img, lab = _batch(world)
+    sl = slice(2 * rank, 2 * rank + 2)
+    local = dict(img=img[sl].to(dev), img_metas=[{}, {}], gt_semantic_seg=lab[sl].to(dev))
+    names = [n for n, p in gmN.named_parameters()]
+
+    def n_rank_step(overlap):
+        was, opt.flat._overlap = opt.flat._overlap, overlap      # per-stage overlapped chunks on / off for this pass
+        out = gmN.train_step(local, opt)
+        opt.zero_grad()
+        out['loss'].backward()
+        pre = None
+        if not overlap:
+            Fg.wgrad_join()
+            torch.cuda.synchronize()
+            pre = opt.flat.flat_g.clone()     # local gradients, before any exchange
+        w = opt.flat.all_reduce_grads()
+        torch.cuda.synchronize()
+        opt.flat._overlap = was
+        return out, w, pre, opt.flat.flat_g.clone()
+
+    outN, w, _, g_over = n_rank_step(overlap=True)
+    _, _, pre, g_plain = n_rank_step(overlap=False)
+    nccl = pre.clone()
+    dist.all_reduce(nccl)
+    den = float(g_plain.abs().max()) + 1e-30
+    res['grad_overlap_vs_plain_max_rel'] = float((g_over - g_plain).abs().max()) / den
+    res['grad_peer_vs_nccl_max_rel'] = float((g_plain - nccl).abs().max()) / den
+
+    # ONE rank on the concatenated batch: same parameters, SyncBN switched to local statistics
+    gm1 = _model(gs, seed, dev)
+    for m in gm1.modules():
+        if getattr(m, 'sync', False):
+            m.sync = False
+    gm1.log_vars_reduce = False
+    out1 = gm1.train_step(dict(img=img.to(dev), img_metas=[{}] * (2 * world), gt_semantic_seg=lab.to(dev)), None)
+    out1['loss'].backward()
+    torch.cuda.synchronize()
+    lossN, loss1 = float(outN['log_vars']['loss']), float(out1['loss'])
+    res['loss_n_rank'], res['loss_1_rank_global_batch'] = lossN, loss1
+    res['loss_rel'] = abs(lossN - loss1) / abs(loss1)
+    pN = dict(gmN.named_parameters())
+    p1 = dict(gm1.named_parameters())
+    worst, worst_name, num, den2 = 0.0, None, 0.0, 0.0
+    for n in names:
+        a = pN[n].grad
+        b = p1[n].grad
+        if b is None:
+            if a is not None and float(a.abs().max()) != 0.0:
+                worst, worst_name = float('inf'), n
+            continue
+        a = a.double() / w
+        b = b.double()
+        num += float((a - b).pow(2).sum())
+        den2 += float(b.pow(2).sum())
+        m = float(b.abs().max())
+        if m > 0:
+            e = float((a - b).abs().max()) / m
+            if e > worst:
+                worst, worst_name = e, n
+    res['grad_rel_l2_vs_1rank'] = math.sqrt(num / (den2 + 1e-300))
+    res['grad_max_rel_vs_1rank'] = worst
+    res['grad_worst_param'] = worst_name
+    bN = {n: b for n, b in gmN.named_buffers() if n.endswith(('running_mean', 'running_var'))}
+    b1 = dict(gm1.named_buffers())
+    # gmN saw the batch twice (overlap on / off), gm1 once: compare through the momentum recursion on the mean only when
+    # both were updated equally -> re-run gm1 forward once more without grad
+    with torch.no_grad():
+        gm1.train_step(dict(img=img.to(dev), img_metas=[{}] * (2 * world), gt_semantic_seg=lab.to(dev)), None)
+    torch.cuda.synchronize()
+    res['running_stats_max_abs_vs_1rank'] = max(float((b - b1[n]).abs().max()) for n, b in bN.items())
+    flat = torch.cat([b.flatten().float() for b in bN.values()])
+    ref = flat.clone()
+    dist.broadcast(ref, 0)
+    res['buffers_identical'] = bool(torch.equal(flat, ref))
+    opt.grad_scale = 1.0 / w
+    opt.step()
+    torch.cuda.synchronize()
+    pflat = opt.flat.flat_p.clone()
+    pref = pflat.clone()
+    dist.broadcast(pref, 0)
+    res['params_identical'] = bool(torch.equal(pflat, pref))
+    # tolerances: the two runs share every kernel and differ in summation order only (fp32 stat partials, split-K atomics),
+    # which flips a few bf16 roundings of stored activations; see DESIGN.md "Multi-GPU parity"
+    ok = (res['syncbn_allreduce_bit_exact'] and res['grad_allreduce_bit_exact'] and res['buffers_identical']
+          and res['params_identical'] and res['loss_rel'] <= 1e-4 and res['grad_rel_l2_vs_1rank'] <= 2e-3
+          and res['grad_max_rel_vs_1rank'] <= 2e-2 and res['grad_overlap_vs_plain_max_rel'] <= 1e-4
+          and res['grad_peer_vs_nccl_max_rel'] <= 1e-5 and res['running_stats_max_abs_vs_1rank'] <= 1e-4)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res['ok'] = bool(int(flag))
+    return res
+
+
+if __name__ == '__main__':
+    import json
+    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+    local = int(os.environ.get('LOCAL_RANK', rank))
+    torch.cuda.set_device(local)
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import gaia_seg_b200 as gs
+    r = run(gs)
+    if rank == 0:
+        print(json.dumps(r))
+    dist.destroy_process_group()
+    sys.exit(0 if r['ok'] else 1)
