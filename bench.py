@@ -119,10 +119,10 @@ class ClockSampler(threading.Thread):
 
 class CpuArm:
     """The CPU oracle (restatement of the reference's mmseg/gaiavision path, oracle/ref_model.py) on the host cores.
-    One CPU step = one sandwich cycle [MAX, MIN, rand, rand] (forward + loss + backward + SGD each) at batch ONE
-    3x512x1024 image per iteration: the same sub-net mix as a GPU step on half its batch -- a bounded sample
-    (about 5-20 s of CPU work).  4 images per CPU step."""
-    IMGS_PER_STEP = CYCLE
+    One CPU step = one sandwich cycle [MAX, MIN, rand, rand] (forward + loss + backward + SGD each) at the GPU arm's
+    per-GPU batch (2 x 3x512x1024 per iteration, 8 images per step, 4 rotating batches): literally one rank's step of
+    the GPU arm -- a bounded sample of about 10-30 s of CPU work."""
+    IMGS_PER_STEP = CYCLE * BATCH
 
     def __init__(self, variant):
         import torch
@@ -136,15 +136,17 @@ class CpuArm:
         MAX, MIN, rnd = sampler_cfg(variant)
         self.sampler = build_model_sampler(sandwich_sampler_cfg(MAX, MIN, rnd, num_random=2, seed=0))
         self.opt = torch.optim.SGD(self.model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
-        img, lab = synth_batch(0, 0)
-        self.img, self.lab = img[:1], lab[:1]
-        self.sample = ('one sandwich cycle [MAX, MIN, rand, rand] of fwd+loss+bwd+SGD iterations at batch 1x3x512x1024 '
-                       '(4 images; same sub-net mix as a GPU step, half its batch), torch CPU fp32 oracle')
+        self.batches = [synth_batch(0, i) for i in range(4)]
+        self.n_it = 0
+        self.sample = (f'one sandwich cycle [MAX, MIN, rand, rand] of fwd+loss+bwd+SGD iterations at batch {BATCH}x3x{IMG_H}x{IMG_W} '
+                       f'({CYCLE * BATCH} images = one rank\'s GPU step, same sub-net sampler and seed), torch CPU fp32 oracle')
 
     def iteration(self):
         self.model.manipulate_arch(self.fold(self.sampler.sample())['arch'])
         self.opt.zero_grad()
-        loss = self.model.parse_losses(self.model.forward_train(self.img, None, self.lab))
+        img, lab = self.batches[self.n_it % len(self.batches)]
+        self.n_it += 1
+        loss = self.model.parse_losses(self.model.forward_train(img, None, lab))
         loss.backward()
         self.opt.step()
         return float(loss.detach())
@@ -160,12 +162,16 @@ def run_reference(args):
         return
     arm = CpuArm(args.variant)
     t0 = time.perf_counter()
-    for _ in range(args.warmup):
+    n_warm = args.warmup
+    for i in range(args.warmup):
         arm.step()
-    per = (time.perf_counter() - t0) / max(args.warmup, 1)
+        if time.perf_counter() - t0 > 60 and i + 1 < args.warmup:   # a CPU step takes ~15-30 s: bound the warm-up too
+            n_warm = i + 1
+            break
+    per = (time.perf_counter() - t0) / max(n_warm, 1)
     steps = args.steps
-    if args.warmup and per * steps > 300:      # keep the whole run within a few minutes
-        steps = max(1, int(300 / per))
+    if args.warmup and per * steps > 150:      # keep the whole run within a few minutes
+        steps = max(1, int(150 / per))
     t0 = time.perf_counter()
     for _ in range(steps):
         arm.step()
@@ -173,11 +179,22 @@ def run_reference(args):
     v = steps * arm.IMGS_PER_STEP / dt
     print(json.dumps({
         'impl': 'reference', 'metric': 'supernet train imgs/s @512x1024', 'value': v, 'unit': 'imgs/s', 'n_gpus': args.gpus,
-        'steps': steps, 'steps_requested': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / steps,
+        'steps': steps, 'steps_requested': args.steps, 'warmup': n_warm, 'warmup_requested': args.warmup,
+        'ms_per_step': 1e3 * dt / steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args.variant), 'variant': args.variant},
+        'config': bench_config(args.variant, args.gpus),
+        'run': {'arm': 'reference CPU path (oracle port) on rank 0 only: ONE rank\'s share of the step '
+                       f'({arm.IMGS_PER_STEP} images per step); value = its images/s', 'threads': arm.cores},
         'cpu_baseline': {'value': v, 'unit': 'imgs/s', 'cores': arm.cores, 'kind': 'port', 'sample': arm.sample},
         'e2e': {'value': v, 'unit': 'imgs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def bench_config(variant, world):
+    """`config` of the JSON line -- the SAME dict for the B200 arm and the reference (CPU) arm."""
+    return {'workload': workload_name(variant), 'variant': variant, 'per_gpu_batch': BATCH, 'global_batch': BATCH * world,
+            'images_per_step': CYCLE * BATCH * world, 'parallelism': f'dp{world}',
+            'l2': 'inputs + activations of every iteration (>1 GB) exceed the 126 MB L2; 4 rotating input batches',
+            'subnet_sampler': 'sandwich [MAX, MIN, random x2], shared seed (all ranks draw the same sub-nets)'}
 
 
 def workload_name(variant):
@@ -215,12 +232,24 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    os.environ.setdefault('GS_COMM_TIMEOUT_S', '120')   # a benchmark must trap, not hang, if a peer never shows up
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node N'
     gs._lib.require_device()
     gs.set_random_seed(0)
+
+    # multi-rank correctness, CUDA vs CUDA on a small model, OUTSIDE the timed region (tools/multi_rank_parity.py): the
+    # exchange kernels bit-exact against ordered sums, N ranks vs one rank on the concatenated batch, overlapped vs plain vs
+    # NCCL gradients, buffers / parameters identical on all ranks -> `parity_multi` of the JSON line
+    parity_multi = None
+    if world > 1:
+        from tools.multi_rank_parity import run as multi_rank_parity
+        try:
+            parity_multi = multi_rank_parity(gs)
+        except Exception as e:   # noqa: BLE001  (report, do not hide the throughput numbers)
+            parity_multi = {'ok': False, 'error': f'{type(e).__name__}: {e}'}
 
     model = gs.build_segmentor(supernet_cfg(args.variant), train_cfg=dict(), test_cfg=dict(mode='whole')).to(dev)
     model.train()
@@ -237,6 +266,22 @@ def main():
     metas = [dict(ori_shape=(IMG_H, IMG_W, 3), flip=False)] * BATCH
     it_count = [0]
 
+    # algorithmic conv FLOPs of every iteration that runs, counted analytically per sampled sub-net (complexity.py:
+    # shape propagation, no device): forward 2*MACs + weight gradient 2*MACs + data gradient 2*(MACs - first conv: the
+    # gradient w.r.t. the image is never computed), times the per-GPU batch
+    from gaia_seg_b200.complexity import Counter, conv_macs
+    flops_box, flops_cache = [0.0], {}
+
+    def train_flops(key):
+        f = flops_cache.get(key)
+        if f is None:
+            macs = conv_macs(model, (3, IMG_H, IMG_W))
+            c0 = Counter()
+            bb = model.backbone
+            c0.conv(bb.stem[0] if bb.deep_stem else bb.conv1, (3, IMG_H, IMG_W))
+            f = flops_cache[key] = BATCH * (6.0 * macs - 2.0 * c0.conv_macs)
+        return f
+
     # with several ranks the graph holds forward + backward (incl. the peer-memory SyncBN exchanges); the NCCL gradient
     # all-reduce and the optimizer launch stay eager
     use_graphs = bool(args.graphs)
@@ -246,8 +291,10 @@ def main():
         meta = fold_dict(sampler_box[0].sample())
         model.manipulate_arch(meta['arch'])
         batch = dict(img=img, img_metas=metas, gt_semantic_seg=lab)
+        akey = json.dumps(meta['arch'], sort_keys=True)
+        flops_box[0] += train_flops(akey)
         if graphed is not None and gs._lib.PROFILE_CALLS is None and Fg.PROFILE is None:
-            out = graphed(json.dumps(meta['arch'], sort_keys=True), batch)
+            out = graphed(akey, batch)
         else:
             out = model.train_step(batch, opt)
             opt.zero_grad()
@@ -369,7 +416,9 @@ def main():
     t_w0 = time.time()
     sampler_box[0] = new_sampler(1)                # the timed loops below all see the SAME sequence of random sub-nets
     ms0 = torch.cuda.memory_stats(dev)
+    flops_box[0] = 0.0
     ms = timed(step_resident, args.steps)
+    step_flops = flops_box[0] / args.steps           # per GPU, mean over exactly the timed steps
     ms1 = torch.cuda.memory_stats(dev)
     alloc_info = {'cudaMalloc_calls_in_timed_region': ms1.get('num_device_alloc', 0) - ms0.get('num_device_alloc', 0),
                   'reserved_GB': round(ms1.get('reserved_bytes.all.current', 0) / 2 ** 30, 2)}
@@ -459,9 +508,7 @@ def main():
                          tflops=v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0) for k, v in shapes.items()]
             rows.sort(key=lambda r: -r['ms'])
             json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'conv_shapes.json'), 'w'), indent=0)
-        tot_flops = sum(v[0] for v in agg.values())
-        breakdown['conv_flops_per_step'] = tot_flops
-        breakdown['whole_step_tflops'] = tot_flops / (ms / args.steps * 1e-3) / 1e12
+        breakdown['profiled_cycle_conv_flops'] = sum(v[0] for v in agg.values())
 
     # ---- second half of the BASELINE metric: sub-net inference imgs/s (config 5: whole-image 1x3x1024x2048, eval-mode
     # BN folded into the conv epilogue, fused resize+argmax, label map read back to the host), rank 0 only ----
@@ -474,6 +521,12 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline(args.variant)
 
+    # whole-step roofline: analytic conv FLOPs of exactly the timed steps / measured step time, per GPU
+    step_tf = step_flops / (ms / args.steps * 1e-3) / 1e12
+    roof_step = {'bound': 'tensor', 'flops_per_step_per_gpu': step_flops, 'ms_per_step': ms / args.steps,
+                 'achieved': step_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': step_tf / peak_tf, 'peak_source': peak_src,
+                 'how': 'conv FLOPs (fwd + wgrad + dgrad, analytic per sampled sub-net, gaia_seg_b200/complexity.py) summed over '
+                        'the timed iterations / CUDA-event time of the timed region; memory-bound kernels count as overhead'}
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -481,15 +534,15 @@ def main():
             'metric': 'supernet train imgs/s @512x1024', 'value': value, 'unit': 'imgs/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': workload_name(args.variant), 'variant': args.variant, 'global_batch': BATCH * world,
-                       'images_per_step': imgs_per_step, 'parallelism': f'dp{world}',
-                       'cuda_graphs': 'MAX and MIN iterations replayed as CUDA graphs, random sub-nets eager' if use_graphs else 'off',
-                       'l2': 'inputs + activations of every iteration (>1 GB) exceed the 126 MB L2; 4 rotating input batches',
-                       'timing': 'CUDA events on the launching stream, barrier+sync both sides, max over ranks'},
+            'config': bench_config(args.variant, world),
+            'run': {'arm': 'b200', 'cuda_graphs': 'MAX and MIN iterations replayed as CUDA graphs, random sub-nets eager'
+                    if use_graphs else 'off',
+                    'timing': 'CUDA events on the launching stream, barrier+sync both sides, max over ranks'},
             'clocks': clk, 'gpu_launches': launches, 'allocator': alloc_info, 'host_enqueue_ms_per_step': host_enqueue_ms,
             'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps},
-            'roofline': roof, 'cpu_baseline': cpu_base, 'subnet_infer': infer, 'breakdown': breakdown}
+            'roofline': roof, 'roofline_step': roof_step, 'parity_multi': parity_multi, 'cpu_baseline': cpu_base,
+            'subnet_infer': infer, 'breakdown': breakdown}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -46,9 +46,6 @@ PROTOTYPES = {
     'gs_conv2d_dgrad_workspace_bytes': (_L, [_G]),
     'gs_conv2d_dgrad': (_I, [_G, _P, _P, _P, _P, _I, _P, _P, _P]),
     'gs_conv2d_wgrad': (_I, [_G, _P, _P, _P, _P]),
-    'gs_conv2d_fwd_simt': (_I, [_G, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
-    'gs_conv2d_dgrad_simt': (_I, [_G, _P, _P, _P, _P, _I, _P]),
-    'gs_conv2d_wgrad_simt': (_I, [_G, _P, _P, _P, _P]),
     'gs_im2col_image': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'gs_bn_stats': (_I, [_P, _L, _I, _I, _P, _P]),
     'gs_bn_finalize': (_I, [_P, _D, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),

@@ -118,51 +118,200 @@ __global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const float* __res
     }
 }
 
-__global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const float* __restrict__ logits, int N, int h, int w,
-                                                              int K, int ld, const PixRec* __restrict__ rec, int H,
-                                                              int W, float rh, float rw, float grad_scale,
-                                                              const float* __restrict__ grad_scale_dev,
-                                                              float* __restrict__ dlogits, int dl_ld) {
-    const long long total = (long long)N * h * w * K;
+// ------------------------------------------------------------------------------------------------
+// backward.  dlogits[n, i, j, k] = grad_scale * sum over valid output pixels (y, x) of
+//                                  wy(y, i) * wx(x, j) * ( exp(v_k(y, x) - lse(y, x)) - [label(y, x) == k] )
+// One CTA owns a TILE of low-res cells (all classes) and is the only writer of its dlogits -> no atomics, fixed
+// summation order (deterministic).  The tile's logits + a one-cell halo live in shared memory; every output pixel whose
+// taps touch the tile has its soft-max terms computed ONCE per CTA (the round-1 kernel recomputed them per
+// (cell, class) thread: ~4*19 times), and the bilinear weights are applied separably:
+//   phase 1  thread <-> output pixel of a strip of R rows:  G[r][x][k] = exp(v_k - lse) - [label == k]
+//   phase 2  thread <-> (row r, low-res column j, k):       T[r][j][k] = sum_x wx(x, j) * G[r][x][k]
+//   phase 3  thread <-> (low-res cell i, j, k):             ACC[i][j][k] += sum_r wy(y_r, i) * T[r][j][k]
+// then ONE coalesced store of ACC * grad_scale.  Classes are processed in chunks of <= kBwdKC (p_k only needs the
+// recorded log-sum-exp, so chunks are independent): K = 150 fits the same shared-memory budget as K = 19.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBwdTile = 8;        // low-res cells per tile edge
+constexpr int kBwdKC = 32;         // classes per chunk
+constexpr int kBwdThreads = 256;
+constexpr int kBwdMaxRegion = 512; // output pixels per tile edge the tap tables can hold (scale factors up to ~50)
+
+struct BwdSmem {
+    // byte offsets into the dynamic shared memory block (all 16-byte aligned)
+    int logits, G, T, acc, xt_i, xt_w, yt_i, yt_w, xr, yr, total;
+};
+
+__host__ __device__ inline BwdSmem bwd_smem_layout(int K, int KC, int XW, int R) {
+    BwdSmem L;
+    const int kcp = KC | 1;   // odd pitch: phase 1 writes a pixel's classes with lane stride kcp -> conflict-free
+    int off = 0;
+    auto take = [&](int bytes) { const int o = off; off += (bytes + 15) & ~15; return o; };
+    L.logits = take((kBwdTile + 2) * (kBwdTile + 2) * K * 4);
+    L.G = take(R * XW * kcp * 4);
+    L.T = take(R * kBwdTile * kcp * 4);
+    L.acc = take(kBwdTile * kBwdTile * kcp * 4);
+    L.xt_i = take(XW * 8);
+    L.xt_w = take(XW * 8);
+    L.yt_i = take(kBwdMaxRegion * 8);
+    L.yt_w = take(kBwdMaxRegion * 8);
+    L.xr = take(kBwdTile * 8);
+    L.yr = take(kBwdTile * 8);
+    L.total = off;
+    return L;
+}
+
+__global__ void __launch_bounds__(kBwdThreads) upsample_ce_bwd_kernel(const float* __restrict__ logits, int N, int h, int w,
+                                                                      int K, int ld, const PixRec* __restrict__ rec, int H,
+                                                                      int W, float rh, float rw, float grad_scale,
+                                                                      const float* __restrict__ grad_scale_dev,
+                                                                      float* __restrict__ dlogits, int dl_ld, int XWmax,
+                                                                      int R, int KC) {
+    extern __shared__ __align__(16) unsigned char smem_bwd[];
+    const BwdSmem L = bwd_smem_layout(K, KC, XWmax, R);
+    float* sL = reinterpret_cast<float*>(smem_bwd + L.logits);
+    float* sG = reinterpret_cast<float*>(smem_bwd + L.G);
+    float* sT = reinterpret_cast<float*>(smem_bwd + L.T);
+    float* sA = reinterpret_cast<float*>(smem_bwd + L.acc);
+    int2* xti = reinterpret_cast<int2*>(smem_bwd + L.xt_i);
+    float2* xtw = reinterpret_cast<float2*>(smem_bwd + L.xt_w);
+    int2* yti = reinterpret_cast<int2*>(smem_bwd + L.yt_i);
+    float2* ytw = reinterpret_cast<float2*>(smem_bwd + L.yt_w);
+    int2* xr = reinterpret_cast<int2*>(smem_bwd + L.xr);   // per tile column: [first, last] region index that touches it
+    int2* yr = reinterpret_cast<int2*>(smem_bwd + L.yr);
+    const int kcp = KC | 1;
+    const int tid = threadIdx.x;
     if (grad_scale_dev) grad_scale *= __ldg(grad_scale_dev);
+
+    const int tiles_w = (w + kBwdTile - 1) / kBwdTile, tiles_h = (h + kBwdTile - 1) / kBwdTile;
+    int t = blockIdx.x;
+    const int tj = t % tiles_w; t /= tiles_w;
+    const int ti = t % tiles_h;
+    const int n = t / tiles_h;
+    const int i0 = ti * kBwdTile, j0 = tj * kBwdTile;
+    const int th = min(kBwdTile, h - i0), tw = min(kBwdTile, w - j0);
+
+    // output-pixel region whose taps can touch the tile (one extra pixel of margin on each side; pixels that turn out
+    // not to touch it get zero weights below)
     const float inv_rh = 1.f / rh, inv_rw = 1.f / rw;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(idx % K);
-        long long t = idx / K;
-        const int j = (int)(t % w); t /= w;
-        const int i = (int)(t % h);
-        const int n = (int)(t / h);
-        int ylo = (int)floorf((i - 0.5f) * inv_rh - 0.5f) - 1;
-        int yhi = (int)ceilf((i + 1.5f) * inv_rh - 0.5f) + 1;
-        int xlo = (int)floorf((j - 0.5f) * inv_rw - 0.5f) - 1;
-        int xhi = (int)ceilf((j + 1.5f) * inv_rw - 0.5f) + 1;
-        if (ylo < 0) ylo = 0;
-        if (xlo < 0) xlo = 0;
-        if (yhi > H - 1) yhi = H - 1;
-        if (xhi > W - 1) xhi = W - 1;
-        const float* base = logits + (long long)n * h * w * ld + k;
-        float acc = 0.f;
-        for (int y = ylo; y <= yhi; ++y) {
-            const Tap ty = src_tap(rh, y, h);
-            const float wy = (ty.i0 == i ? ty.l0 : 0.f) + (ty.i1 == i ? ty.l1 : 0.f);
-            if (wy == 0.f) continue;
-            const float* r0 = base + (long long)ty.i0 * w * ld;
-            const float* r1 = base + (long long)ty.i1 * w * ld;
-            const PixRec* rrow = rec + ((long long)n * H + y) * W;
-            for (int x = xlo; x <= xhi; ++x) {
-                const Tap tx = src_tap(rw, x, w);
-                const float wx = (tx.i0 == j ? tx.l0 : 0.f) + (tx.i1 == j ? tx.l1 : 0.f);
-                if (wx == 0.f) continue;
-                const PixRec r = rrow[x];
-                if (r.label < 0) continue;
-                const float v = lerp4(ty, tx, __ldg(r0 + (long long)tx.i0 * ld), __ldg(r0 + (long long)tx.i1 * ld),
-                                      __ldg(r1 + (long long)tx.i0 * ld), __ldg(r1 + (long long)tx.i1 * ld));
-                const float g = __expf(v - r.lse) - (r.label == k ? 1.f : 0.f);
-                acc = fmaf(wy * wx, g, acc);
+    int ylo = (int)floorf((i0 - 0.5f) * inv_rh - 0.5f) - 1;
+    int yhi = (int)ceilf((i0 + th + 0.5f) * inv_rh - 0.5f) + 1;
+    int xlo = (int)floorf((j0 - 0.5f) * inv_rw - 0.5f) - 1;
+    int xhi = (int)ceilf((j0 + tw + 0.5f) * inv_rw - 0.5f) + 1;
+    if (ylo < 0) ylo = 0;
+    if (xlo < 0) xlo = 0;
+    if (yhi > H - 1) yhi = H - 1;
+    if (xhi > W - 1) xhi = W - 1;
+    const int XW = xhi - xlo + 1, YH = yhi - ylo + 1;   // host guarantees XW <= XWmax, YH <= kBwdMaxRegion
+
+    // tap tables + the tile's logits (with halo) -> shared memory
+    for (int i = tid; i < XW; i += kBwdThreads) {
+        const Tap tp = src_tap(rw, xlo + i, w);
+        xti[i] = make_int2(tp.i0, tp.i1);
+        xtw[i] = make_float2(tp.l0, tp.l1);
+    }
+    for (int i = tid; i < YH; i += kBwdThreads) {
+        const Tap tp = src_tap(rh, ylo + i, h);
+        yti[i] = make_int2(tp.i0, tp.i1);
+        ytw[i] = make_float2(tp.l0, tp.l1);
+    }
+    constexpr int LW = kBwdTile + 2;
+    for (int i = tid; i < LW * LW * K; i += kBwdThreads) {
+        const int k = i % K;
+        const int c = i / K;
+        const int lj = c % LW, li = c / LW;
+        const int gi = i0 - 1 + li, gj = j0 - 1 + lj;
+        float v = 0.f;
+        if (gi >= 0 && gi < h && gj >= 0 && gj < w) v = __ldg(logits + ((long long)(n * h + gi) * w + gj) * ld + k);
+        sL[i] = v;
+    }
+    __syncthreads();
+    if (tid < kBwdTile) {          // first / last region column touching tile column tid (taps are monotone in x)
+        int a = XW, b = -1;
+        for (int i = 0; i < XW; ++i)
+            if (xti[i].x == j0 + tid || xti[i].y == j0 + tid) { if (i < a) a = i; b = i; }
+        xr[tid] = make_int2(a, b);
+    } else if (tid >= 32 && tid < 32 + kBwdTile) {
+        const int c = tid - 32;
+        int a = YH, b = -1;
+        for (int i = 0; i < YH; ++i)
+            if (yti[i].x == i0 + c || yti[i].y == i0 + c) { if (i < a) a = i; b = i; }
+        yr[c] = make_int2(a, b);
+    }
+    __syncthreads();
+
+    for (int kc = 0; kc < K; kc += KC) {
+        const int kn = min(KC, K - kc);
+        for (int i = tid; i < kBwdTile * kBwdTile * kcp; i += kBwdThreads) sA[i] = 0.f;
+        for (int yb = 0; yb < YH; yb += R) {
+            const int rows = min(R, YH - yb);
+            // ---- phase 1: soft-max gradient terms of the strip, once per pixel ----
+            for (int p = tid; p < rows * XW; p += kBwdThreads) {
+                const int r = p / XW, xx = p - r * XW;
+                const int2 yi = yti[yb + r], xi = xti[xx];
+                float* g = sG + (size_t)(r * XW + xx) * kcp;
+                const PixRec pr = rec[((long long)n * H + (ylo + yb + r)) * W + (xlo + xx)];
+                const bool inside = yi.x >= i0 - 1 && yi.y <= i0 + th && xi.x >= j0 - 1 && xi.y <= j0 + tw;
+                if (pr.label < 0 || !inside) {
+                    for (int kk = 0; kk < kn; ++kk) g[kk] = 0.f;
+                    continue;
+                }
+                const float2 wy = ytw[yb + r], wx = xtw[xx];
+                Tap ty, tx;
+                ty.l0 = wy.x; ty.l1 = wy.y; tx.l0 = wx.x; tx.l1 = wx.y;
+                const float* a00 = sL + ((yi.x - i0 + 1) * LW + (xi.x - j0 + 1)) * K + kc;
+                const float* a01 = sL + ((yi.x - i0 + 1) * LW + (xi.y - j0 + 1)) * K + kc;
+                const float* a10 = sL + ((yi.y - i0 + 1) * LW + (xi.x - j0 + 1)) * K + kc;
+                const float* a11 = sL + ((yi.y - i0 + 1) * LW + (xi.y - j0 + 1)) * K + kc;
+                const int lab = pr.label - kc;
+                for (int kk = 0; kk < kn; ++kk) {
+                    const float v = lerp4(ty, tx, a00[kk], a01[kk], a10[kk], a11[kk]);
+                    g[kk] = __expf(v - pr.lse) - (kk == lab ? 1.f : 0.f);
+                }
             }
+            __syncthreads();
+            // ---- phase 2: horizontal taps: T[r][j][kk] = sum_x wx(x, j) * G[r][x][kk]  (x ascending: fixed order) ----
+            for (int o = tid; o < rows * tw * kn; o += kBwdThreads) {
+                const int kk = o % kn;
+                const int c = o / kn;
+                const int j = c % tw, r = c / tw;
+                const int2 range = xr[j];
+                float acc = 0.f;
+                const float* g = sG + (size_t)(r * XW) * kcp + kk;
+                for (int xx = range.x; xx <= range.y; ++xx) {
+                    const int2 xi = xti[xx];
+                    const float2 wx = xtw[xx];
+                    const float wgt = (xi.x == j0 + j ? wx.x : 0.f) + (xi.y == j0 + j ? wx.y : 0.f);
+                    acc = fmaf(wgt, g[(size_t)xx * kcp], acc);
+                }
+                sT[(r * kBwdTile + j) * kcp + kk] = acc;
+            }
+            __syncthreads();
+            // ---- phase 3: vertical taps into the tile accumulators (rows ascending: fixed order) ----
+            for (int o = tid; o < th * tw * kn; o += kBwdThreads) {
+                const int kk = o % kn;
+                const int c = o / kn;
+                const int j = c % tw, i = c / tw;
+                const int2 range = yr[i];
+                const int ra = max(range.x - yb, 0), rb = min(range.y - yb, rows - 1);
+                float acc = sA[(i * kBwdTile + j) * kcp + kk];
+                for (int r = ra; r <= rb; ++r) {
+                    const int2 yi = yti[yb + r];
+                    const float2 wy = ytw[yb + r];
+                    const float wgt = (yi.x == i0 + i ? wy.x : 0.f) + (yi.y == i0 + i ? wy.y : 0.f);
+                    acc = fmaf(wgt, sT[(r * kBwdTile + j) * kcp + kk], acc);
+                }
+                sA[(i * kBwdTile + j) * kcp + kk] = acc;
+            }
+            __syncthreads();
         }
-        dlogits[((long long)(n * h + i) * w + j) * dl_ld + k] = acc * grad_scale;
+        // ---- store the chunk: consecutive threads -> consecutive classes of one cell ----
+        for (int o = tid; o < th * tw * kn; o += kBwdThreads) {
+            const int kk = o % kn;
+            const int c = o / kn;
+            const int j = c % tw, i = c / tw;
+            dlogits[((long long)(n * h + i0 + i) * w + (j0 + j)) * dl_ld + kc + kk] = sA[(i * kBwdTile + j) * kcp + kk] * grad_scale;
+        }
+        __syncthreads();
     }
 }
 
@@ -248,9 +397,27 @@ extern "C" int gs_upsample_ce_bwd(const float* logits, int32_t N, int32_t h, int
     GS_REQUIRE(logits && pix_rec && dlogits, "upsample_ce_bwd: null pointer");
     GS_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && K > 0 && ld >= K && dl_ld >= K, "upsample_ce_bwd: bad shape");
     const float rh = static_cast<float>(h) / static_cast<float>(H), rw = static_cast<float>(w) / static_cast<float>(W);
-    upsample_ce_bwd_kernel<<<loss_grid((long long)N * h * w * K), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    // widest output-pixel region a tile can touch (same arithmetic as the kernel, + slack), strip height R and class chunk
+    // sized for <= ~96 KB of shared memory per CTA (2 CTAs per SM)
+    const int xw_max = static_cast<int>(ceilf((kBwdTile + 1.5f) / rw)) + 6;
+    const int yh_max = static_cast<int>(ceilf((kBwdTile + 1.5f) / rh)) + 6;
+    GS_REQUIRE(xw_max <= kBwdMaxRegion && yh_max <= kBwdMaxRegion,
+               "upsample_ce_bwd: scale factor %dx%d -> %dx%d too large for the tile tables", h, w, H, W);
+    const int KC = K < kBwdKC ? K : kBwdKC;
+    int R = (40 * 1024) / (xw_max * (KC | 1) * 4);
+    if (R < 1) R = 1;
+    if (R > 16) R = 16;
+    const BwdSmem L = bwd_smem_layout(K, KC, xw_max, R);
+    GS_REQUIRE(L.total <= 200 * 1024, "upsample_ce_bwd: %d classes need %d bytes of shared memory", K, L.total);
+    static int attr_bytes = 0;
+    if (L.total > attr_bytes) {
+        GS_CUDA_OK(cudaFuncSetAttribute(upsample_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        attr_bytes = L.total;
+    }
+    const int tiles = N * ((h + kBwdTile - 1) / kBwdTile) * ((w + kBwdTile - 1) / kBwdTile);
+    upsample_ce_bwd_kernel<<<tiles, kBwdThreads, L.total, static_cast<cudaStream_t>(stream)>>>(
         logits, N, h, w, K, ld, reinterpret_cast<const PixRec*>(pix_rec), H, W, rh, rw, grad_scale, grad_scale_dev, dlogits,
-        dl_ld);
+        dl_ld, xw_max, R, KC);
     GS_LAUNCHED();
     return 0;
 }

@@ -21,9 +21,6 @@ from ._lib import ConvGeom, GsError, call
 
 BF16 = torch.bfloat16
 
-# 'tc' = tcgen05 implicit GEMM (product path); 'simt' = CUDA-core triage kernels (debug only)
-CONV_IMPL = os.environ.get('GS_CONV_IMPL', 'tc')
-
 # bench.py sets this to a list to time every convolution launch with CUDA events on the launching stream:
 # entries are (kind, algorithmic_flops, start_event, end_event)
 PROFILE = None
@@ -308,8 +305,7 @@ def conv_forward(x, conv, Co, scale=None, shift=None, residual=None, relu=False,
     if residual is not None:
         residual = as_act(residual)
         res_ld = act_ld(residual)
-    fn = 'gs_conv2d_fwd' if CONV_IMPL == 'tc' else 'gs_conv2d_fwd_simt'
-    _timed_call('fwd', g, fn, ctypes.byref(g), a.data_ptr(), krsc.data_ptr(), y.data_ptr(), _ptr(scale), _ptr(shift),
+    _timed_call('fwd', g, 'gs_conv2d_fwd', ctypes.byref(g), a.data_ptr(), krsc.data_ptr(), y.data_ptr(), _ptr(scale), _ptr(shift),
                 _ptr(residual), res_ld, flags, _ptr(stats), st)
     return y, stats, a, g
 
@@ -330,7 +326,7 @@ def conv_wgrad(conv, a, dy, g):
     st = _stream()
     gw = _weight_grad(conv)
     g.y_ld = act_ld(dy)
-    fn = 'gs_conv2d_wgrad' if CONV_IMPL == 'tc' else 'gs_conv2d_wgrad_simt'
+    fn = 'gs_conv2d_wgrad'
     if is_image_conv(conv):
         Co_max = conv.out_channels
         K = conv.kernel_size[0] * conv.kernel_size[1] * conv.in_channels
@@ -354,16 +350,12 @@ def conv_dgrad(conv, dy, g, x_shape, add=None):
         add = as_act(add)
         add_ld = act_ld(add)
     st = _stream()
-    if CONV_IMPL == 'tc':
-        ws = None
-        nbytes = _lib.load().gs_conv2d_dgrad_workspace_bytes(ctypes.byref(g))
-        if nbytes > 0:
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dy.device)
-        _timed_call('dgrad', g, 'gs_conv2d_dgrad', ctypes.byref(g), dy.data_ptr(), krsc.data_ptr(), dx.data_ptr(),
-                    _ptr(add), add_ld, _ptr(ws), None, st)
-    else:
-        _timed_call('dgrad', g, 'gs_conv2d_dgrad_simt', ctypes.byref(g), dy.data_ptr(), krsc.data_ptr(), dx.data_ptr(),
-                    _ptr(add), add_ld, st)
+    ws = None
+    nbytes = _lib.load().gs_conv2d_dgrad_workspace_bytes(ctypes.byref(g))
+    if nbytes > 0:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dy.device)
+    _timed_call('dgrad', g, 'gs_conv2d_dgrad', ctypes.byref(g), dy.data_ptr(), krsc.data_ptr(), dx.data_ptr(),
+                _ptr(add), add_ld, _ptr(ws), None, st)
     return dx
 
 
@@ -379,7 +371,9 @@ def bn_batch_mode(bn):
 def _all_agree(ok, group=None):
     """Collective AND over the group: the peer-memory path is taken only when EVERY rank could set it up -- a rank that
     fell back to NCCL alone while its peers spin in the peer kernels would hang the job."""
-    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=torch.device('cuda', torch.cuda.current_device()))
+    on_gpu = torch.cuda.is_available() and str(dist.get_backend(group)).lower() != 'gloo'
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32,
+                     device=torch.device('cuda', torch.cuda.current_device()) if on_gpu else torch.device('cpu'))
     dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
     return bool(int(t.item()))
 
@@ -466,7 +460,7 @@ class PeerExchange:
         inst = cls._instances.get(key)
         if inst is None:
             world = dist.get_world_size(group)
-            want = os.environ.get('GS_SYNCBN_PEER', '1') != '0' and world <= 8
+            want = os.environ.get('GS_SYNCBN_PEER', '1') != '0' and world <= 8 and torch.cuda.is_available()
             if not _all_agree(want, group):
                 inst = False
             else:

@@ -104,14 +104,6 @@ int gs_conv2d_wgrad(const gs_conv_geom* g, const void* x, const void* dy, float*
 int gs_im2col_image(const float* img_nchw, int32_t N, int32_t C, int32_t H, int32_t W, int32_t kh, int32_t kw,
                     int32_t stride, int32_t pad, int32_t Ho, int32_t Wo, int32_t Kpad, void* out, void* stream);
 
-/* Debug / triage twins of the three convolution entry points on CUDA cores (one thread per output,
- * same arguments and math contract; dgrad reads w_krsc).  Not the product path. */
-int gs_conv2d_fwd_simt(const gs_conv_geom* g, const void* x, const void* w_krsc, void* y, const float* scale,
-                       const float* shift, const void* residual, int32_t res_ld, int32_t flags, double* stats,
-                       void* stream);
-int gs_conv2d_dgrad_simt(const gs_conv_geom* g, const void* dy, const void* w_krsc, void* dx, const void* residual,
-                         int32_t res_ld, void* stream);
-int gs_conv2d_wgrad_simt(const gs_conv_geom* g, const void* x, const void* dy, float* dw_krsc, void* stream);
 
 /* ---- dynamic batch norm ------------------------------------------------------------------ */
 /* replaces: [EXT] DynamicBatchNorm2d / DynamicSyncBatchNorm.forward == F.batch_norm on

@@ -1,13 +1,14 @@
 // gs_conv_simt.cu -- direct (one thread per output) convolution kernels on CUDA cores.
 //
-// NOT the product path: these exist to triage the tcgen05 implicit-GEMM kernels on the GPU box
-// (same C-ABI arguments, suffix _simt; selected with GS_CONV_IMPL=simt on the Python side and used
-// by tests/ to separate "descriptor / pipeline bug" from "host-side geometry bug").  Same math
+// TEST INFRASTRUCTURE, not the product: built into tests/libgaiaseg_simt.so (never into libgaiaseg_b200.so) and loaded
+// only by tests/gs_checks.py / tools/gpu_diag.py to triage the tcgen05 implicit-GEMM kernels on the GPU box
+// (same C-ABI arguments, suffix _simt: separates "descriptor / pipeline bug" from "host-side geometry bug").  Same math
 // contract: bf16 operands, fp32 accumulation, identical epilogue order.
 #include <cuda_bf16.h>
 
 #include "../../include/gaiaseg_b200.h"
-#include "gs_host.h"
+#include "../../gaia_seg_b200/csrc/gs_host.h"
+#include "gs_conv_simt.h"
 
 namespace gs {
 

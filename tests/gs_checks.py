@@ -24,6 +24,59 @@ from oracle import ref_model as O  # noqa: E402
 BF16_EPS = 2.0 ** -8
 
 
+# ------------------------------------------------------------------------------------------------
+# test-only CUDA-core conv twins (tests/csrc/gs_conv_simt.cu -> tests/libgaiaseg_simt.so)
+# ------------------------------------------------------------------------------------------------
+_SIMT = None
+
+
+def simt_lib():
+    import ctypes
+    global _SIMT
+    if _SIMT is None:
+        from gaia_seg_b200._lib import ConvGeom
+        lib = ctypes.CDLL(os.path.join(ROOT, 'tests', 'libgaiaseg_simt.so'))
+        P, I, G = ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ConvGeom)
+        lib.gs_conv2d_fwd_simt.argtypes = [G, P, P, P, P, P, P, I, I, P, P]
+        lib.gs_conv2d_dgrad_simt.argtypes = [G, P, P, P, P, I, P]
+        lib.gs_conv2d_wgrad_simt.argtypes = [G, P, P, P, P]
+        lib.gs_last_error.restype = ctypes.c_char_p
+        _SIMT = lib
+    return _SIMT
+
+
+class simt_convs:
+    """Context manager (tests / tools/gpu_diag.py only): route the three convolution entry points of the launch layer to
+    the CUDA-core twins, everything else stays on the product library -- separates a tcgen05 descriptor / pipeline bug from
+    a host-side geometry bug.  The product has no such switch."""
+
+    def __init__(self, gs):
+        self.Fg = gs.functional
+
+    def __enter__(self):
+        lib, Fg = simt_lib(), self.Fg
+        self.orig = Fg.call
+
+        def call(name, *args):
+            if name == 'gs_conv2d_fwd':
+                rc = lib.gs_conv2d_fwd_simt(*args)
+            elif name == 'gs_conv2d_dgrad':      # (g, dy, w, dx, residual, res_ld, workspace, fuse, stream)
+                rc = lib.gs_conv2d_dgrad_simt(*(args[:6] + args[8:]))
+            elif name == 'gs_conv2d_wgrad':
+                rc = lib.gs_conv2d_wgrad_simt(*args)
+            else:
+                return self.orig(name, *args)
+            if rc != 0:
+                raise self.Fg.GsError(f'{name}_simt failed ({rc}): {lib.gs_last_error().decode()}')
+
+        Fg.call = call
+        return self
+
+    def __exit__(self, *exc):
+        self.Fg.call = self.orig
+        return False
+
+
 def bf16r(t):
     """Round an fp32 tensor to bf16-representable values (kept in fp32)."""
     return t.to(torch.bfloat16).float()
@@ -164,13 +217,16 @@ def _mk_conv(case, dev, gs, bias=False):
     return conv, x, g
 
 
+def with_simt(gs, fn):
+    with simt_convs(gs):
+        return fn()
+
+
 def conv_case_checks(case, gs, impl=None):
     """fwd / dgrad / wgrad of one geometry against F.conv2d on the CPU (fp64)."""
+    import contextlib
     Fg = gs.functional
-    if impl is not None:
-        old = Fg.CONV_IMPL
-        Fg.CONV_IMPL = impl
-    try:
+    with (simt_convs(gs) if impl == 'simt' else contextlib.nullcontext()):
         name, N, H, W, Ci, Co, k, s, p, d, Ci_max, Co_max = case
         tag = f'conv[{name}]' + (f'[{impl}]' if impl else '')
         dev = torch.device('cuda')
@@ -201,9 +257,6 @@ def conv_case_checks(case, gs, impl=None):
         rest[:Co, :Ci] = 0
         out.append(dict(name=tag + '.wgrad_outside_slice_zero', ok=bool((rest == 0).all()), err=float(rest.abs().max()), tol=0))
         return out
-    finally:
-        if impl is not None:
-            Fg.CONV_IMPL = old
 
 
 def conv_epilogue_checks(gs):
@@ -381,7 +434,8 @@ def _labels(g, N, K, H, W, ignore_ratio=0.1):
     return lab
 
 
-def loss_checks(gs, cases=((2, 19, 16, 32, 128, 256), (1, 150, 8, 8, 64, 64), (2, 19, 7, 9, 33, 50), (1, 19, 16, 16, 16, 16))):
+def loss_checks(gs, cases=((2, 19, 16, 32, 128, 256), (1, 150, 8, 8, 64, 64), (2, 19, 7, 9, 33, 50), (1, 19, 16, 16, 16, 16),
+                           (1, 19, 20, 24, 10, 12), (1, 150, 17, 5, 19, 40), (1, 7, 3, 3, 150, 150), (2, 150, 16, 16, 128, 128))):
     """fused upsample + CE(ignore) + accuracy and its gradient vs the oracle (F.interpolate -> cross_entropy)."""
     Fg = gs.functional
     dev = torch.device('cuda')

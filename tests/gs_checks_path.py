@@ -503,3 +503,36 @@ def config3_full_size_checks(gs):
     out.append(dict(name='config3.R101_ASPP.labelmap_agreement', ok=agree >= 0.97, err=1 - agree, tol=0.03,
                     seconds=round(time.time() - t0, 1)))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# fused upsample + CE at the benchmark size, forward AND backward values
+# ------------------------------------------------------------------------------------------------
+def loss_full_size_checks(gs):
+    """2 x 19 x 64 x 128 -> 512 x 1024 (the benchmark's loss call) and 2 x 150 x 64 x 64 -> 512 x 512 (config 4): loss,
+    exact ignored-pixel count and dlogits against F.interpolate -> cross_entropy autograd on the host."""
+    Fg = gs.functional
+    out = []
+    for (N, K, h, w, H, W) in ((2, 19, 64, 128, 512, 1024), (2, 150, 64, 64, 512, 512)):
+        g = torch.Generator().manual_seed(K + H)
+        tag = f'loss_full[N{N},K{K},{h}x{w}->{H}x{W}]'
+        logits = torch.randn(N, K, h, w, generator=g) * 2
+        lab = C._labels(g, N, K, H, W)
+        lo = logits.clone().requires_grad_(True)
+        up = F.interpolate(lo, size=(H, W), mode='bilinear', align_corners=False)
+        loss_o = O.cross_entropy(up, lab.squeeze(1), 255)
+        loss_o.backward()
+        lg = logits.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        loss_g, acc_g, counts = Fg.upsample_ce(lg, lab.cuda(), 255, 1.0)
+        loss_g.backward()
+        torch.cuda.synchronize()
+        out.append(check_f32(loss_g.reshape(1).cpu(), loss_o.detach().reshape(1), tag + '.loss', 1e-4))
+        n_ign = int((lab == 255).sum())
+        out.append(dict(name=tag + '.ignored_count_exact', ok=int(counts[0]) == n_ign, err=abs(int(counts[0]) - n_ign), tol=0))
+        out.append(check_f32(lg.grad.cpu(), lo.grad, tag + '.dlogits', 2e-3))
+        # deterministic: a second backward gives bit-identical gradients (single writer per cell, fixed order)
+        lg2 = logits.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        Fg.upsample_ce(lg2, lab.cuda(), 255, 1.0)[0].backward()
+        torch.cuda.synchronize()
+        out.append(dict(name=tag + '.dlogits_bitwise_reproducible', ok=bool(torch.equal(lg.grad, lg2.grad)), err=0.0, tol=0))
+    return out

@@ -30,6 +30,10 @@ def test_dropout2d_injected_mask(gs):
     _assert_all(P.dropout_checks(gs))
 
 
+def test_fused_loss_full_size_fwd_bwd(gs):
+    _assert_all(P.loss_full_size_checks(gs))
+
+
 def test_rescale_two_step_resize(gs):
     _assert_all(P.rescale_checks(gs))
 

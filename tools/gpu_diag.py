@@ -11,9 +11,10 @@ OUT = os.path.join(ROOT, 'gpurun_out')
 
 GROUPS = {
     # name: (env, python expression over `C` (tests/gs_checks) and `gs`)
-    'simt_conv': ({'GS_CONV_IMPL': 'simt'}, "sum((C.conv_case_checks(c, gs, 'simt') for c in C.CONV_CASES), [])"),
-    'elementwise': ({'GS_CONV_IMPL': 'simt'}, "C.image_conv_checks(gs) + C.bn_checks(gs) + C.standalone_bn_checks(gs) + C.maxpool_checks(gs) + C.loss_checks(gs) + C.argmax_checks(gs)"),
-    'model_simt': ({'GS_CONV_IMPL': 'simt'}, "C.model_checks(gs)"),
+    # (the *_simt groups route the three conv entry points to the TEST-ONLY CUDA-core twins, tests/libgaiaseg_simt.so)
+    'simt_conv': ({}, "sum((C.conv_case_checks(c, gs, 'simt') for c in C.CONV_CASES), [])"),
+    'elementwise': ({}, "C.with_simt(gs, lambda: C.image_conv_checks(gs) + C.bn_checks(gs) + C.standalone_bn_checks(gs)) + C.maxpool_checks(gs) + C.loss_checks(gs) + C.argmax_checks(gs)"),
+    'model_simt': ({}, "C.with_simt(gs, lambda: C.model_checks(gs))"),
     'tc_1x1': ({}, "sum((C.conv_case_checks(c, gs, 'tc') for c in C.CONV_CASES if c[0].startswith('1x1') and 's2' not in c[0]), [])"),
     'tc_3x3': ({}, "sum((C.conv_case_checks(c, gs, 'tc') for c in C.CONV_CASES if c[0].startswith('3x3') and 's2' not in c[0]), [])"),
     'tc_s2': ({}, "sum((C.conv_case_checks(c, gs, 'tc') for c in C.CONV_CASES if 's2' in c[0]), [])"),
@@ -23,6 +24,16 @@ GROUPS = {
     'psp_ops': ({}, "C.psp_op_checks(gs)"),
     'full_size': ({}, "C.full_size_checks(gs)"),
     'model_tc': ({}, "C.model_checks(gs)"),
+    'sgd': ({}, "P.sgd_checks(gs)"),
+    'bn_calib': ({}, "P.bn_calibration_checks(gs)"),
+    'dropout': ({}, "P.dropout_checks(gs)"),
+    'rescale': ({}, "P.rescale_checks(gs)"),
+    'loss_full': ({}, "P.loss_full_size_checks(gs)"),
+    'big_conv': ({}, "sum((P.big_conv_case_checks(c, gs) for c in P.BIG_CONV_CASES), [])"),
+    'deep_stage': ({}, "P.deep_stage_checks(gs)"),
+    'config3': ({}, "P.config3_full_size_checks(gs)"),
+    'loss': ({}, "C.loss_checks(gs) + C.argmax_checks(gs)"),
+    'small_ops': ({}, "C.maxpool_checks(gs) + C.standalone_bn_checks(gs) + P.dropout_checks(gs)[:5]"),
 }
 
 CHILD = r'''
@@ -31,6 +42,7 @@ sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests')
 import torch
 import gaia_seg_b200 as gs
 import gs_checks as C
+import gs_checks_path as P
 res = []
 try:
     res = {expr}
@@ -53,7 +65,7 @@ def main():
         code = CHILD.format(root=ROOT, expr=expr, name=name, out=out)
         t0 = time.time()
         try:
-            r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=420)
+            r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=int(os.environ.get('GS_DIAG_TIMEOUT', '420')))
             tail = (r.stdout[-1500:] + r.stderr[-2500:])
             rc = r.returncode
         except subprocess.TimeoutExpired as e:
