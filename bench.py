@@ -390,6 +390,20 @@ def main():
         rows = sorted(({'kernel': k, 'ms': v[0] / 1e3, 'launches': v[1]} for k, v in agg.items()), key=lambda r: -r['ms'])
         os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
         json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'kineto_kernels.json'), 'w'), indent=0)
+        # compact timeline (name, stream, start us, duration us) of every kernel of the cycle, for gap / overlap analysis
+        try:
+            tmp = os.path.join(ROOT, 'gpurun_out', '_trace_full.json')
+            prof.export_chrome_trace(tmp)
+            ev = json.load(open(tmp)).get('traceEvents', [])
+            ker = [(e['name'].split('(')[0][:60], e.get('args', {}).get('stream'), e['ts'], e['dur']) for e in ev
+                   if e.get('ph') == 'X' and e.get('cat') in ('kernel', 'gpu_memcpy', 'gpu_memset')]
+            ker.sort(key=lambda r: r[2])
+            t0 = ker[0][2] if ker else 0
+            json.dump([(n, s_, round(ts - t0, 3), round(d, 3)) for n, s_, ts, d in ker],
+                      open(os.path.join(ROOT, 'gpurun_out', 'kineto_timeline.json'), 'w'))
+            os.remove(tmp)
+        except Exception as e:   # noqa: BLE001
+            print('timeline export failed:', e, file=sys.stderr)
     if args.host_profile and rank != 0:
         step_resident()
         torch.cuda.synchronize()

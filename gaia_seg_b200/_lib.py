@@ -27,6 +27,11 @@ class BnBwdFuse(Structure):
                 ('relu', c_int32), ('sums', c_void_p)]
 
 
+class SyncDesc(Structure):
+    """struct gs_sync_desc (include/gaiaseg_b200.h): the SyncBN peer exchange a DynBN kernel runs itself."""
+    _fields_ = [('peer_inboxes', c_void_p), ('rank', c_int32), ('world', c_int32), ('seq_dev', c_void_p)]
+
+
 _P = c_void_p
 _I = c_int32
 _L = c_int64
@@ -51,7 +56,8 @@ PROTOTYPES = {
     'gs_bn_finalize': (_I, [_P, _D, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
     'gs_bn_eval_affine': (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P]),
     'gs_bn_apply': (_I, [_P, _I, _P, _P, _P, _I, _I, _P, _I, _L, _I, _P]),
-    'gs_bn_apply_train': (_I, [_P, _I, _P, _D, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _P, _I, _L, _I, _P]),
+    'gs_bn_apply_train': (_I, [_P, _I, _P, _D, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _P, _I, _L, _I, _P, _P]),
+    'gs_bn_bwd': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _D, _L, _I, _P, _I, _P, _I, _P, _P, _P, _P]),
     'gs_bn_bwd_reduce': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _L, _I, _P, _P]),
     'gs_bn_bwd_apply': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _D, _L, _I, _P, _I, _P, _I, _P, _P, _P]),
     'gs_affine_bwd': (_I, [_P, _I, _P, _I, _P, _L, _I, _P, _I, _P, _I, _P]),

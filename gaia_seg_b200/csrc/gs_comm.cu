@@ -17,6 +17,7 @@
 // dgamma += sum g*xhat) -- they are averaged later by the gradient all-reduce like every other parameter gradient.
 #include "../../include/gaiaseg_b200.h"
 #include "gs_host.h"
+#include "gs_comm.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -24,97 +25,14 @@
 
 namespace gs {
 
-constexpr int kCommSlots = 4;
-constexpr int kCommMaxWorld = 8;
-constexpr int kCommSlotDoubles = 2 * 4096;   // 2*C doubles, C <= 4096
 constexpr int kCommThreads = 1024;
-constexpr int kCommPerThread = kCommSlotDoubles / kCommThreads;
-
-struct PeerPtrs {
-    ulonglong2* p[kCommMaxWorld];
-};
-
-__device__ __forceinline__ void st_u64_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ ulonglong2 ld_v2_sys(const ulonglong2* p) {
-    ulonglong2 v;
-    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 __global__ void __launch_bounds__(kCommThreads) syncbn_allreduce_kernel(double* __restrict__ stats, int n, PeerPtrs peers,
                                                                         int rank, int world, unsigned long long* seq_dev,
                                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                         unsigned long long timeout_ns) {
-    const int tid = threadIdx.x;
-    const unsigned long long seq = *seq_dev + 1;     // every thread reads the counter; thread 0 bumps it at the very end
-    const unsigned long long tag = (seq & 0xFFFFFFFFull) << 32;
-    const int slot = static_cast<int>(seq % kCommSlots);
-    double mine[kCommPerThread];
-    // 1. push the local contribution to every peer
-#pragma unroll
-    for (int k = 0; k < kCommPerThread; ++k) {
-        const int i = tid + k * kCommThreads;
-        if (i < n) {
-            const double v = stats[i];
-            mine[k] = v;
-            const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
-            const unsigned long long w0 = (b & 0xFFFFFFFFull) | tag, w1 = (b >> 32) | tag;
-            for (int r = 0; r < world; ++r) {
-                if (r == rank) continue;
-                unsigned long long* dst = reinterpret_cast<unsigned long long*>(
-                    peers.p[r] + (static_cast<size_t>(slot) * world + rank) * kCommSlotDoubles + i);
-                st_u64_sys(dst, w0);
-                st_u64_sys(dst + 1, w1);
-            }
-        }
-    }
-    // BN parameter gradients from the LOCAL sums (n = 2C: [sum g | sum g*xhat])
-    if (dbeta != nullptr || dgamma != nullptr) {
-        const int C = n >> 1;
-#pragma unroll
-        for (int k = 0; k < kCommPerThread; ++k) {
-            const int i = tid + k * kCommThreads;
-            if (i < n) {
-                if (i < C) { if (dbeta) dbeta[i] += static_cast<float>(mine[k]); }
-                else if (dgamma) dgamma[i - C] += static_cast<float>(mine[k]);
-            }
-        }
-    }
-    // 2. poll the own inbox, reduce in rank order
-    const ulonglong2* inbox = peers.p[rank] + static_cast<size_t>(slot) * world * kCommSlotDoubles;
-    const unsigned long long t0 = gtimer();
-#pragma unroll
-    for (int k = 0; k < kCommPerThread; ++k) {
-        const int i = tid + k * kCommThreads;
-        if (i < n) {
-            double s = 0.0;
-            for (int r = 0; r < world; ++r) {
-                if (r == rank) { s += mine[k]; continue; }
-                const ulonglong2* src = inbox + static_cast<size_t>(r) * kCommSlotDoubles + i;
-                ulonglong2 w = ld_v2_sys(src);
-                unsigned int spins = 0;
-                while ((w.x & 0xFFFFFFFF00000000ull) != tag || (w.y & 0xFFFFFFFF00000000ull) != tag) {
-                    if ((++spins & 1023u) == 0 && gtimer() - t0 > timeout_ns) {
-                        printf("gaiaseg_b200: SyncBN peer exchange timed out (rank %d waiting for rank %d, seq %llu)\n", rank,
-                               r, seq);
-                        __trap();
-                    }
-                    w = ld_v2_sys(src);
-                }
-                s += __longlong_as_double(static_cast<long long>((w.x & 0xFFFFFFFFull) | (w.y << 32)));
-            }
-            stats[i] = s;
-        }
-    }
-    __syncthreads();      // every thread has read *seq_dev long before, but keep the bump strictly last
-    if (tid == 0) *seq_dev = seq;
+    pdl_sync();
+    syncbn_exchange_block(stats, n, peers, rank, world, seq_dev, dgamma, dbeta, timeout_ns, threadIdx.x, kCommThreads);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -137,6 +55,7 @@ struct FlagPtrs {
 
 __global__ void peer_barrier_kernel(FlagPtrs flags, int rank, int world, unsigned long long* seq_dev, int set, int bump,
                                     unsigned long long timeout_ns) {
+    pdl_sync();
     const int tid = threadIdx.x;
     const unsigned long long seq = *seq_dev + (bump ? 1ull : 0ull);
     __syncthreads();
@@ -170,6 +89,7 @@ __device__ __forceinline__ void st_f4_sys(float4* p, const float4& v) {
 }
 
 __global__ void __launch_bounds__(256) grad_reduce_push_kernel(GradPtrs ptrs, long long lo4, long long hi4, int world) {
+    pdl_sync();
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = lo4 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < hi4; i += stride) {
         float4 v[kCommMaxWorld];
@@ -190,7 +110,7 @@ __global__ void __launch_bounds__(256) grad_reduce_push_kernel(GradPtrs ptrs, lo
 // Spin budget of the peer kernels.  A rank may legitimately wait for a peer that is busy with rank-local host work
 // (checkpoint write, dataset.evaluate, a stalled DataLoader): the default matches NCCL's watchdog scale (10 minutes),
 // GS_COMM_TIMEOUT_S overrides it (tests and benchmarks use a short budget so that a bug traps instead of hanging a box).
-static unsigned long long comm_timeout_ns() {
+unsigned long long comm_timeout_ns() {
     static const unsigned long long v = [] {
         const char* e = getenv("GS_COMM_TIMEOUT_S");
         double s = e ? atof(e) : 600.0;
@@ -229,14 +149,14 @@ extern "C" int gs_grad_allreduce(const void* const* peer_grads, int64_t offset, 
     long long lo4 = o4 + per * rank, hi4 = lo4 + per;
     if (lo4 > o4 + n4) lo4 = o4 + n4;
     if (hi4 > o4 + n4) hi4 = o4 + n4;
-    peer_barrier_kernel<<<1, 32, 0, st>>>(fp, rank, world, seq, 0, 1, comm_timeout_ns());
+    gs::launch(peer_barrier_kernel, dim3(1), dim3(32), 0, st, fp, rank, world, seq, 0, 1, comm_timeout_ns());
     if (hi4 > lo4) {
         long long blocks = (hi4 - lo4 + 256 * 4 - 1) / (256 * 4);
         const long long cap = static_cast<long long>(num_sms()) * 4;
         if (blocks > cap) blocks = cap;
-        grad_reduce_push_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(gp, lo4, hi4, world);
+        gs::launch(grad_reduce_push_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, gp, lo4, hi4, world);
     }
-    peer_barrier_kernel<<<1, 32, 0, st>>>(fp, rank, world, seq, 1, 0, comm_timeout_ns());
+    gs::launch(peer_barrier_kernel, dim3(1), dim3(32), 0, st, fp, rank, world, seq, 1, 0, comm_timeout_ns());
     GS_LAUNCHED();
     return 0;
 }
@@ -293,7 +213,7 @@ extern "C" int gs_syncbn_allreduce(double* stats, int32_t n, const void* const* 
     }
     int threads = ((n + 31) / 32) * 32;
     if (threads > kCommThreads) threads = kCommThreads;
-    syncbn_allreduce_kernel<<<1, kCommThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(syncbn_allreduce_kernel, dim3(1), dim3(kCommThreads), 0, static_cast<cudaStream_t>(stream), 
         stats, n, pp, rank, world, reinterpret_cast<unsigned long long*>(seq_dev), dgamma, dbeta, comm_timeout_ns());
     (void)threads;
     GS_LAUNCHED();

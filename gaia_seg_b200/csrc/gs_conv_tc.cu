@@ -106,6 +106,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_trigger();                       // the next kernel's blocks may be scheduled; they wait for our completion
     if (threadIdx.x == 0) trace(0);
 
     if (warp == 0 && elect_one()) {
@@ -133,6 +134,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     else __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
+    // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the previous kernel;
+    // from here on global memory is touched: wait for the earlier kernels of the stream to complete
+    pdl_wait();
 
     // Work unit = one CTA (CG 1) or one CTA pair (CG 2).  Unit u owns ONE n-tile (u % n_tiles) for the whole kernel and
     // walks m-units u / n_tiles + i * groups; CTA `rank` of the unit computes m-tile  m_unit * CG + rank  (a pair with
@@ -638,19 +642,9 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     if (groups > m_units) groups = m_units;
     const int grid = groups * p.n_tiles * cg;
     if (cg == 1) {
-        igemm_kernel<1><<<grid, kIgThreads, IgCfg<1>::kSmemBytes, stream>>>(tmA, tmB, tmC, tmR, p);
+        gs::launch<2>(igemm_kernel<1>, dim3(grid), dim3(kIgThreads), IgCfg<1>::kSmemBytes, stream, tmA, tmB, tmC, tmR, p);
     } else {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(kIgThreads);
-        cfg.dynamicSmemBytes = IgCfg<2>::kSmemBytes;
-        cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        GS_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel<2>, tmA, tmB, tmC, tmR, p));
+        gs::launch_pair<2>(igemm_kernel<2>, dim3(grid), dim3(kIgThreads), IgCfg<2>::kSmemBytes, stream, tmA, tmB, tmC, tmR, p);
     }
     GS_LAUNCHED();
     return 0;
@@ -662,6 +656,7 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 __global__ void zero_insert_kernel(const uint4* __restrict__ dy, long long dy_ld8, uint4* __restrict__ up, int N,
                                    int Ho, int Wo, int Hu, int Wu, int S, int C8) {
+    pdl_sync();
     const long long total = static_cast<long long>(N) * Hu * Wu * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -687,6 +682,7 @@ __global__ void zero_insert_kernel(const uint4* __restrict__ dy, long long dy_ld
 constexpr int kWgBoxBytes = 64 * 64 * 2;           // [64 pixels][64 channels] bf16
 constexpr int kWgABytes = 2 * kWgBoxBytes;
 constexpr int kWgThreads = 192;
+constexpr int kWgMaxUnits = 148;
 // CG = 2: a CTA pair (cta_group::2, M = 256 output channels): each CTA stages its own 128 output channels of dY and HALF
 // of the X tile -- 32 KB instead of 48 KB of L2 -> SM traffic per 64-pixel chunk, which is what bounds the main loop.
 template <int CG>
@@ -697,19 +693,51 @@ struct WgCfg {
     static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
 };
 
+// Work decomposition ("stream-K"): an ITEM is one (output-channel tile, input-channel tile, filter tap) accumulator of
+// the weight gradient, its K loop runs over `chunks_total` 64-pixel chunks.  The linearised (item-major, chunk-minor)
+// space is cut into `units` contiguous ranges of equal WEIGHTED length (weight = bytes a chunk of that item loads), one per
+// CTA (or CTA pair): every SM gets the same amount of work whatever items x split-K would have quantised to (round 1:
+// grid = items x splitk, e.g. 54 x 3 = 162 CTAs on 148 SMs = two waves).  A unit whose range crosses an item boundary
+// flushes its accumulator (fp32 red.add into dW) and starts the next one in the other TMEM buffer.
 struct WgradParams {
-    int N, Ho, Wo, TH, TW, tiles_h, tiles_w, chunks_total, splitk;
+    int N, Ho, Wo, TH, TW, tiles_h, tiles_w, chunks_total;
     int Co, Ci, co_tiles, ci_tiles;
     int kh, kw, stride, pad, dil;
     float* dw;
     long long row_stride;  // kh*kw*Ci_max
     int Ci_max;
+    int units, items;
+    int start_item[kWgMaxUnits + 1];     // unit u owns [ (start_item[u], start_chunk[u]), (start_item[u+1], start_chunk[u+1]) )
+    int start_chunk[kWgMaxUnits + 1];
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                  : "memory");
 }
+
+template <int CG>
+struct WgItem {
+    int r, s, co0, ci0, ci_valid, co_valid, n_half, cb0, a_boxes, b_boxes;
+    uint32_t umma_n;
+    __device__ __forceinline__ WgItem(const WgradParams& p, int item, int rank) {
+        // (CG 2: the two CTAs of a pair take output-channel tiles 2*cot and 2*cot + 1; a pair with an odd tile count ends on
+        // a phantom tile: its dY loads are out of bounds = zero and its epilogue stores nothing)
+        int t = item;
+        const int tap = t % (p.kh * p.kw); t /= (p.kh * p.kw);
+        const int cit = t % p.ci_tiles;
+        const int cot = t / p.ci_tiles;
+        r = tap / p.kw; s = tap - r * p.kw;
+        co0 = (cot * CG + rank) * 128; ci0 = cit * 256;
+        ci_valid = p.Ci - ci0; if (ci_valid > 256) ci_valid = 256;
+        co_valid = p.Co - co0; if (co_valid > 128) co_valid = 128;
+        umma_n = (ci_valid + 15) & ~15;
+        n_half = static_cast<int>(umma_n) / CG;          // this CTA's share of the X tile (input channels)
+        cb0 = ci0 + rank * (CG == 2 ? n_half : 0);
+        a_boxes = CG == 2 ? 2 : (co_valid + 63) >> 6;   // pair: both CTAs always load 2 boxes (equal byte counts)
+        b_boxes = ((CG == 2 ? n_half : ci_valid) + 63) >> 6;
+    }
+};
 
 template <int CG>
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -722,145 +750,218 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kWgStages;
-    uint64_t* tfull_bar = bars + 2 * kWgStages;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+    uint64_t* tfull_bar = bars + 2 * kWgStages;   // [2] accumulator buffer complete
+    uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator buffer drained
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    // work item (CG 2: the two CTAs of a pair take output-channel tiles 2*cot and 2*cot + 1; a pair with an odd tile
-    // count ends on a phantom tile: its dY loads are out of bounds = zero and its epilogue stores nothing)
     const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
-    int t = blockIdx.x / CG;
-    const int tap = t % (p.kh * p.kw); t /= (p.kh * p.kw);
-    const int cit = t % p.ci_tiles;
-    const int cot = t / p.ci_tiles;
-    const int r = tap / p.kw, s = tap - r * p.kw;
-    const int co0 = (cot * CG + rank) * 128, ci0 = cit * 256;
-    int ci_valid = p.Ci - ci0; if (ci_valid > 256) ci_valid = 256;
-    int co_valid = p.Co - co0; if (co_valid > 128) co_valid = 128;
-    const uint32_t umma_n = (ci_valid + 15) & ~15;
-    const int n_half = static_cast<int>(umma_n) / CG;          // this CTA's share of the X tile (input channels)
-    const int cb0 = ci0 + rank * (CG == 2 ? n_half : 0);
-    const int a_boxes = CG == 2 ? 2 : (co_valid + 63) >> 6;   // pair: both CTAs always load 2 boxes (equal byte counts)
-    const int b_boxes = ((CG == 2 ? n_half : ci_valid) + 63) >> 6;
-    const int per = (p.chunks_total + p.splitk - 1) / p.splitk;
-    const int c_begin = blockIdx.y * per;
-    int c_end = c_begin + per; if (c_end > p.chunks_total) c_end = p.chunks_total;
+    pdl_trigger();
+    const int unit = blockIdx.x / CG;
+    const int it0 = p.start_item[unit], ch0 = p.start_chunk[unit];
+    const int it1 = p.start_item[unit + 1], ch1 = p.start_chunk[unit + 1];
     const int tiles_hw = p.tiles_h * p.tiles_w;
 
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmDY);
         tma_prefetch_desc(&tmX);
         for (int i = 0; i < kWgStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        mbar_init(tfull_bar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4 * CG); }
         fence_mbar_init();
     }
     if (warp == 1) {
-        if (CG == 2) tmem_alloc_pair(tmem_ptr, 256);
-        else tmem_alloc(tmem_ptr, 256);
+        if (CG == 2) tmem_alloc_pair(tmem_ptr, 512);
+        else tmem_alloc(tmem_ptr, 512);
     }
     tc_fence_before_sync();
     if (CG == 2) cluster_sync_all();
     else __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr;
-    const bool has_work = c_begin < c_end;
+    pdl_wait();     // prologue done; global memory from here on
 
     if (warp == 0) {
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t tx = CG * (a_boxes + b_boxes) * kWgBoxBytes;   // pair: the leader's barrier counts both CTAs
-            for (int c = c_begin; c < c_end; ++c) {
-                const int img = c / tiles_hw;
-                const int rem = c - img * tiles_hw;
-                const int ho0 = (rem / p.tiles_w) * p.TH;
-                const int wo0 = (rem % p.tiles_w) * p.TW;
-                const int ih = ho0 * p.stride - p.pad + r * p.dil;
-                const int iw = wo0 * p.stride - p.pad + s * p.dil;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* a_dst = smem + stage * kWgStageBytes;
-                uint8_t* b_dst = a_dst + kWgABytes;
-                if (CG == 1) {
-                    mbar_arrive_expect_tx(&full_bar[stage], tx);
-                    for (int j = 0; j < a_boxes; ++j)
-                        tma_load_4d(a_dst + j * kWgBoxBytes, &tmDY, &full_bar[stage], co0 + j * 64, wo0, ho0, img);
-                    for (int j = 0; j < b_boxes; ++j)
-                        tma_load_4d(b_dst + j * kWgBoxBytes, &tmX, &full_bar[stage], ci0 + j * 64, iw, ih, img);
-                } else {
-                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
-                    for (int j = 0; j < a_boxes; ++j)
-                        tma_load_4d_pair(a_dst + j * kWgBoxBytes, &tmDY, &full_bar[stage], co0 + j * 64, wo0, ho0, img);
-                    for (int j = 0; j < b_boxes; ++j)
-                        tma_load_4d_pair(b_dst + j * kWgBoxBytes, &tmX, &full_bar[stage], cb0 + j * 64, iw, ih, img);
+            for (int item = it0; item <= it1; ++item) {
+                const int c_begin = item == it0 ? ch0 : 0;
+                const int c_end = item == it1 ? ch1 : p.chunks_total;
+                if (c_begin >= c_end) continue;
+                const WgItem<CG> w(p, item, rank);
+                const uint32_t tx = CG * (w.a_boxes + w.b_boxes) * kWgBoxBytes;   // pair: the leader's barrier counts both CTAs
+                for (int c = c_begin; c < c_end; ++c) {
+                    const int img = c / tiles_hw;
+                    const int rem = c - img * tiles_hw;
+                    const int ho0 = (rem / p.tiles_w) * p.TH;
+                    const int wo0 = (rem % p.tiles_w) * p.TW;
+                    const int ih = ho0 * p.stride - p.pad + w.r * p.dil;
+                    const int iw = wo0 * p.stride - p.pad + w.s * p.dil;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* a_dst = smem + stage * kWgStageBytes;
+                    uint8_t* b_dst = a_dst + kWgABytes;
+                    if (CG == 1) {
+                        mbar_arrive_expect_tx(&full_bar[stage], tx);
+                        for (int j = 0; j < w.a_boxes; ++j)
+                            tma_load_4d(a_dst + j * kWgBoxBytes, &tmDY, &full_bar[stage], w.co0 + j * 64, wo0, ho0, img);
+                        for (int j = 0; j < w.b_boxes; ++j)
+                            tma_load_4d(b_dst + j * kWgBoxBytes, &tmX, &full_bar[stage], w.ci0 + j * 64, iw, ih, img);
+                    } else {
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
+                        for (int j = 0; j < w.a_boxes; ++j)
+                            tma_load_4d_pair(a_dst + j * kWgBoxBytes, &tmDY, &full_bar[stage], w.co0 + j * 64, wo0, ho0, img);
+                        for (int j = 0; j < w.b_boxes; ++j)
+                            tma_load_4d_pair(b_dst + j * kWgBoxBytes, &tmX, &full_bar[stage], w.cb0 + j * 64, iw, ih, img);
+                    }
+                    if (++stage == kWgStages) { stage = 0; phase ^= 1; }
                 }
-                if (++stage == kWgStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (rank == 0 && elect_one() && has_work) {
+        if (rank == 0 && elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t idesc = make_idesc_bf16(128 * CG, umma_n, true, true);
-            uint32_t accumulate = 0;
-            for (int c = c_begin; c < c_end; ++c) {
-                mbar_wait(&full_bar[stage], phase);
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int item = it0; item <= it1; ++item) {
+                const int c_begin = item == it0 ? ch0 : 0;
+                const int c_end = item == it1 ? ch1 : p.chunks_total;
+                if (c_begin >= c_end) continue;
+                const WgItem<CG> w(p, item, rank);
+                const uint32_t idesc = make_idesc_bf16(128 * CG, w.umma_n, true, true);
+                if (CG == 2) mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+                else mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after_sync();
-                const uint32_t a_addr = smem_u32(smem + stage * kWgStageBytes);
-                const uint32_t b_addr = a_addr + kWgABytes;
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                uint32_t accumulate = 0;
+                for (int c = c_begin; c < c_end; ++c) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem_u32(smem + stage * kWgStageBytes);
+                    const uint32_t b_addr = a_addr + kWgABytes;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 2048, kWgBoxBytes, 1024);
-                    const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 2048, kWgBoxBytes, 1024);
-                    if (CG == 2) umma_bf16_ss_pair(tmem_base, adesc, bdesc, idesc, accumulate);
-                    else umma_bf16_ss(tmem_base, adesc, bdesc, idesc, accumulate);
-                    accumulate = 1;
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 2048, kWgBoxBytes, 1024);
+                        const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 2048, kWgBoxBytes, 1024);
+                        if (CG == 2) umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, accumulate);
+                        else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+                        accumulate = 1;
+                    }
+                    if (CG == 2) umma_commit_pair(&empty_bar[stage]);
+                    else umma_commit(&empty_bar[stage]);
+                    if (++stage == kWgStages) { stage = 0; phase ^= 1; }
                 }
-                if (CG == 2) umma_commit_pair(&empty_bar[stage]);
-                else umma_commit(&empty_bar[stage]);
-                if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+                if (CG == 2) umma_commit_pair(&tfull_bar[acc]);
+                else umma_commit(&tfull_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
             }
-            if (CG == 2) umma_commit_pair(tfull_bar);
-            else umma_commit(tfull_bar);
         }
-    } else if (has_work) {
+    } else {
+        // epilogue warps 2..5: drain the finished accumulator buffer into dW with vector fp32 reductions while the MMA
+        // thread already accumulates the unit's next item in the other buffer
         const int q = warp & 3;
-        const int co = co0 + q * 32 + lane;
-        mbar_wait(tfull_bar, 0);
-        tc_fence_after_sync();
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        float* dst_row = p.dw + static_cast<long long>(co) * p.row_stride + static_cast<long long>(r * p.kw + s) * p.Ci_max + ci0;
-        const int nchunks = (ci_valid + 31) >> 5;
+        int acc = 0; uint32_t acc_phase = 0;
         const bool vec_ok = (p.Ci_max % 4 == 0) && (p.Ci % 4 == 0);
-        for (int c = 0; c < nchunks; ++c) {
-            uint32_t raw[32];
-            tmem_ld_32x32b_x32(t_addr + c * 32, raw);
-            tmem_ld_wait();
-            if (co < p.Co) {
-                if (vec_ok) {
+        for (int item = it0; item <= it1; ++item) {
+            const int c_begin = item == it0 ? ch0 : 0;
+            const int c_end = item == it1 ? ch1 : p.chunks_total;
+            if (c_begin >= c_end) continue;
+            const WgItem<CG> w(p, item, rank);
+            const int co = w.co0 + q * 32 + lane;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after_sync();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+            float* dst_row = p.dw + static_cast<long long>(co) * p.row_stride +
+                             static_cast<long long>(w.r * p.kw + w.s) * p.Ci_max + w.ci0;
+            const int nchunks = (w.ci_valid + 31) >> 5;
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t raw[32];
+                tmem_ld_32x32b_x32(t_addr + c * 32, raw);
+                tmem_ld_wait();
+                if (c == nchunks - 1) {
+                    // the whole share of this warp is in registers (or already reduced): hand the buffer back
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
+                }
+                if (co < p.Co) {
+                    if (vec_ok) {
 #pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
-                        const int col = c * 32 + g4 * 4;
-                        if (col < ci_valid)
-                            red_add_v4(dst_row + col, __uint_as_float(raw[g4 * 4 + 0]), __uint_as_float(raw[g4 * 4 + 1]),
-                                       __uint_as_float(raw[g4 * 4 + 2]), __uint_as_float(raw[g4 * 4 + 3]));
-                    }
-                } else {
+                        for (int g4 = 0; g4 < 8; ++g4) {
+                            const int col = c * 32 + g4 * 4;
+                            if (col < w.ci_valid)
+                                red_add_v4(dst_row + col, __uint_as_float(raw[g4 * 4 + 0]), __uint_as_float(raw[g4 * 4 + 1]),
+                                           __uint_as_float(raw[g4 * 4 + 2]), __uint_as_float(raw[g4 * 4 + 3]));
+                        }
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int col = c * 32 + i;
-                        if (col < ci_valid) atomicAdd(dst_row + col, __uint_as_float(raw[i]));
+                        for (int i = 0; i < 32; ++i) {
+                            const int col = c * 32 + i;
+                            if (col < w.ci_valid) atomicAdd(dst_row + col, __uint_as_float(raw[i]));
+                        }
                     }
                 }
             }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
         }
     }
     tc_fence_before_sync();
     if (CG == 2) cluster_sync_all();
     else __syncthreads();
     if (warp == 1) {
-        if (CG == 2) tmem_dealloc_pair(tmem_base, 256);
-        else tmem_dealloc(tmem_base, 256);
+        if (CG == 2) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
+}
+
+// Equal-weight partition of the (item, chunk) space (host side, a few hundred items at most).
+static void wgrad_partition(WgradParams& p, int cg, int max_units) {
+    const int taps = p.kh * p.kw;
+    const int items = (int)gs_ceil_div(p.co_tiles, cg) * p.ci_tiles * taps;
+    p.items = items;
+    // GS_WGRAD_WEIGHT: 0 = every chunk costs the same (the main loop is bound by the per-chunk pipeline latency, measured:
+    // a 24 KB chunk takes as long as a 48 KB one), 1 = cost proportional to the bytes a chunk loads
+    static const int wmode = [] { const char* e = getenv("GS_WGRAD_WEIGHT"); return e ? atoi(e) : 0; }();
+    auto weight = [&](int item) {
+        if (wmode == 0) return 1;
+        int t = item / taps;
+        const int cit = t % p.ci_tiles, cot = t / p.ci_tiles;
+        int ci_valid = p.Ci - cit * 256; if (ci_valid > 256) ci_valid = 256;
+        if (cg == 2) return 2 + (int)gs_ceil_div(gs_round_up(ci_valid, 16) / 2, 64);
+        int co_valid = p.Co - cot * 128; if (co_valid > 128) co_valid = 128;
+        return (int)gs_ceil_div(co_valid, 64) + (int)gs_ceil_div(ci_valid, 64);
+    };
+    // at least 8 chunks (512 pixels) per unit on average, so the fp32 reductions stay a small tail
+    long long total_chunks = (long long)items * p.chunks_total;
+    int units = (int)(total_chunks / 8 < max_units ? total_chunks / 8 : max_units);
+    if (units < 1) units = 1;
+    if (units > kWgMaxUnits) units = kWgMaxUnits;
+    p.units = units;
+    double W = 0.0;
+    for (int i = 0; i < items; ++i) W += (double)p.chunks_total * weight(i);
+    p.start_item[0] = 0; p.start_chunk[0] = 0;
+    int item = 0;
+    double prefix = 0.0;           // weighted work before `item`
+    const int snap = p.chunks_total >= 16 ? 4 : 0;   // do not leave slivers of < 4 chunks next to an item boundary
+    for (int u = 1; u < units; ++u) {
+        const double pos = W * u / units;
+        while (item < items && prefix + (double)p.chunks_total * weight(item) <= pos) {
+            prefix += (double)p.chunks_total * weight(item);
+            ++item;
+        }
+        int it = item, ch = 0;
+        if (item < items) {
+            ch = (int)((pos - prefix) / weight(item) + 0.5);
+            if (ch < snap) ch = 0;
+            if (ch > p.chunks_total - snap) { it = item + 1; ch = 0; }
+        }
+        // monotone
+        if (it < p.start_item[u - 1] || (it == p.start_item[u - 1] && ch < p.start_chunk[u - 1])) {
+            it = p.start_item[u - 1]; ch = p.start_chunk[u - 1];
+        }
+        p.start_item[u] = it; p.start_chunk[u] = ch;
+    }
+    p.start_item[units] = items; p.start_chunk[units] = 0;
 }
 
 static int launch_wgrad(const gs_conv_geom* g, const void* x, const void* dy, float* dw, cudaStream_t stream) {
@@ -879,19 +980,11 @@ static int launch_wgrad(const gs_conv_geom* g, const void* x, const void* dy, fl
     p.dw = dw; p.Ci_max = g->Ci_max;
     p.row_stride = static_cast<long long>(g->kh) * g->kw * g->Ci_max;
     static const int cg_env = [] { const char* e = getenv("GS_WGRAD_CTA_GROUP"); return e ? atoi(e) : 2; }();
-    // pairs pay off only for the big layers (measured: >= ~2.5e10 MACs; smaller launches are bound by the split-K
-    // atomics and the short per-CTA pixel range, where the lock-step of a pair costs a little)
+    static const double pair_min_macs = [] { const char* e = getenv("GS_WGRAD_PAIR_MIN_MACS"); return e ? atof(e) : 2.5e10; }();
+    // pairs pay off only for the big layers (measured round 1: >= ~2.5e10 MACs)
     const double macs = (double)g->N * g->Ho * g->Wo * g->Co * g->Ci * g->kh * g->kw;
-    const int cg = (cg_env == 2 && p.co_tiles >= 2 && macs >= 2.5e10) ? 2 : 1;
-    const int items = (int)gs_ceil_div(p.co_tiles, cg) * p.ci_tiles * g->kh * g->kw;   // CTAs or CTA pairs
-    static const int waves_x2 = getenv("GS_WGRAD_HALF_WAVES") ? atoi(getenv("GS_WGRAD_HALF_WAVES")) : 2;   // one wave: fewer split-K atomics; wgrad runs beside the BN kernels anyway
-    int splitk = (int)gs_ceil_div((long long)waves_x2 * (num_sms() / cg) / 2, items);
-    if (splitk > p.chunks_total) splitk = p.chunks_total;
-    if (splitk < 1) splitk = 1;
-    // keep at least 8 pixel-chunks (512 pixels) per CTA so the fp32 atomics stay a small tail
-    const int max_split = (int)gs_ceil_div(p.chunks_total, 8);
-    if (splitk > max_split) splitk = max_split;
-    p.splitk = splitk;
+    const int cg = (cg_env == 2 && p.co_tiles >= 2 && macs >= pair_min_macs) ? 2 : 1;
+    wgrad_partition(p, cg, num_sms() / cg);
 
     CUtensorMap tmDY, tmX;
     {
@@ -917,20 +1010,9 @@ static int launch_wgrad(const gs_conv_geom* g, const void* x, const void* dy, fl
         attr_set = true;
     }
     if (cg == 1) {
-        dim3 grid(items, splitk);
-        wgrad_kernel<1><<<grid, kWgThreads, WgCfg<1>::kSmemBytes, stream>>>(tmDY, tmX, p);
+        gs::launch<4>(wgrad_kernel<1>, dim3(p.units), dim3(kWgThreads), WgCfg<1>::kSmemBytes, stream, tmDY, tmX, p);
     } else {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(items * 2, splitk);
-        cfg.blockDim = dim3(kWgThreads);
-        cfg.dynamicSmemBytes = WgCfg<2>::kSmemBytes;
-        cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        GS_CUDA_OK(cudaLaunchKernelEx(&cfg, wgrad_kernel<2>, tmDY, tmX, p));
+        gs::launch_pair<4>(wgrad_kernel<2>, dim3(p.units * 2), dim3(kWgThreads), WgCfg<2>::kSmemBytes, stream, tmDY, tmX, p);
     }
     GS_LAUNCHED();
     return 0;
@@ -999,7 +1081,7 @@ extern "C" int gs_conv2d_dgrad(const gs_conv_geom* g, const void* dy, const void
         const int C8 = g->Co / 8;
         const long long total = (long long)g->N * Hu * Wu * C8;
         const int blocks = (int)(gs_ceil_div(total, 256) < 148 * 16 ? gs_ceil_div(total, 256) : 148 * 16);
-        zero_insert_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(dy), g->y_ld / 8,
+        gs::launch(zero_insert_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const uint4*>(dy), g->y_ld / 8,
                                                        reinterpret_cast<uint4*>(workspace), g->N, g->Ho, g->Wo, Hu, Wu,
                                                        g->stride, C8);
         GS_LAUNCHED();

@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -53,6 +54,11 @@ int encode_tmap_4d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, con
                (unsigned long long)strides_bytes[1], (unsigned long long)strides_bytes[2], box[0], box[1], box[2],
                box[3], estr[0], estr[1], estr[2], estr[3]);
     return 0;
+}
+
+bool pdl_enabled(int kind_bit) {
+    static const int mask = [] { const char* e = getenv("GS_PDL"); return e == nullptr ? 6 : atoi(e); }();
+    return (mask & kind_bit) != 0;
 }
 
 int num_sms() {

@@ -20,7 +20,64 @@ int encode_tmap_4d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, con
 
 int num_sms();
 
+// spin budget of the peer-memory kernels in ns (GS_COMM_TIMEOUT_S, default 600 s; gs_comm.cu)
+unsigned long long comm_timeout_ns();
+
+// Programmatic dependent launch (PDL).  Every kernel of this library starts with pdl_sync() (or, for the tensor-core
+// kernels, pdl_trigger() at the top and pdl_wait() after the barrier / TMEM / tensor-map prologue), and is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the launch latency, block dispatch and prologue of kernel i+1 overlap
+// the tail of kernel i on the same stream (~1050 conv + ~1100 BN launches of 10-40 us per sandwich cycle), while
+// griddepcontrol.wait still orders every global-memory access after the COMPLETION of all earlier kernels -- the
+// semantics of a plain stream are unchanged.  Legal inside captured CUDA graphs (programmatic edges).  GS_PDL=0 disables it.
+// GS_PDL is a bit mask: 1 = memory-bound kernels, 2 = igemm (conv fwd / dgrad), 4 = wgrad.  Default 6, MEASURED on the
+// sandwich cycle (profiles/r02_pdl_sweep.md): early-scheduled blocks of the memory-bound kernels take the scheduling gaps
+// the low-priority side-stream wgrad kernels live on (52.3 -> 55.4 ms), the tensor-core kernels gain (52.3 -> 50.7 ms).
+bool pdl_enabled(int kind_bit = 1);
+
+template <int KIND = 1, typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled(KIND) ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through GS_LAUNCHED()
+}
+
+// cluster-of-2 variant (CTA pairs of the tensor-core kernels)
+template <int KIND = 1, typename... KArgs, typename... Args>
+inline void launch_pair(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled(KIND) ? 2 : 1;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace gs
+
+#ifdef __CUDACC__
+namespace gs {
+// allow the next kernel of the stream to be scheduled (its blocks still wait for OUR completion in pdl_wait)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// block until every earlier kernel of the stream has completed and its writes are visible
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
+}  // namespace gs
+#endif
 
 #define GS_REQUIRE(cond, ...)          \
     do {                               \

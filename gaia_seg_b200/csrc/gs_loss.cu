@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const float* __res
                                                               int H, int W, int ignore_index, float rh, float rw,
                                                               PixRec* __restrict__ rec, double* __restrict__ out_sum,
                                                               unsigned long long* __restrict__ out_counts) {
+    pdl_sync();
     double loss_acc = 0.0;
     unsigned int n_ign = 0, n_hit = 0;
     const long long total = (long long)N * H * W;
@@ -133,7 +134,8 @@ __global__ void __launch_bounds__(256) upsample_ce_fwd_kernel(const float* __res
 // ------------------------------------------------------------------------------------------------
 constexpr int kBwdTile = 8;        // low-res cells per tile edge
 constexpr int kBwdKC = 32;         // classes per chunk
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 512;
+constexpr int kBwdKSplit = 4;     // phase 1: threads per output pixel (classes interleaved) -> 4x the parallelism
 constexpr int kBwdMaxRegion = 512; // output pixels per tile edge the tap tables can hold (scale factors up to ~50)
 
 struct BwdSmem {
@@ -166,6 +168,7 @@ __global__ void __launch_bounds__(kBwdThreads) upsample_ce_bwd_kernel(const floa
                                                                       const float* __restrict__ grad_scale_dev,
                                                                       float* __restrict__ dlogits, int dl_ld, int XWmax,
                                                                       int R, int KC) {
+    pdl_sync();
     extern __shared__ __align__(16) unsigned char smem_bwd[];
     const BwdSmem L = bwd_smem_layout(K, KC, XWmax, R);
     float* sL = reinterpret_cast<float*>(smem_bwd + L.logits);
@@ -244,15 +247,17 @@ __global__ void __launch_bounds__(kBwdThreads) upsample_ce_bwd_kernel(const floa
         for (int i = tid; i < kBwdTile * kBwdTile * kcp; i += kBwdThreads) sA[i] = 0.f;
         for (int yb = 0; yb < YH; yb += R) {
             const int rows = min(R, YH - yb);
-            // ---- phase 1: soft-max gradient terms of the strip, once per pixel ----
-            for (int p = tid; p < rows * XW; p += kBwdThreads) {
+            // ---- phase 1: soft-max gradient terms of the strip, once per pixel (kBwdKSplit lanes share a pixel) ----
+            for (int it = tid; it < rows * XW * kBwdKSplit; it += kBwdThreads) {
+                const int q = it & (kBwdKSplit - 1);
+                const int p = it / kBwdKSplit;
                 const int r = p / XW, xx = p - r * XW;
                 const int2 yi = yti[yb + r], xi = xti[xx];
                 float* g = sG + (size_t)(r * XW + xx) * kcp;
                 const PixRec pr = rec[((long long)n * H + (ylo + yb + r)) * W + (xlo + xx)];
                 const bool inside = yi.x >= i0 - 1 && yi.y <= i0 + th && xi.x >= j0 - 1 && xi.y <= j0 + tw;
                 if (pr.label < 0 || !inside) {
-                    for (int kk = 0; kk < kn; ++kk) g[kk] = 0.f;
+                    for (int kk = q; kk < kn; kk += kBwdKSplit) g[kk] = 0.f;
                     continue;
                 }
                 const float2 wy = ytw[yb + r], wx = xtw[xx];
@@ -263,7 +268,8 @@ __global__ void __launch_bounds__(kBwdThreads) upsample_ce_bwd_kernel(const floa
                 const float* a10 = sL + ((yi.y - i0 + 1) * LW + (xi.x - j0 + 1)) * K + kc;
                 const float* a11 = sL + ((yi.y - i0 + 1) * LW + (xi.y - j0 + 1)) * K + kc;
                 const int lab = pr.label - kc;
-                for (int kk = 0; kk < kn; ++kk) {
+#pragma unroll 4
+                for (int kk = q; kk < kn; kk += kBwdKSplit) {
                     const float v = lerp4(ty, tx, a00[kk], a01[kk], a10[kk], a11[kk]);
                     g[kk] = __expf(v - pr.lse) - (kk == lab ? 1.f : 0.f);
                 }
@@ -277,6 +283,7 @@ __global__ void __launch_bounds__(kBwdThreads) upsample_ce_bwd_kernel(const floa
                 const int2 range = xr[j];
                 float acc = 0.f;
                 const float* g = sG + (size_t)(r * XW) * kcp + kk;
+#pragma unroll 4
                 for (int xx = range.x; xx <= range.y; ++xx) {
                     const int2 xi = xti[xx];
                     const float2 wx = xtw[xx];
@@ -320,6 +327,7 @@ __global__ void __launch_bounds__(kBwdThreads) upsample_ce_bwd_kernel(const floa
 __global__ void __launch_bounds__(256) upsample_argmax_kernel(const float* __restrict__ logits, int N, int h, int w,
                                                               int K, int ld, int H, int W, float rh, float rw,
                                                               long long* __restrict__ out) {
+    pdl_sync();
     const long long total = (long long)N * H * W;
     for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
          pix += (long long)gridDim.x * blockDim.x) {
@@ -345,6 +353,7 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(const float* __res
 __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const float* __restrict__ src, int N, int h, int w, int K,
                                                                 int ld, float* __restrict__ dst, int H, int W,
                                                                 int dst_ld, float rh, float rw) {
+    pdl_sync();
     const long long total = (long long)N * H * W * K;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -384,7 +393,7 @@ extern "C" int gs_upsample_ce_fwd(const float* logits, int32_t N, int32_t h, int
     GS_REQUIRE(logits && labels && out_sum && out_counts, "upsample_ce_fwd: null pointer");
     GS_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && K > 0 && ld >= K, "upsample_ce_fwd: bad shape");
     const float rh = static_cast<float>(h) / static_cast<float>(H), rw = static_cast<float>(w) / static_cast<float>(W);
-    upsample_ce_fwd_kernel<<<loss_grid((long long)N * H * W), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(upsample_ce_fwd_kernel, dim3(loss_grid((long long)N * H * W)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         logits, N, h, w, K, ld, reinterpret_cast<const long long*>(labels), H, W, ignore_index, rh, rw,
         reinterpret_cast<PixRec*>(pix_rec), out_sum, reinterpret_cast<unsigned long long*>(out_counts));
     GS_LAUNCHED();
@@ -398,13 +407,13 @@ extern "C" int gs_upsample_ce_bwd(const float* logits, int32_t N, int32_t h, int
     GS_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && K > 0 && ld >= K && dl_ld >= K, "upsample_ce_bwd: bad shape");
     const float rh = static_cast<float>(h) / static_cast<float>(H), rw = static_cast<float>(w) / static_cast<float>(W);
     // widest output-pixel region a tile can touch (same arithmetic as the kernel, + slack), strip height R and class chunk
-    // sized for <= ~96 KB of shared memory per CTA (2 CTAs per SM)
+    // sized for <= ~110 KB of shared memory per CTA (2 CTAs of 512 threads per SM)
     const int xw_max = static_cast<int>(ceilf((kBwdTile + 1.5f) / rw)) + 6;
     const int yh_max = static_cast<int>(ceilf((kBwdTile + 1.5f) / rh)) + 6;
     GS_REQUIRE(xw_max <= kBwdMaxRegion && yh_max <= kBwdMaxRegion,
                "upsample_ce_bwd: scale factor %dx%d -> %dx%d too large for the tile tables", h, w, H, W);
     const int KC = K < kBwdKC ? K : kBwdKC;
-    int R = (40 * 1024) / (xw_max * (KC | 1) * 4);
+    int R = (64 * 1024) / (xw_max * (KC | 1) * 4);
     if (R < 1) R = 1;
     if (R > 16) R = 16;
     const BwdSmem L = bwd_smem_layout(K, KC, xw_max, R);
@@ -415,7 +424,7 @@ extern "C" int gs_upsample_ce_bwd(const float* logits, int32_t N, int32_t h, int
         attr_bytes = L.total;
     }
     const int tiles = N * ((h + kBwdTile - 1) / kBwdTile) * ((w + kBwdTile - 1) / kBwdTile);
-    upsample_ce_bwd_kernel<<<tiles, kBwdThreads, L.total, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(upsample_ce_bwd_kernel, dim3(tiles), dim3(kBwdThreads), L.total, static_cast<cudaStream_t>(stream), 
         logits, N, h, w, K, ld, reinterpret_cast<const PixRec*>(pix_rec), H, W, rh, rw, grad_scale, grad_scale_dev, dlogits,
         dl_ld, xw_max, R, KC);
     GS_LAUNCHED();
@@ -427,7 +436,7 @@ extern "C" int gs_upsample_argmax(const float* logits, int32_t N, int32_t h, int
     GS_REQUIRE(logits && labels_out, "upsample_argmax: null pointer");
     GS_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && K > 0 && ld >= K, "upsample_argmax: bad shape");
     const float rh = static_cast<float>(h) / static_cast<float>(H), rw = static_cast<float>(w) / static_cast<float>(W);
-    upsample_argmax_kernel<<<loss_grid((long long)N * H * W), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(upsample_argmax_kernel, dim3(loss_grid((long long)N * H * W)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         logits, N, h, w, K, ld, H, W, rh, rw, reinterpret_cast<long long*>(labels_out));
     GS_LAUNCHED();
     return 0;
@@ -438,7 +447,7 @@ extern "C" int gs_upsample_bilinear_f32(const float* src, int32_t N, int32_t h, 
     GS_REQUIRE(src && dst, "upsample_bilinear: null pointer");
     GS_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && K > 0 && ld >= K && dst_ld >= K, "upsample_bilinear: bad shape");
     const float rh = static_cast<float>(h) / static_cast<float>(H), rw = static_cast<float>(w) / static_cast<float>(W);
-    upsample_bilinear_kernel<<<loss_grid((long long)N * H * W * K), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(upsample_bilinear_kernel, dim3(loss_grid((long long)N * H * W * K)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         src, N, h, w, K, ld, dst, H, W, dst_ld, rh, rw);
     GS_LAUNCHED();
     return 0;

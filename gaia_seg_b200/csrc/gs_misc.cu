@@ -19,6 +19,7 @@ static inline int flat_grid(long long total, int threads) {
 // ------------------------------------------------------------------------------------------------
 __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, long long x_ld8, int N, int H, int W, int C8,
                                    uint4* __restrict__ y, long long y_ld8, uint2* __restrict__ idx, int Ho, int Wo) {
+    pdl_sync();
     const long long total = (long long)N * Ho * Wo * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -60,6 +61,7 @@ __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, long long x_ld8,
 
 __global__ void maxpool_bwd_kernel(const uint4* __restrict__ dy, long long dy_ld8, const uint2* __restrict__ idx, int N,
                                    int H, int W, int C8, int Ho, int Wo, uint4* __restrict__ dx, long long dx_ld8) {
+    pdl_sync();
     const long long total = (long long)N * H * W * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -108,6 +110,7 @@ __global__ void maxpool_bwd_kernel(const uint4* __restrict__ dy, long long dy_ld
 __global__ void __launch_bounds__(256) adaptive_pool_fwd_kernel(const uint4* __restrict__ x, long long x_ld8, int H,
                                                                 int W, int C8, int S, uint4* __restrict__ y,
                                                                 long long y_ld8) {
+    pdl_sync();
     __shared__ float red[256 * 8];
     const int bin = blockIdx.x % (S * S);
     const int n = blockIdx.x / (S * S);
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(256) adaptive_pool_fwd_kernel(const uint4* __r
 // dx[n,h,w,c] (+)= sum over bins containing (h,w) of dy[n,bin,c] / npx(bin)
 __global__ void adaptive_pool_bwd_kernel(const uint4* __restrict__ dy, long long dy_ld8, int N, int H, int W, int C8,
                                          int S, uint4* __restrict__ dx, long long dx_ld8, int accumulate) {
+    pdl_sync();
     const long long total = (long long)N * H * W * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -191,6 +195,7 @@ __global__ void adaptive_pool_bwd_kernel(const uint4* __restrict__ dy, long long
 // ------------------------------------------------------------------------------------------------
 __global__ void copy_channels_kernel(const uint4* __restrict__ src, long long src_ld8, uint4* __restrict__ dst,
                                      long long dst_ld8, long long P, int C8) {
+    pdl_sync();
     const long long total = P * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -202,6 +207,7 @@ __global__ void copy_channels_kernel(const uint4* __restrict__ src, long long sr
 
 __global__ void add_channels_kernel(const uint4* __restrict__ src, long long src_ld8, uint4* __restrict__ dst,
                                     long long dst_ld8, long long P, int C8) {
+    pdl_sync();
     const long long total = P * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -220,6 +226,7 @@ __global__ void add_channels_kernel(const uint4* __restrict__ src, long long src
 // y[n, p, c] = x[n, p, c] * scale_nc[n*C + c]      (Dropout2d mask / keep-prob)
 __global__ void scale_nc_kernel(const uint4* __restrict__ x, long long x_ld8, const float* __restrict__ scale_nc,
                                 uint4* __restrict__ y, long long y_ld8, int N, long long HW, int C8) {
+    pdl_sync();
     const long long total = (long long)N * HW * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -238,6 +245,7 @@ __global__ void scale_nc_kernel(const uint4* __restrict__ x, long long x_ld8, co
 // fp32 [P][src_ld] (C used) -> bf16 [P][dst_ld], columns C..dst_ld zero-filled
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long src_ld, __nv_bfloat16* __restrict__ dst,
                                      long long dst_ld, long long P, int C) {
+    pdl_sync();
     const long long total = P * dst_ld;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -250,6 +258,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long sr
 // out[c] (+)= sum_p src[p][c]    (fp32; bias gradient of conv_seg)
 __global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict__ src, long long ld, long long P, int C,
                                                          float* __restrict__ out) {
+    pdl_sync();
     // block handles a slab of pixels; thread t handles column t % Cc, row group t / Cc
     __shared__ float red[256];
     const int Cc = C < 256 ? C : 256;
@@ -274,6 +283,7 @@ __global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict
 // fp32 NCHW -> bf16 NHWC (pitch ld, channels C..Cpad zero) via a 32x32 smem transpose per (n, c-tile, hw-tile)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int C, long long HW, __nv_bfloat16* __restrict__ dst,
                                     long long ld, int Cpad) {
+    pdl_sync();
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const long long hw0 = (long long)blockIdx.x * 32;
@@ -293,6 +303,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int C, long l
 
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, long long ld, int C, long long HW,
                                     float* __restrict__ dst) {
+    pdl_sync();
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const long long hw0 = (long long)blockIdx.x * 32;
@@ -315,6 +326,7 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, long 
 // ------------------------------------------------------------------------------------------------
 __global__ void im2col_image_kernel(const float* __restrict__ img, int N, int C, int H, int W, int kh, int kw,
                                     int stride, int pad, int Ho, int Wo, int Kpad, __nv_bfloat16* __restrict__ out) {
+    pdl_sync();
     const long long total = (long long)N * Ho * Wo * Kpad;
     const int K = kh * kw * C;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -360,6 +372,7 @@ __device__ __forceinline__ Tap2 src_tap2(float scale, int dst, int in_size) {
 
 __global__ void upsample_bf16_fwd_kernel(const uint4* __restrict__ src, long long src_ld8, int N, int h, int w, int C8,
                                          uint4* __restrict__ dst, long long dst_ld8, int H, int W, float rh, float rw) {
+    pdl_sync();
     const long long total = (long long)N * H * W * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -383,6 +396,7 @@ __global__ void upsample_bf16_fwd_kernel(const uint4* __restrict__ src, long lon
 __global__ void __launch_bounds__(256) upsample_bf16_bwd_kernel(const uint4* __restrict__ ddst, long long ddst_ld8, int H,
                                                                 int W, int C8, uint4* __restrict__ dsrc,
                                                                 long long dsrc_ld8, int h, int w, float rh, float rw) {
+    pdl_sync();
     __shared__ float red[256 * 8];
     const int cell = blockIdx.x % (h * w);
     const int n = blockIdx.x / (h * w);
@@ -433,6 +447,7 @@ __global__ void __launch_bounds__(256) upsample_bf16_bwd_kernel(const uint4* __r
 
 // zero-fill channels [0, C) of P pixels (the gap of the segmented PSP concat)
 __global__ void zero_channels_kernel(uint4* __restrict__ dst, long long dst_ld8, long long P, int C8) {
+    pdl_sync();
     const long long total = P * C8;
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -460,7 +475,7 @@ extern "C" int gs_maxpool3x3s2_fwd(const void* x, int32_t N, int32_t H, int32_t 
     GS_REQUIRE(Ho == (H + 2 - 3) / 2 + 1 && Wo == (W + 2 - 3) / 2 + 1, "maxpool: output size (%d,%d) inconsistent", Ho, Wo);
     const long long total = (long long)N * Ho * Wo * (C / 8);
     if (total <= 0) return 0;
-    maxpool_fwd_kernel<<<flat_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(maxpool_fwd_kernel, dim3(flat_grid(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const uint4*>(x), x_ld / 8, N, H, W, C / 8, reinterpret_cast<uint4*>(y), y_ld / 8,
         reinterpret_cast<uint2*>(idx), Ho, Wo);
     GS_LAUNCHED();
@@ -473,7 +488,7 @@ extern "C" int gs_maxpool3x3s2_bwd(const void* dy, int32_t dy_ld, const void* id
     GS_REQUIRE(idx != nullptr, "maxpool_bwd: null index tensor");
     const long long total = (long long)N * H * W * (C / 8);
     if (total <= 0) return 0;
-    maxpool_bwd_kernel<<<flat_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(maxpool_bwd_kernel, dim3(flat_grid(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const uint4*>(dy), dy_ld / 8, reinterpret_cast<const uint2*>(idx), N, H, W, C / 8, Ho, Wo,
         reinterpret_cast<uint4*>(dx), dx_ld / 8);
     GS_LAUNCHED();
@@ -488,7 +503,7 @@ extern "C" int gs_adaptive_avgpool_fwd(const void* x, int32_t N, int32_t H, int3
     const int Vc = C8 < 32 ? C8 : 32;
     int gy = (C8 + Vc - 1) / Vc;
     dim3 grid(N * S * S, gy);
-    adaptive_pool_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(adaptive_pool_fwd_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const uint4*>(x), x_ld / 8, H, W, C8, S, reinterpret_cast<uint4*>(y), y_ld / 8);
     GS_LAUNCHED();
     return 0;
@@ -499,7 +514,7 @@ extern "C" int gs_adaptive_avgpool_bwd(const void* dy, int32_t dy_ld, int32_t N,
     if (check_act8(dy, dy_ld, C, "adaptive_pool dy") || check_act8(dx, dx_ld, C, "adaptive_pool dx")) return -1;
     const long long total = (long long)N * H * W * (C / 8);
     if (total <= 0) return 0;
-    adaptive_pool_bwd_kernel<<<flat_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(adaptive_pool_bwd_kernel, dim3(flat_grid(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const uint4*>(dy), dy_ld / 8, N, H, W, C / 8, S, reinterpret_cast<uint4*>(dx), dx_ld / 8,
         accumulate);
     GS_LAUNCHED();
@@ -512,7 +527,7 @@ extern "C" int gs_upsample_bf16_fwd(const void* src, int32_t src_ld, int32_t N, 
     const long long total = (long long)N * H * W * (C / 8);
     if (total <= 0) return 0;
     const float rh = static_cast<float>(h) / static_cast<float>(H), rw = static_cast<float>(w) / static_cast<float>(W);
-    upsample_bf16_fwd_kernel<<<flat_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(upsample_bf16_fwd_kernel, dim3(flat_grid(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const uint4*>(src), src_ld / 8, N, h, w, C / 8, reinterpret_cast<uint4*>(dst), dst_ld / 8, H, W,
         rh, rw);
     GS_LAUNCHED();
@@ -528,7 +543,7 @@ extern "C" int gs_upsample_bf16_bwd(const void* ddst, int32_t ddst_ld, int32_t N
     const int C8 = C / 8;
     const int Vc = C8 < 32 ? C8 : 32;
     dim3 grid(N * h * w, (C8 + Vc - 1) / Vc);
-    upsample_bf16_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(upsample_bf16_bwd_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const uint4*>(ddst), ddst_ld / 8, H, W, C8, reinterpret_cast<uint4*>(dsrc), dsrc_ld / 8, h, w, rh,
         rw);
     GS_LAUNCHED();
@@ -538,7 +553,7 @@ extern "C" int gs_upsample_bf16_bwd(const void* ddst, int32_t ddst_ld, int32_t N
 extern "C" int gs_zero_channels(void* dst, int32_t dst_ld, int64_t P, int32_t C, void* stream) {
     if (check_act8(dst, dst_ld, C, "zero_channels dst")) return -1;
     if (P <= 0) return 0;
-    zero_channels_kernel<<<flat_grid(P * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(zero_channels_kernel, dim3(flat_grid(P * (C / 8), 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<uint4*>(dst), dst_ld / 8, P, C / 8);
     GS_LAUNCHED();
     return 0;
@@ -548,7 +563,7 @@ extern "C" int gs_copy_channels(const void* src, int32_t src_ld, void* dst, int3
                                 void* stream) {
     if (check_act8(src, src_ld, C, "copy_channels src") || check_act8(dst, dst_ld, C, "copy_channels dst")) return -1;
     if (P <= 0) return 0;
-    copy_channels_kernel<<<flat_grid(P * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(copy_channels_kernel, dim3(flat_grid(P * (C / 8), 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const uint4*>(src), src_ld / 8, reinterpret_cast<uint4*>(dst), dst_ld / 8, P, C / 8);
     GS_LAUNCHED();
     return 0;
@@ -558,7 +573,7 @@ extern "C" int gs_add_channels(const void* src, int32_t src_ld, void* dst, int32
                                void* stream) {
     if (check_act8(src, src_ld, C, "add_channels src") || check_act8(dst, dst_ld, C, "add_channels dst")) return -1;
     if (P <= 0) return 0;
-    add_channels_kernel<<<flat_grid(P * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(add_channels_kernel, dim3(flat_grid(P * (C / 8), 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const uint4*>(src), src_ld / 8, reinterpret_cast<uint4*>(dst), dst_ld / 8, P, C / 8);
     GS_LAUNCHED();
     return 0;
@@ -570,7 +585,7 @@ extern "C" int gs_scale_nc(const void* x, int32_t x_ld, const float* scale_nc, v
     GS_REQUIRE(scale_nc != nullptr, "scale_nc: null scale");
     const long long total = (long long)N * HW * (C / 8);
     if (total <= 0) return 0;
-    scale_nc_kernel<<<flat_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(scale_nc_kernel, dim3(flat_grid(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const uint4*>(x), x_ld / 8, scale_nc, reinterpret_cast<uint4*>(y), y_ld / 8, N, HW, C / 8);
     GS_LAUNCHED();
     return 0;
@@ -580,7 +595,7 @@ extern "C" int gs_cast_f32_bf16(const float* src, int32_t src_ld, void* dst, int
                                 void* stream) {
     GS_REQUIRE(src && dst && C > 0 && src_ld >= C && dst_ld >= C, "cast_f32_bf16: bad arguments");
     if (P <= 0) return 0;
-    cast_f32_bf16_kernel<<<flat_grid(P * dst_ld, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(cast_f32_bf16_kernel, dim3(flat_grid(P * dst_ld, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         src, src_ld, reinterpret_cast<__nv_bfloat16*>(dst), dst_ld, P, C);
     GS_LAUNCHED();
     return 0;
@@ -594,7 +609,7 @@ extern "C" int gs_colsum_f32(const float* src, int32_t ld, int64_t P, int32_t C,
     long long g = (P + (long long)R * 64 - 1) / ((long long)R * 64);
     if (g > 148 * 4) g = 148 * 4;
     if (g < 1) g = 1;
-    colsum_f32_kernel<<<(int)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ld, P, C, out);
+    gs::launch(colsum_f32_kernel, dim3((int)g), dim3(256), 0, static_cast<cudaStream_t>(stream), src, ld, P, C, out);
     GS_LAUNCHED();
     return 0;
 }
@@ -604,7 +619,7 @@ extern "C" int gs_nchw_f32_to_nhwc_bf16(const float* src, int32_t N, int32_t C, 
     GS_REQUIRE(src && dst && N > 0 && C > 0 && Cpad >= C && ld >= Cpad, "nchw->nhwc: bad arguments");
     const long long HW = (long long)H * W;
     dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((Cpad + 31) / 32), (unsigned)N);
-    nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(nchw_to_nhwc_kernel, dim3(grid), dim3(dim3(32, 8)), 0, static_cast<cudaStream_t>(stream), 
         src, C, HW, reinterpret_cast<__nv_bfloat16*>(dst), ld, Cpad);
     GS_LAUNCHED();
     return 0;
@@ -615,7 +630,7 @@ extern "C" int gs_nhwc_bf16_to_nchw_f32(const void* src, int32_t ld, int32_t N, 
     GS_REQUIRE(src && dst && N > 0 && C > 0 && ld >= C, "nhwc->nchw: bad arguments");
     const long long HW = (long long)H * W;
     dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N);
-    nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(nhwc_to_nchw_kernel, dim3(grid), dim3(dim3(32, 8)), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const __nv_bfloat16*>(src), ld, C, HW, dst);
     GS_LAUNCHED();
     return 0;
@@ -630,7 +645,7 @@ extern "C" int gs_im2col_image(const float* img_nchw, int32_t N, int32_t C, int3
                "im2col: output size (%d,%d) inconsistent", Ho, Wo);
     const long long total = (long long)N * Ho * Wo * Kpad;
     if (total <= 0) return 0;
-    im2col_image_kernel<<<flat_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(im2col_image_kernel, dim3(flat_grid(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         img_nchw, N, C, H, W, kh, kw, stride, pad, Ho, Wo, Kpad, reinterpret_cast<__nv_bfloat16*>(out));
     GS_LAUNCHED();
     return 0;

@@ -11,6 +11,7 @@
 #include "../../include/gaiaseg_b200.h"
 #include "gs_host.h"
 #include "gs_vec.cuh"
+#include "gs_comm.cuh"
 
 #include <stdlib.h>
 
@@ -46,6 +47,7 @@ __device__ __forceinline__ void block_reduce16_atomic(float (&a)[8], float (&b)[
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bn_stats_kernel(const uint4* __restrict__ x, long long ld8, long long P, int C,
                                                        int C8, int Vc, int R, double* __restrict__ stats) {
+    pdl_sync();
     __shared__ float red[256 * 16];
     const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
     const long long S = (long long)gridDim.x * R;
@@ -86,6 +88,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
                                    const float* __restrict__ beta, float* __restrict__ rm, float* __restrict__ rv,
                                    float momentum, float eps, float* __restrict__ mean, float* __restrict__ invstd,
                                    float* __restrict__ scale, float* __restrict__ shift) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double m = stats[c] / count;
@@ -110,6 +113,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
 __global__ void bn_eval_affine_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ rm, const float* __restrict__ rv, float eps,
                                       float* __restrict__ scale, float* __restrict__ shift) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float g = gamma ? gamma[c] : 1.f;
@@ -136,6 +140,10 @@ struct BnTrainArgs {
     float momentum, eps;
     float* aff;            // [4][C]: mean, invstd, scale, shift
     int C;
+    // several ranks: block 0 runs the SyncBN exchange of `stats` itself (in place) and then raises flag[0]; the other
+    // blocks wait for it before they read the sums -- no separate exchange launch on the critical chain
+    SyncArgs sync;
+    unsigned long long* flag;   // zero-initialised device word (NULL when sync.world <= 1)
 };
 
 template <bool HAS_RES, bool FROM_STATS>
@@ -144,16 +152,31 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
                                                        const uint4* __restrict__ res, long long res_ld8, int relu,
                                                        uint4* __restrict__ z, long long z_ld8, long long P, int C8,
                                                        int Vc, int R, BnTrainArgs t) {
+    pdl_sync();
     const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
     const long long S = (long long)gridDim.x * R;
+    if (FROM_STATS && t.sync.world > 1) {
+        if (blockIdx.x == 0) {
+            syncbn_exchange_block(const_cast<double*>(t.stats), 2 * t.C, t.sync.peers, t.sync.rank, t.sync.world,
+                                  t.sync.seq_dev, nullptr, nullptr, t.sync.timeout_ns, threadIdx.x, blockDim.x);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) st_release_gpu(t.flag, 1ull);
+        } else {
+            if (threadIdx.x == 0) {
+                while (ld_acquire_gpu(t.flag) == 0ull) {}
+            }
+            __syncthreads();
+        }
+    }
     for (int cv = cx; cv < C8; cv += Vc) {
         float sc[8], sh[8];
         if (FROM_STATS) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int c = cv * 8 + i;
-                const double m = t.stats[c] * t.inv_count;
-                double var = t.stats[t.C + c] * t.inv_count - m * m;
+                const double m = __ldcg(t.stats + c) * t.inv_count;
+                double var = __ldcg(t.stats + t.C + c) * t.inv_count - m * m;
                 if (var < 0.0) var = 0.0;
                 const float mf = static_cast<float>(m);
                 const float istd = rsqrtf(static_cast<float>(var) + t.eps);   // fp64 only where cancellation can occur
@@ -234,6 +257,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift, long long P, int C,
                                                             int C8, int Vc, int R, double* __restrict__ sums) {
+    pdl_sync();
     constexpr bool HAS_Z = (MASK == 1);
     __shared__ float red[256 * 16];
     const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
@@ -309,6 +333,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
                                                            uint4* __restrict__ dy, long long dy_ld8,
                                                            uint4* __restrict__ dres, long long dres_ld8,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    pdl_sync();
     constexpr bool HAS_Z = (MASK == 1);
     const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
     const long long S = (long long)gridDim.x * R;
@@ -377,6 +402,208 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused backward: reduce -> grid barrier (-> SyncBN exchange by block 0) -> apply, ONE cooperative launch.
+// Halves the BN-backward launches (2 x ~360 per sandwich cycle of 10-30 us kernels whose time is mostly launch ramp and
+// tail), the second pass over dz / y comes from L2, and with several ranks the exchange needs no launch of its own.
+// scratch: two zero-initialised 64-bit words: [0] arrival counter of the grid barrier, [1] "sums final" flag.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_reduce8_atomic(const float (&a)[8], float* red, int Vc, int R, int cv0, int C8,
+                                                     double* out) {
+    const int tid = threadIdx.x;
+    __syncthreads();  // previous round finished reading `red`
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[tid * 8 + i] = a[i];
+    __syncthreads();
+    const int nthreads = Vc * R;
+    for (int o = tid; o < 8 * Vc; o += nthreads) {
+        const int cx = o >> 3, i = o & 7;
+        const int cv = cv0 + cx;
+        if (cv >= C8) continue;
+        float s = 0.f;
+        for (int r = 0; r < R; ++r) s += red[(r * Vc + cx) * 8 + i];
+        atomicAdd(out + cv * 8 + i, static_cast<double>(s));
+    }
+}
+
+template <int MASK, bool HAS_DRES>
+__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const uint4* __restrict__ dz, long long dz_ld8,
+                                                           const uint4* __restrict__ y, long long y_ld8,
+                                                           const uint4* __restrict__ z, long long z_ld8,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           const float* __restrict__ gamma, double* __restrict__ sums,
+                                                           double inv_count, long long P, int C, int C8, int Vc, int R,
+                                                           uint4* __restrict__ dy, long long dy_ld8,
+                                                           uint4* __restrict__ dres, long long dres_ld8,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           SyncArgs sync, unsigned long long* __restrict__ scratch) {
+    pdl_sync();
+    constexpr bool HAS_Z = (MASK == 1);
+    __shared__ float red[256 * 8];
+    const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
+    const long long S = (long long)gridDim.x * R;
+    // ---------------- phase 1: per-channel sums of g and g * xhat ----------------
+    for (int cv0 = 0; cv0 < C8; cv0 += Vc) {
+        const int cv = cv0 + cx;
+        float sg[8], sx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sg[i] = 0.f; sx[i] = 0.f; }
+        if (cv < C8) {
+            float mu[8], is[8], sc[8], sh[8];
+            load8f(mean + cv * 8, mu);
+            load8f(invstd + cv * 8, is);
+            if (MASK == 2) { load8f(scale + cv * 8, sc); load8f(shift + cv * 8, sh); }
+            long long p = (long long)blockIdx.x * R + ry;
+            for (; p + 3 * S < P; p += 4 * S) {
+                uint4 a[4], b[4], c[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    a[u] = __ldg(dz + (p + u * S) * dz_ld8 + cv);      // (default caching: phase 2 re-reads these lines)
+                    b[u] = __ldg(y + (p + u * S) * y_ld8 + cv);
+                    if (HAS_Z) c[u] = __ldg(z + (p + u * S) * z_ld8 + cv);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float g[8], yy[8], zz[8];
+                    unpack8(a[u], g);
+                    unpack8(b[u], yy);
+                    if (HAS_Z) unpack8(c[u], zz);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        bool dead = HAS_Z && !(zz[i] > 0.f);
+                        if (MASK == 2) dead = !(fmaf(yy[i], sc[i], sh[i]) > 0.f);
+                        const float gi = dead ? 0.f : g[i];
+                        sg[i] += gi;
+                        sx[i] = fmaf(gi, (yy[i] - mu[i]) * is[i], sx[i]);
+                    }
+                }
+            }
+            for (; p < P; p += S) {
+                float g[8], yy[8], zz[8];
+                unpack8(__ldg(dz + p * dz_ld8 + cv), g);
+                unpack8(__ldg(y + p * y_ld8 + cv), yy);
+                if (HAS_Z) unpack8(__ldg(z + p * z_ld8 + cv), zz);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    bool dead = HAS_Z && !(zz[i] > 0.f);
+                    if (MASK == 2) dead = !(fmaf(yy[i], sc[i], sh[i]) > 0.f);
+                    const float gi = dead ? 0.f : g[i];
+                    sg[i] += gi;
+                    sx[i] = fmaf(gi, (yy[i] - mu[i]) * is[i], sx[i]);
+                }
+            }
+        }
+        block_reduce8_atomic(sg, red, Vc, R, cv0, C8, sums);
+        block_reduce8_atomic(sx, red, Vc, R, cv0, C8, sums + C);
+    }
+    // ---------------- grid barrier; block 0 finalises the sums ----------------
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(scratch, 1ull);
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = gtimer();
+            unsigned int spins = 0;
+            while (ld_acquire_gpu(scratch) < static_cast<unsigned long long>(gridDim.x)) {
+                if ((++spins & 4095u) == 0 && gtimer() - t0 > 5000000000ull) {
+                    printf("gaiaseg_b200: bn_bwd grid barrier timed out (%llu of %u blocks arrived)\n", ld_acquire_gpu(scratch),
+                           gridDim.x);
+                    __trap();
+                }
+            }
+        }
+        __syncthreads();
+        if (sync.world > 1) {
+            // LOCAL sums -> parameter gradients, then the exchange over NVLink peer memory (sums := sums over all ranks)
+            syncbn_exchange_block(sums, 2 * C, sync.peers, sync.rank, sync.world, sync.seq_dev, dgamma, dbeta,
+                                  sync.timeout_ns, threadIdx.x, blockDim.x);
+        } else {
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                if (dgamma) dgamma[c] += static_cast<float>(__ldcg(sums + C + c));
+                if (dbeta) dbeta[c] += static_cast<float>(__ldcg(sums + c));
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_gpu(scratch + 1, 1ull);
+    } else {
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = gtimer();
+            unsigned int spins = 0;
+            while (ld_acquire_gpu(scratch + 1) == 0ull) {
+                if ((++spins & 4095u) == 0 && gtimer() - t0 > (sync.world > 1 ? sync.timeout_ns + 5000000000ull : 5000000000ull)) {
+                    printf("gaiaseg_b200: bn_bwd waited too long for block 0\n");
+                    __trap();
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---------------- phase 2: dy = gamma*invstd*( g - mean(g) - xhat*mean(g*xhat) ); dres = g ----------------
+    for (int cv = cx; cv < C8; cv += Vc) {
+        float mu[8], is[8], k0[8], k1[8], k2[8], sc[8], sh[8];
+        load8f(mean + cv * 8, mu);
+        load8f(invstd + cv * 8, is);
+        if (MASK == 2) { load8f(scale + cv * 8, sc); load8f(shift + cv * 8, sh); }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = cv * 8 + i;
+            const float g = gamma ? __ldg(gamma + c) : 1.f;
+            k0[i] = g * is[i];
+            k1[i] = static_cast<float>(__ldcg(sums + c) * inv_count);
+            k2[i] = static_cast<float>(__ldcg(sums + C + c) * inv_count);
+        }
+        long long p = (long long)blockIdx.x * R + ry;
+        for (; p + 3 * S < P; p += 4 * S) {
+            uint4 va[4], vb[4], vc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                va[u] = ldg_stream(dz + (p + u * S) * dz_ld8 + cv);
+                vb[u] = ldg_stream(y + (p + u * S) * y_ld8 + cv);
+                if (HAS_Z) vc[u] = ldg_stream(z + (p + u * S) * z_ld8 + cv);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float g[8], yy[8], zz[8], o[8];
+                unpack8(va[u], g);
+                unpack8(vb[u], yy);
+                if (HAS_Z) unpack8(vc[u], zz);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    bool dead = HAS_Z && !(zz[i] > 0.f);
+                    if (MASK == 2) dead = !(fmaf(yy[i], sc[i], sh[i]) > 0.f);
+                    const float gi = dead ? 0.f : g[i];
+                    g[i] = gi;
+                    const float xh = (yy[i] - mu[i]) * is[i];
+                    o[i] = k0[i] * (gi - k1[i] - xh * k2[i]);
+                }
+                stg_stream(dy + (p + u * S) * dy_ld8 + cv, pack8(o));
+                if (HAS_DRES) stg_stream(dres + (p + u * S) * dres_ld8 + cv, pack8(g));
+            }
+        }
+        for (; p < P; p += S) {
+            float g[8], yy[8], zz[8], o[8];
+            unpack8(ldg_stream(dz + p * dz_ld8 + cv), g);
+            unpack8(ldg_stream(y + p * y_ld8 + cv), yy);
+            if (HAS_Z) unpack8(ldg_stream(z + p * z_ld8 + cv), zz);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                bool dead = HAS_Z && !(zz[i] > 0.f);
+                if (MASK == 2) dead = !(fmaf(yy[i], sc[i], sh[i]) > 0.f);
+                const float gi = dead ? 0.f : g[i];
+                g[i] = gi;
+                const float xh = (yy[i] - mu[i]) * is[i];
+                o[i] = k0[i] * (gi - k1[i] - xh * k2[i]);
+            }
+            stg_stream(dy + p * dy_ld8 + cv, pack8(o));
+            if (HAS_DRES) stg_stream(dres + p * dres_ld8 + cv, pack8(g));
+        }
+    }
+}
+
 // eval-mode / frozen BN backward: dy = scale * g (no statistics terms); dres = g
 template <bool HAS_Z, bool HAS_DRES>
 __global__ void __launch_bounds__(256) affine_bwd_kernel(const uint4* __restrict__ dz, long long dz_ld8,
@@ -384,6 +611,7 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(const uint4* __restrict
                                                          const float* __restrict__ scale, long long P, int C8, int Vc,
                                                          int R, uint4* __restrict__ dy, long long dy_ld8,
                                                          uint4* __restrict__ dres, long long dres_ld8) {
+    pdl_sync();
     const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
     const long long S = (long long)gridDim.x * R;
     for (int cv = cx; cv < C8; cv += Vc) {
@@ -411,6 +639,7 @@ __global__ void __launch_bounds__(256) affine_bwd_kernel(const uint4* __restrict
 
 __global__ void bn_bwd_param_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, int accumulate) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float dg = static_cast<float>(sums[C + c]);
@@ -445,6 +674,26 @@ static inline int reduce_grid(const ColMap& m, long long P) {
     const int per_sm = m.threads <= 192 ? bps + 1 : bps;   // narrow blocks (C8 = 160, 320): keep >= 480 threads per SM
     return colmap_grid(m, P, ppt, 148 * per_sm);
 }
+// gs_sync_desc (C ABI) -> SyncArgs (kernel argument); NULL / world <= 1 -> no exchange
+static int make_sync(const gs_sync_desc* d, SyncArgs* out, const char* what) {
+    *out = SyncArgs{};
+    out->world = 1;
+    if (d == nullptr || d->world <= 1) return 0;
+    GS_REQUIRE(d->world <= kCommMaxWorld && d->rank >= 0 && d->rank < d->world, "%s: bad rank %d / world %d", what, d->rank,
+               d->world);
+    GS_REQUIRE(d->peer_inboxes != nullptr && d->seq_dev != nullptr, "%s: sync descriptor without inboxes / sequence counter",
+               what);
+    for (int r = 0; r < d->world; ++r) {
+        GS_REQUIRE(d->peer_inboxes[r] != nullptr, "%s: inbox of rank %d is not mapped", what, r);
+        out->peers.p[r] = reinterpret_cast<ulonglong2*>(const_cast<void*>(d->peer_inboxes[r]));
+    }
+    out->rank = d->rank;
+    out->world = d->world;
+    out->seq_dev = reinterpret_cast<unsigned long long*>(d->seq_dev);
+    out->timeout_ns = comm_timeout_ns();
+    return 0;
+}
+
 static inline int stream_grid(const ColMap& m, long long P) {
     static const int bps = env_int("GS_BN_STREAM_BLOCKS_PER_SM", 3), ppt = env_int("GS_BN_STREAM_PPT", 12);
     return colmap_grid(m, P, ppt, 148 * bps);
@@ -456,7 +705,7 @@ extern "C" int gs_bn_stats(const void* x, int64_t P, int32_t C, int32_t ld, doub
     if (P <= 0) return 0;
     const ColMap m = make_colmap(C);
     const int grid = reduce_grid(m, P);
-    bn_stats_kernel<<<grid, m.threads, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(bn_stats_kernel, dim3(grid), dim3(m.threads), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const uint4*>(x), ld / 8, P, C, m.C8, m.Vc, m.R, stats);
     GS_LAUNCHED();
     return 0;
@@ -467,7 +716,7 @@ extern "C" int gs_bn_finalize(const double* stats, double count, int32_t C, cons
                               float* invstd, float* scale, float* shift, void* stream) {
     GS_REQUIRE(stats && scale && shift, "bn_finalize: null pointer");
     GS_REQUIRE(C > 0 && count > 0, "bn_finalize: empty reduction (C=%d count=%f)", C, count);
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), 
         stats, count, C, gamma, beta, running_mean, running_var, momentum, eps, mean, invstd, scale, shift);
     GS_LAUNCHED();
     return 0;
@@ -477,7 +726,7 @@ extern "C" int gs_bn_eval_affine(int32_t C, const float* gamma, const float* bet
                                  const float* running_var, float eps, float* scale, float* shift, void* stream) {
     GS_REQUIRE(running_mean && running_var && scale && shift, "bn_eval_affine: null pointer");
     GS_REQUIRE(C > 0, "bn_eval_affine: C=%d", C);
-    bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(bn_eval_affine_kernel, dim3((C + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), 
         C, gamma, beta, running_mean, running_var, eps, scale, shift);
     GS_LAUNCHED();
     return 0;
@@ -493,11 +742,11 @@ extern "C" int gs_bn_apply(const void* y, int32_t y_ld, const float* scale, cons
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     BnTrainArgs t{};
     if (residual)
-        bn_apply_kernel<true, false><<<grid, m.threads, 0, st>>>(
+        gs::launch(bn_apply_kernel<true, false>, dim3(grid), dim3(m.threads), 0, st, 
             reinterpret_cast<const uint4*>(y), y_ld / 8, scale, shift, reinterpret_cast<const uint4*>(residual),
             res_ld / 8, relu, reinterpret_cast<uint4*>(z), z_ld / 8, P, m.C8, m.Vc, m.R, t);
     else
-        bn_apply_kernel<false, false><<<grid, m.threads, 0, st>>>(
+        gs::launch(bn_apply_kernel<false, false>, dim3(grid), dim3(m.threads), 0, st, 
             reinterpret_cast<const uint4*>(y), y_ld / 8, scale, shift, nullptr, 0, relu, reinterpret_cast<uint4*>(z),
             z_ld / 8, P, m.C8, m.Vc, m.R, t);
     GS_LAUNCHED();
@@ -507,7 +756,7 @@ extern "C" int gs_bn_apply(const void* y, int32_t y_ld, const float* scale, cons
 extern "C" int gs_bn_apply_train(const void* y, int32_t y_ld, const double* stats, double count, const float* gamma,
                                  const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                                  float* aff, const void* residual, int32_t res_ld, int32_t relu, void* z, int32_t z_ld,
-                                 int64_t P, int32_t C, void* stream) {
+                                 int64_t P, int32_t C, const gs_sync_desc* sync, void* stream) {
     if (check_act(y, y_ld, C, "bn_apply_train y") || check_act(z, z_ld, C, "bn_apply_train z")) return -1;
     if (residual && check_act(residual, res_ld, C, "bn_apply_train residual")) return -1;
     GS_REQUIRE(stats && aff && count > 0, "bn_apply_train: null stats / aff or empty count");
@@ -519,12 +768,18 @@ extern "C" int gs_bn_apply_train(const void* y, int32_t y_ld, const double* stat
     t.stats = stats; t.inv_count = 1.0 / count; t.unbias = count > 1.0 ? count / (count - 1.0) : 1.0;
     t.gamma = gamma; t.beta = beta; t.rm = running_mean; t.rv = running_var; t.momentum = momentum; t.eps = eps;
     t.aff = aff; t.C = C;
+    if (make_sync(sync, &t.sync, "bn_apply_train")) return -1;
+    if (t.sync.world > 1) {
+        GS_REQUIRE(C <= kCommSlotDoubles / 2, "bn_apply_train: %d channels exceed the exchange slot", C);
+        // the caller's stats buffer carries two zero-initialised scratch words behind the 2C sums
+        t.flag = reinterpret_cast<unsigned long long*>(const_cast<double*>(stats) + 2 * C) + 1;
+    }
     if (residual)
-        bn_apply_kernel<true, true><<<grid, m.threads, 0, st>>>(
+        gs::launch(bn_apply_kernel<true, true>, dim3(grid), dim3(m.threads), 0, st, 
             reinterpret_cast<const uint4*>(y), y_ld / 8, nullptr, nullptr, reinterpret_cast<const uint4*>(residual),
             res_ld / 8, relu, reinterpret_cast<uint4*>(z), z_ld / 8, P, m.C8, m.Vc, m.R, t);
     else
-        bn_apply_kernel<false, true><<<grid, m.threads, 0, st>>>(
+        gs::launch(bn_apply_kernel<false, true>, dim3(grid), dim3(m.threads), 0, st, 
             reinterpret_cast<const uint4*>(y), y_ld / 8, nullptr, nullptr, nullptr, 0, relu,
             reinterpret_cast<uint4*>(z), z_ld / 8, P, m.C8, m.Vc, m.R, t);
     GS_LAUNCHED();
@@ -544,7 +799,7 @@ extern "C" int gs_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* y, in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int mask = !relu ? 0 : (z ? 1 : 2);
 #define GS_BWD_REDUCE(MK)                                                                                            \
-    bn_bwd_reduce_kernel<MK><<<grid, m.threads, 0, st>>>(                                                            \
+    gs::launch(bn_bwd_reduce_kernel<MK>, dim3(grid), dim3(m.threads), 0, st,                                                             \
         reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8,                  \
         reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, scale, shift, P, C, m.C8, m.Vc, m.R, sums)
     if (mask == 0) GS_BWD_REDUCE(0);
@@ -574,7 +829,7 @@ extern "C" int gs_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* y, int
     const double inv_count = 1.0 / count;
     const int mask = !relu ? 0 : (z ? 1 : 2);
 #define GS_BWD_APPLY(MK, HD)                                                                                         \
-    bn_bwd_apply_kernel<MK, HD><<<grid, m.threads, 0, st>>>(                                                         \
+    gs::launch(bn_bwd_apply_kernel<MK, HD>, dim3(grid), dim3(m.threads), 0, st,                                                          \
         reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8,                  \
         reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, scale, shift, gamma, sums, inv_count, P, C, m.C8, \
         m.Vc, m.R, reinterpret_cast<uint4*>(dy), dy_ld / 8, reinterpret_cast<uint4*>(dres), dres_ld / 8, dgamma, dbeta)
@@ -592,6 +847,61 @@ extern "C" int gs_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* y, int
     return 0;
 }
 
+extern "C" int gs_bn_bwd(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z, int32_t z_ld,
+                         const float* mean, const float* invstd, const float* scale, const float* shift, int32_t relu,
+                         const float* gamma, double* sums, double count, int64_t P, int32_t C, void* dy, int32_t dy_ld,
+                         void* dres, int32_t dres_ld, float* dgamma, float* dbeta, const gs_sync_desc* sync,
+                         void* stream) {
+    if (check_act(dz, dz_ld, C, "bn_bwd dz") || check_act(y, y_ld, C, "bn_bwd y") || check_act(dy, dy_ld, C, "bn_bwd dy"))
+        return -1;
+    if (z && check_act(z, z_ld, C, "bn_bwd z")) return -1;
+    if (dres && check_act(dres, dres_ld, C, "bn_bwd dres")) return -1;
+    GS_REQUIRE(mean && invstd && sums && count > 0, "bn_bwd: null pointer / empty count");
+    GS_REQUIRE(!relu || z || (scale && shift), "bn_bwd: ReLU mask needs z or (scale, shift)");
+    if (P <= 0) return 0;
+    SyncArgs sa;
+    if (make_sync(sync, &sa, "bn_bwd")) return -1;
+    GS_REQUIRE(sa.world <= 1 || C <= kCommSlotDoubles / 2, "bn_bwd: %d channels exceed the exchange slot", C);
+    const ColMap m = make_colmap(C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int mask = !relu ? 0 : (z ? 1 : 2);
+    // the blocks wait on one another (grid barrier): COOPERATIVE launch, grid <= what is co-resident by construction
+    static const int bps = env_int("GS_BN_FUSED_BLOCKS_PER_SM", 2), ppt = env_int("GS_BN_FUSED_PPT", 8);
+    const int grid = colmap_grid(m, P, ppt, num_sms() * bps);
+    unsigned long long* scratch = reinterpret_cast<unsigned long long*>(sums + 2 * C);   // two zeroed words behind the sums
+    const double inv_count = 1.0 / count;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(m.threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    static const int coop = env_int("GS_BN_FUSED_COOP", 1);
+    cfg.numAttrs = coop ? 1 : 0;
+#define GS_BWD_FUSED(MK, HD)                                                                                           \
+    GS_CUDA_OK(cudaLaunchKernelEx(&cfg, bn_bwd_fused_kernel<MK, HD>, reinterpret_cast<const uint4*>(dz),              \
+                                  (long long)(dz_ld / 8), reinterpret_cast<const uint4*>(y), (long long)(y_ld / 8),   \
+                                  reinterpret_cast<const uint4*>(z), (long long)(z_ld / 8), mean, invstd, scale, shift, \
+                                  gamma, sums, inv_count, (long long)P, (int)C, m.C8, m.Vc, m.R,                      \
+                                  reinterpret_cast<uint4*>(dy), (long long)(dy_ld / 8), reinterpret_cast<uint4*>(dres), \
+                                  (long long)(dres_ld / 8), dgamma, dbeta, sa, scratch))
+    if (dres) {
+        if (mask == 0) GS_BWD_FUSED(0, true);
+        else if (mask == 1) GS_BWD_FUSED(1, true);
+        else GS_BWD_FUSED(2, true);
+    } else {
+        if (mask == 0) GS_BWD_FUSED(0, false);
+        else if (mask == 1) GS_BWD_FUSED(1, false);
+        else GS_BWD_FUSED(2, false);
+    }
+#undef GS_BWD_FUSED
+    GS_LAUNCHED();
+    return 0;
+}
+
 extern "C" int gs_affine_bwd(const void* dz, int32_t dz_ld, const void* z, int32_t z_ld, const float* scale, int64_t P,
                              int32_t C, void* dy, int32_t dy_ld, void* dres, int32_t dres_ld, void* stream) {
     if (check_act(dz, dz_ld, C, "affine_bwd dz") || check_act(dy, dy_ld, C, "affine_bwd dy")) return -1;
@@ -602,7 +912,7 @@ extern "C" int gs_affine_bwd(const void* dz, int32_t dz_ld, const void* z, int32
     const int grid = stream_grid(m, P);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define GS_AFF_BWD(HZ, HD)                                                                                      \
-    affine_bwd_kernel<HZ, HD><<<grid, m.threads, 0, st>>>(                                                      \
+    gs::launch(affine_bwd_kernel<HZ, HD>, dim3(grid), dim3(m.threads), 0, st,                                                       \
         reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(z), z_ld / 8, scale, P,   \
         m.C8, m.Vc, m.R, reinterpret_cast<uint4*>(dy), dy_ld / 8, reinterpret_cast<uint4*>(dres), dres_ld / 8)
     if (z && dres) GS_AFF_BWD(true, true);
@@ -617,7 +927,7 @@ extern "C" int gs_affine_bwd(const void* dz, int32_t dz_ld, const void* z, int32
 extern "C" int gs_bn_bwd_param(const double* sums_local, int32_t C, float* dgamma, float* dbeta, int32_t accumulate,
                                void* stream) {
     GS_REQUIRE(sums_local != nullptr && C > 0, "bn_bwd_param: null pointer");
-    bn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums_local, C, dgamma, dbeta,
+    gs::launch(bn_bwd_param_kernel, dim3((C + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), sums_local, C, dgamma, dbeta,
                                                                                       accumulate);
     GS_LAUNCHED();
     return 0;

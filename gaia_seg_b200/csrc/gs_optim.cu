@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) sgd_flat_kernel(float4* __restrict__ p, c
                                                        float4* __restrict__ buf, long long n4,
                                                        const float* __restrict__ hyper, int first,
                                                        uint2* __restrict__ shadow) {
+    pdl_sync();
     // hyper-parameters live in device memory so that a captured CUDA graph of the step follows the LR schedule
     const float lr = __ldg(hyper), mom = __ldg(hyper + 1), wd = __ldg(hyper + 2), gscale = __ldg(hyper + 3);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
@@ -59,7 +60,7 @@ extern "C" int gs_sgd_flat(float* p, const float* g, float* momentum_buf, int64_
     const long long n4 = n / 4;
     long long grid = (n4 + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
-    sgd_flat_kernel<<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gs::launch(sgd_flat_kernel, dim3((int)grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(momentum_buf), n4,
         hyper, first_step, reinterpret_cast<uint2*>(shadow_bf16));
     GS_LAUNCHED();

@@ -299,7 +299,7 @@ def conv_forward(x, conv, Co, scale=None, shift=None, residual=None, relu=False,
     g.y_ld = y_ld
     stats = None
     if want_stats:
-        stats = zeros_f64(2 * Co, dev)
+        stats = zeros_f64(2 * Co + 2, dev)[:2 * Co]   # + two zeroed scratch words behind the sums (gs_sync_desc contract)
     flags = (1 if relu else 0) | (2 if out_f32 else 0)
     res_ld = 0
     if residual is not None:
@@ -362,6 +362,11 @@ def conv_dgrad(conv, dy, g, x_shape, add=None):
 # ------------------------------------------------------------------------------------------------
 # batch norm pieces
 # ------------------------------------------------------------------------------------------------
+# GS_BN_FUSED_BWD=0: the round-1 two-kernel BN backward; GS_SYNCBN_FOLD=0: separate gs_syncbn_allreduce launches
+FUSED_BN_BWD = os.environ.get('GS_BN_FUSED_BWD', 'auto')    # 'auto': only with several ranks (measured, profiles/r02_bn_fused.md)
+FOLD_EXCHANGE = os.environ.get('GS_SYNCBN_FOLD', '1') != '0'
+
+
 def bn_batch_mode(bn):
     """True when the layer normalises with mini-batch statistics (train mode, or running stats dropped
     by `caliberate_bn.use_minibatch_stats`, tools/test_supernet.py:190-198)."""
@@ -449,6 +454,9 @@ class PeerExchange:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.own, self.ptrs = own, table
         self.seq = torch.zeros(1, dtype=torch.int64, device=torch.device('cuda', torch.cuda.current_device()))
+        # descriptor handed to the DynBN kernels that run the exchange themselves (gs_bn_apply_train / gs_bn_bwd)
+        self.desc = _lib.SyncDesc(ctypes.cast(self.ptrs, ctypes.c_void_p), self.rank, self.world, self.seq.data_ptr())
+        self.desc_ref = ctypes.byref(self.desc)
 
     def all_reduce(self, stats, dgamma=None, dbeta=None):
         call('gs_syncbn_allreduce', stats.data_ptr(), stats.numel(), self.ptrs, self.rank, self.world, self.seq.data_ptr(),
@@ -560,8 +568,13 @@ def bn_train_apply(bn, y, stats, C, residual=None, relu=False):
     """all-reduce the packed (sum, sumsq) over the SyncBN group, then ONE kernel: finalize (mean / invstd / scale /
     shift, running-stat update of the channel prefix) + normalise + residual + ReLU.  Returns (z, aff, count)."""
     pg, world = _sync_group(bn)
+    sync = None
     if world > 1:
-        stats_all_reduce(stats, pg)
+        ex = PeerExchange.get(pg)
+        if ex and FOLD_EXCHANGE:
+            sync = ex.desc_ref            # block 0 of the apply kernel exchanges the sums itself: no extra launch
+        else:
+            stats_all_reduce(stats, pg)
     count = float(_pixels(y)) * world
     aff = torch.empty((4, C), dtype=torch.float32, device=y.device)
     upd = bn.training and bn.track_running_stats and bn.running_mean is not None
@@ -576,7 +589,7 @@ def bn_train_apply(bn, y, stats, C, residual=None, relu=False):
     call('gs_bn_apply_train', y.data_ptr(), act_ld(y), stats.data_ptr(), count, _ptr(bn.weight), _ptr(bn.bias),
          bn.running_mean.data_ptr() if upd else None, bn.running_var.data_ptr() if upd else None,
          float(bn.momentum if bn.momentum is not None else 0.0), float(bn.eps), aff.data_ptr(), _ptr(residual), res_ld,
-         1 if relu else 0, z.data_ptr(), C, _pixels(y), C, _stream())
+         1 if relu else 0, z.data_ptr(), C, _pixels(y), C, sync, _stream())
     if upd:
         bn._gs_nbt_pending = getattr(bn, '_gs_nbt_pending', 0) + 1
         if _touched_bns is not None:
@@ -591,20 +604,29 @@ def bn_backward(bn, dz, y, aff, count, zmask, relu, want_dres):
     P, dev, st = N * H * W, dz.device, _stream()
     mean, invstd, scale, shift = aff[0], aff[1], aff[2], aff[3]
     zl = act_ld(zmask) if zmask is not None else 0
-    sums = zeros_f64(2 * C, dev)
-    call('gs_bn_bwd_reduce', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),
-         invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, P, C, sums.data_ptr(), st)
     gw = bn.weight is not None and bn.weight.requires_grad
     gb = bn.bias is not None and bn.bias.requires_grad
     dgam = _param_grad(bn.weight).data_ptr() if gw else None
     dbet = _param_grad(bn.bias).data_ptr() if gb else None
     pg, world = _sync_group(bn)
+    ex = PeerExchange.get(pg) if world > 1 else None
+    sums = zeros_f64(2 * C + 2, dev)[:2 * C]
+    dy = new_act(N, C, H, W, dev)
+    dres = new_act(N, C, H, W, dev) if want_dres else None
+    fused = FUSED_BN_BWD == '1' or (FUSED_BN_BWD == 'auto' and world > 1)
+    if fused and (world == 1 or (ex and FOLD_EXCHANGE)):
+        # ONE cooperative launch: reduce -> grid barrier -> (peer exchange by block 0, parameter gradients from the local
+        # sums) -> apply; the second pass over dz / y comes from L2
+        call('gs_bn_bwd', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),
+             invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, _ptr(bn.weight), sums.data_ptr(),
+             float(count), P, C, dy.data_ptr(), C, _ptr(dres), C, dgam, dbet, ex.desc_ref if world > 1 else None, st)
+        return dy, dres
+    call('gs_bn_bwd_reduce', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),
+         invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, P, C, sums.data_ptr(), st)
     if world > 1:
         # parameter gradients come from the LOCAL sums (the gradient all-reduce averages them later): same kernel
         stats_all_reduce(sums, pg, dgam, dbet)
         dgam = dbet = None
-    dy = new_act(N, C, H, W, dev)
-    dres = new_act(N, C, H, W, dev) if want_dres else None
     call('gs_bn_bwd_apply', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),
          invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, _ptr(bn.weight), sums.data_ptr(),
          float(count), P, C, dy.data_ptr(), C, _ptr(dres), C, dgam, dbet, st)
@@ -621,7 +643,7 @@ def bn_eval_affine(bn, C):
 def bn_stats(x):
     x = as_act(x)
     C = x.shape[1]
-    stats = zeros_f64(2 * C, x.device)
+    stats = zeros_f64(2 * C + 2, x.device)[:2 * C]
     call('gs_bn_stats', x.data_ptr(), _pixels(x), C, act_ld(x), stats.data_ptr(), _stream())
     return stats
 

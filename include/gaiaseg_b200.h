@@ -129,13 +129,26 @@ int gs_bn_eval_affine(int32_t C, const float* gamma, const float* beta, const fl
 int gs_bn_apply(const void* y, int32_t y_ld, const float* scale, const float* shift, const void* residual,
                 int32_t res_ld, int32_t relu, void* z, int32_t z_ld, int64_t P, int32_t C, void* stream);
 
+/* SyncBN over several ranks WITHOUT a separate exchange launch: the DynBN kernels below take this descriptor of the
+ * NVLink peer-memory exchange (see gs_syncbn_allreduce) and run it themselves -- block 0 exchanges the packed sums in
+ * place while the other blocks wait on a flag.  NULL (or world <= 1): the sums are used as they are.
+ * The sums buffer handed to such a kernel must be 2*C + 2 doubles, all ZERO-initialised before the producing kernel runs:
+ * the two trailing 8-byte words are scratch (grid-barrier counter, "sums final" flag).
+ * replaces: [EXT] torch.nn.SyncBatchNorm's all_gather / all_reduce under gaiavision DynSyncBN
+ * (configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:20-23). */
+typedef struct gs_sync_desc {
+    const void* const* peer_inboxes; /* [world] inbox of every rank (own + gs_ipc_open'ed), as for gs_syncbn_allreduce */
+    int32_t rank, world;
+    void* seq_dev;                    /* device-resident int64 sequence counter shared by ALL exchanges of the group */
+} gs_sync_desc;
+
 /* Training-mode apply with the finalize step folded into the kernel prologue (one launch instead of two):
  * scale / shift are derived from the (all-reduced) sums, block 0 stores aff = [mean | invstd | scale | shift]
  * ([4][C] fp32, needed by the backward pass) and updates running_mean / running_var (NULL to skip). */
 int gs_bn_apply_train(const void* y, int32_t y_ld, const double* stats, double count, const float* gamma,
                       const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                       float* aff, const void* residual, int32_t res_ld, int32_t relu, void* z, int32_t z_ld, int64_t P,
-                      int32_t C, void* stream);
+                      int32_t C, const gs_sync_desc* sync, void* stream);
 
 /* Backward pass 1: g = dz * mask;  sums[0:C] += sum g ; sums[C:2C] += sum g * xhat, xhat = (y-mean)*invstd.
  * mask: relu == 0 -> none; z != NULL -> [z > 0] (needed when a residual was added before the ReLU);
@@ -143,6 +156,15 @@ int gs_bn_apply_train(const void* y, int32_t y_ld, const double* stats, double c
 int gs_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z, int32_t z_ld,
                      const float* mean, const float* invstd, const float* scale, const float* shift, int32_t relu,
                      int64_t P, int32_t C, double* sums, void* stream);
+
+/* Fused backward: pass 1 (below) -> grid barrier -> [SyncBN exchange of the sums by block 0, parameter gradients from the
+ * LOCAL sums] -> pass 2 (below) in ONE cooperative launch; the second pass over dz / y / z comes from L2.
+ * sums: fp64 [2*C + 2], zero on entry (see gs_sync_desc); count = elements per channel over the whole SyncBN group.
+ * dgamma / dbeta (may be NULL) are incremented by the local sums. */
+int gs_bn_bwd(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z, int32_t z_ld, const float* mean,
+              const float* invstd, const float* scale, const float* shift, int32_t relu, const float* gamma, double* sums,
+              double count, int64_t P, int32_t C, void* dy, int32_t dy_ld, void* dres, int32_t dres_ld, float* dgamma,
+              float* dbeta, const gs_sync_desc* sync, void* stream);
 
 /* Backward pass 2 (sums all-reduced over the SyncBN group, count = elements per channel in the group):
  *   dy = gamma*invstd*( g - sum_g/count - xhat*sum_gx/count )           -> dy (bf16)

@@ -135,11 +135,19 @@ def _reset_running_stats(model):
             m.running_var.fill_(1)
 
 
+def rel_l2(got, ref, tol, name):
+    got, ref = got.detach().double().cpu().flatten(), ref.detach().double().cpu().flatten()
+    err = float((got - ref).norm() / (ref.norm() + 1e-300)) if torch.isfinite(got).all() else float('inf')
+    return dict(name=name, ok=err <= tol, err=err, tol=tol)
+
+
 def bn_calibration_checks(gs):
     """(a) use_minibatch_stats: eval() with the running statistics dropped normalises with the statistics of the test
     batch; (b) reset_stats followed by train-mode forward passes (multi_gpu_test does not call eval()) re-estimates the
-    running statistics; (c) eval() afterwards uses them.  Low-res logits vs the fp32 oracle (bf16 tolerance of the
-    whole-net tests: 2e-2 relative to the logit scale) and label-map agreement >= 97 %."""
+    running statistics; (c) eval() afterwards uses them.  Low-res logits vs the fp32 oracle as a relative L2 error over
+    the whole logit tensor <= 5e-2 (bf16 activation storage through ~35 layers; an ELEMENT-wise bound is meaningless here:
+    batch statistics on 8 x 12 maps with random weights leave channels with variance ~1e-6 whose 1 / std amplifies one bf16
+    rounding to O(1) in a few logits) and label-map agreement >= 97 %."""
     import numpy as np
     out = []
     cfg = C.small_cfg(aux=False, deep_stem=True, os8=True)
@@ -154,18 +162,40 @@ def bn_calibration_checks(gs):
             lg = gm.encode_decode_lowres(img.cuda(), metas[0]).float().cpu()
         return lo, lg
 
-    # (a)
+    # (a) batch statistics on 8 x 12 maps amplify bf16 STORAGE rounding (channels with variance ~1e-6 get 1 / std ~ 1e3), so
+    # the reference here is the oracle with bf16 storage emulated at the CUDA path's rounding points (fp64 arithmetic);
+    # the plain fp32 oracle's distance is reported next to it
     om, gm, _ = C.build_pair(gs, cfg, seed=6)
     om.manipulate_arch(arch); gm.manipulate_arch(arch)
     _drop_running_stats(om); _drop_running_stats(gm)
     om.eval(); gm.eval()
-    lo, lg = lowres(om, gm)
-    out.append(rel_err(lg, lo, 2e-2, 'bn_calib.use_minibatch_stats.eval_logits_vs_fp32_oracle'))
+    lo32, lg = lowres(om, gm)
+    def storage_oracle(dtype):
+        ome = O.build_segmentor(cfg)
+        ome.load_state_dict(om.state_dict(), strict=False)
+        ome.manipulate_arch(arch)
+        _drop_running_stats(ome)
+        C.emulate_bf16_storage(ome)
+        ome = ome.to(dtype).eval()
+        with torch.no_grad():
+            return ome.decode_head(ome.backbone(img.to(dtype))).double(), ome.simple_test(img.to(dtype))
+
+    lo, po = storage_oracle(torch.float64)
+    lo_s32, po_s32 = storage_oracle(torch.float32)
+    # noise floor of this ill-conditioned case: the SAME oracle (same bf16 rounding points) in fp32 vs fp64 arithmetic
+    floor = rel_l2(lo_s32, lo, 1.0, '')['err']
+    floor_agree = float((po_s32 == po).float().mean())
+    tol = 4 * floor + 2e-2
+    r = rel_l2(lg, lo, tol, 'bn_calib.use_minibatch_stats.eval_logits_rel_l2_vs_bf16_storage_oracle')
+    r.update(oracle_fp32_vs_fp64_same_rounding_points=floor, rel_l2_vs_plain_fp32_oracle=rel_l2(lg, lo32, 1.0, '')['err'],
+             plain_fp32_vs_bf16_storage_oracle=rel_l2(lo32, lo, 1.0, '')['err'])
+    out.append(r)
     with torch.no_grad():
-        po = om.simple_test(img)
         pg = gm(return_loss=False, img=[img.cuda()], img_metas=metas)
     agree = float((torch.from_numpy(np.stack(pg)) == po).float().mean())
-    out.append(dict(name='bn_calib.use_minibatch_stats.labelmap_agreement', ok=agree >= 0.97, err=1 - agree, tol=0.03))
+    need = min(0.97, floor_agree - 0.03)
+    out.append(dict(name='bn_calib.use_minibatch_stats.labelmap_agreement', ok=agree >= need, err=1 - agree, tol=1 - need,
+                    oracle_fp32_vs_fp64_agreement=floor_agree))
     # the batch-stat eval result must differ from the running-stat eval result (otherwise the mode is not exercised)
     om2, gm2, _ = C.build_pair(gs, cfg, seed=6)
     om2.manipulate_arch(arch); gm2.manipulate_arch(arch)
@@ -205,7 +235,12 @@ def bn_calibration_checks(gs):
                     if v > 0) and any(v == 3 for v in nbt), err=0.0, tol=0))
     om.eval(); gm.eval()
     lo, lg = lowres(om, gm)
-    out.append(rel_err(lg, lo, 3e-2, 'bn_calib.eval_after_recalibration_logits_vs_fp32_oracle'))
+    out.append(rel_l2(lg, lo, 5e-2, 'bn_calib.eval_after_recalibration_logits_rel_l2_vs_fp32_oracle'))
+    with torch.no_grad():
+        po = om.simple_test(img)
+        pg = gm(return_loss=False, img=[img.cuda()], img_metas=metas)
+    agree = float((torch.from_numpy(np.stack(pg)) == po).float().mean())
+    out.append(dict(name='bn_calib.eval_after_recalibration.labelmap_agreement', ok=agree >= 0.97, err=1 - agree, tol=0.03))
     return out
 
 
@@ -446,11 +481,68 @@ def deep_stage_checks(gs, depth=29):
     out.append(dict(name=name + '.param_grads_mean_1mcos', ok=m_c <= 4 * m_s + 5e-3 and len(d_c) == len(d_s), err=m_c,
                     tol=4 * m_s + 5e-3, oracle_fp32_vs_fp64=m_s, worst_param=worst, worst_1mcos=d_c[worst],
                     n_params=len(d_c)))
-    # the LAST block's gradients see only one block of chaos: tight
-    last = {n: v for n, v in d_c.items() if n.startswith(f'{depth - 1}.')}
-    wl = max(last, key=last.get)
-    out.append(dict(name=name + '.last_block_param_grads_1mcos', ok=last[wl] <= 5e-3, err=last[wl], tol=5e-3, worst_param=wl))
+    out += deep_stage_teacher_forced(gs, kw, w_act, depth, x, dz)
     return out
+
+
+def deep_stage_teacher_forced(gs, kw, w_act, depth, x, dz):
+    """TIGHT full-depth check without the chaos: the storage-emulating fp64 oracle runs the whole stage once; then EVERY
+    one of its `depth` blocks is run alone on the CUDA path with the oracle's own (bf16-stored) input activation and
+    output gradient of that block.  Each block's forward, input gradient and parameter gradients must match at the
+    single-block tolerances of stage_checks (fwd rel-L2 2 * 2^-8, 1 - cos(dx) <= 2e-3, 1 - cos(param grad) <= 5e-3) --
+    so depth indexing, per-block dilation / downsample wiring and every block's weights are pinned at full depth."""
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    ol = O.DynamicResLayer(block=O.DynamicBottleneck, **kw)
+    C.randomize(ol, 9)
+    sd = {k_: v.clone() for k_, v in ol.state_dict().items()}
+    ol.manipulate_arch({'width': w_act, 'depth': depth})
+    ol.train()
+    C.emulate_bf16_storage(ol)
+    ol = ol.double()
+    xin, zout, gin, gout = {}, {}, {}, {}
+
+    def mk(b):
+        def hook(mod, inp, outp):
+            xin[b], zout[b] = inp[0], outp
+            outp.register_hook(lambda g_, b=b: gout.__setitem__(b, g_.detach().clone()))
+            if inp[0].requires_grad:
+                inp[0].register_hook(lambda g_, b=b: gin.__setitem__(b, g_.detach().clone()))
+        return hook
+
+    for b in range(depth):
+        ol[b].register_forward_hook(mk(b))       # registered AFTER the storage-rounding hooks: sees the stored values
+    xo = x.clone().double().requires_grad_(True)
+    zo = ol(xo)
+    zo.backward(dz.double())
+    g_or = {n: p.grad.detach() for n, p in ol.named_parameters() if p.grad is not None}
+    gl = gs.DynamicResLayer(block=gs.DynamicBottleneck, **kw)
+    gl.load_state_dict(sd)
+    gl = gl.to(dev)
+    gl.manipulate_arch({'width': w_act, 'depth': depth})
+    gl.train()
+    worst = dict(fwd=(0.0, -1), dx=(0.0, -1), dp=(0.0, ''))
+    for b in range(depth):
+        xb = Fg.as_act(xin[b].detach().float().to(dev)).requires_grad_(True)
+        zb = gl[b](xb)
+        zb.backward(Fg.as_act(gout[b].float().to(dev)))
+        torch.cuda.synchronize()
+        ref = zout[b].detach()
+        e = float((zb.float().double().cpu() - ref).norm() / (ref.norm() + 1e-300))
+        worst['fwd'] = max(worst['fwd'], (e, b))
+        d = C._grad_cos({'x': xb.grad.float().cpu()}, {'x': gin[b]})['x'] if b in gin else 0.0
+        worst['dx'] = max(worst['dx'], (d, b))
+        gq = {f'{b}.{n}': p.grad.detach().cpu() for n, p in gl[b].named_parameters() if p.grad is not None}
+        dc = C._grad_cos(gq, {n: v for n, v in g_or.items() if n.startswith(f'{b}.')})
+        for n, v in dc.items():
+            worst['dp'] = max(worst['dp'], (v, n))
+    name = f'deep_stage_teacher_forced[{depth} blocks]'
+    return [dict(name=name + '.every_block_fwd_rel_l2', ok=worst['fwd'][0] <= 2 * C.BF16_EPS, err=worst['fwd'][0],
+                 tol=2 * C.BF16_EPS, worst_block=worst['fwd'][1]),
+            dict(name=name + '.every_block_dx_1mcos', ok=worst['dx'][0] <= 2e-3, err=worst['dx'][0], tol=2e-3,
+                 worst_block=worst['dx'][1]),
+            dict(name=name + '.every_block_param_grads_1mcos', ok=worst['dp'][0] <= 5e-3, err=worst['dp'][0], tol=5e-3,
+                 worst_param=worst['dp'][1])]
 
 
 # ------------------------------------------------------------------------------------------------
