@@ -32,6 +32,15 @@ class SyncDesc(Structure):
     _fields_ = [('peer_inboxes', c_void_p), ('rank', c_int32), ('world', c_int32), ('seq_dev', c_void_p)]
 
 
+class AugParams(Structure):
+    """struct gs_aug_params (include/gaiaseg_b200.h): every pre-drawn decision of the train pipeline for one sample."""
+    _fields_ = ([(n, c_int32) for n in ('H0', 'W0', 'new_h', 'new_w', 'crop_h', 'crop_w', 'out_h', 'out_w')] +
+                [('box_y', c_int32 * 11), ('box_x', c_int32 * 11), ('flip', c_int32), ('has_brightness', c_int32),
+                 ('brightness', c_float), ('contrast_first', c_int32), ('has_contrast', c_int32), ('contrast', c_float),
+                 ('has_saturation', c_int32), ('saturation', c_float), ('has_hue', c_int32), ('hue', c_int32),
+                 ('mean', c_float * 3), ('inv_std', c_float * 3), ('cat_max_ratio', c_float), ('ignore_index', c_int32)])
+
+
 _P = c_void_p
 _I = c_int32
 _L = c_int64
@@ -90,6 +99,9 @@ PROTOTYPES = {
     'gs_comm_flags_bytes': (_L, []),
     'gs_grad_allreduce': (_I, [_P, _L, _L, _P, _I, _I, _P, _P]),
     'gs_sgd_flat': (_I, [_P, _P, _P, _L, _P, _I, _P, _P]),
+    'gs_aug_workspace_bytes': (_L, []),
+    'gs_aug_choose_crop': (_I, [_P, _P, _P, _P, _P]),
+    'gs_aug_fused': (_I, [_P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

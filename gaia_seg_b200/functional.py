@@ -362,9 +362,11 @@ def conv_dgrad(conv, dy, g, x_shape, add=None):
 # ------------------------------------------------------------------------------------------------
 # batch norm pieces
 # ------------------------------------------------------------------------------------------------
-# GS_BN_FUSED_BWD=0: the round-1 two-kernel BN backward; GS_SYNCBN_FOLD=0: separate gs_syncbn_allreduce launches
-FUSED_BN_BWD = os.environ.get('GS_BN_FUSED_BWD', 'auto')    # 'auto': only with several ranks (measured, profiles/r02_bn_fused.md)
-FOLD_EXCHANGE = os.environ.get('GS_SYNCBN_FOLD', '1') != '0'
+# GS_BN_FUSED_BWD=1: one cooperative kernel for the BN backward (single rank; measured SLOWER than reduce + apply, kept as
+# an experiment); GS_SYNCBN_FOLD=1: block 0 of the forward apply kernel runs the SyncBN exchange itself instead of a separate
+# gs_syncbn_allreduce launch (parity-green at N = 2, no measurable gain there: 59.4 vs 59.1 ms per cycle)
+FUSED_BN_BWD = os.environ.get('GS_BN_FUSED_BWD', '0')    # measured slower than reduce + apply at N = 1 (profiles/r02_experiments.md); single rank only
+FOLD_EXCHANGE = os.environ.get('GS_SYNCBN_FOLD', '0') != '0'
 
 
 def bn_batch_mode(bn):
@@ -613,8 +615,7 @@ def bn_backward(bn, dz, y, aff, count, zmask, relu, want_dres):
     sums = zeros_f64(2 * C + 2, dev)[:2 * C]
     dy = new_act(N, C, H, W, dev)
     dres = new_act(N, C, H, W, dev) if want_dres else None
-    fused = FUSED_BN_BWD == '1' or (FUSED_BN_BWD == 'auto' and world > 1)
-    if fused and (world == 1 or (ex and FOLD_EXCHANGE)):
+    if FUSED_BN_BWD == '1' and world == 1:
         # ONE cooperative launch: reduce -> grid barrier -> (peer exchange by block 0, parameter gradients from the local
         # sums) -> apply; the second pass over dz / y comes from L2
         call('gs_bn_bwd', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),

@@ -259,6 +259,39 @@ int gs_upsample_argmax(const float* logits, int32_t N, int32_t h, int32_t w, int
 int gs_upsample_bilinear_f32(const float* src, int32_t N, int32_t h, int32_t w, int32_t K, int32_t ld, float* dst,
                              int32_t H, int32_t W, int32_t dst_ld, void* stream);
 
+/* ---- training data pipeline ----------------------------------------------------------- */
+/* replaces the mmseg train pipeline of configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:60-75 ([EXT] mmseg
+ * transforms over mmcv / OpenCV, run by DataLoader workers): Resize(ratio 0.5-2.0, keep_ratio) -> RandomCrop(cat_max_ratio)
+ * -> RandomFlip -> PhotoMetricDistortion -> Normalize(to_rgb) -> Pad(0 / 255) -> DefaultFormatBundle, for ONE sample.
+ * Inputs: the decoded uint8 BGR image [H0][W0][3] and uint8 label map [H0][W0] in device memory.  All random decisions
+ * are made by the caller (host, counter-based stream) and passed in gs_aug_params; the data-dependent choice among the
+ * GS_AUG_CANDIDATES pre-drawn crop boxes is made on the device (gs_aug_choose_crop -> chosen_dev) -- no host round trip.
+ * 8-bit arithmetic is OpenCV's (fixed-point INTER_LINEAR, INTER_NEAREST labels, integer BGR->HSV, fp32 HSV->BGR). */
+#define GS_AUG_CANDIDATES 11
+typedef struct gs_aug_params {
+    int32_t H0, W0;            /* decoded image size */
+    int32_t new_h, new_w;      /* size after Resize */
+    int32_t crop_h, crop_w;    /* min(crop_size, resized size) */
+    int32_t out_h, out_w;      /* Pad size == crop_size of the config (512 x 1024) */
+    int32_t box_y[GS_AUG_CANDIDATES], box_x[GS_AUG_CANDIDATES];   /* RandomCrop candidates, top-left in the resized image */
+    int32_t flip;              /* RandomFlip (horizontal) */
+    int32_t has_brightness; float brightness;       /* PhotoMetricDistortion, in application order */
+    int32_t contrast_first, has_contrast; float contrast;
+    int32_t has_saturation; float saturation;
+    int32_t has_hue, hue;
+    float mean[3], inv_std[3]; /* RGB order; inv_std = 1 / std in fp32 (mmcv.imnormalize multiplies) */
+    float cat_max_ratio; int32_t ignore_index;
+} gs_aug_params;
+
+int64_t gs_aug_workspace_bytes(void);
+/* class histograms of the candidate crops on the nearest-resized label map + the re-draw rule of RandomCrop:
+ * *chosen_dev = first candidate t < 10 with > 1 class and max / sum < cat_max_ratio over non-ignored pixels, else 10. */
+int gs_aug_choose_crop(const uint8_t* seg, const gs_aug_params* params, void* workspace, int32_t* chosen_dev, void* stream);
+/* the fused per-output-pixel pipeline: out_img fp32 [3][out_h][out_w] (RGB, normalised, 0-padded), out_labels int64
+ * [out_h][out_w] (255-padded). */
+int gs_aug_fused(const uint8_t* img_bgr, const uint8_t* seg, const gs_aug_params* params, const int32_t* chosen_dev,
+                 float* out_img, int64_t* out_labels, void* stream);
+
 /* ---- SyncBN statistic exchange over NVLink peer memory ------------------------------------------- */
 /* replaces the per-layer NCCL collectives of [EXT] torch.nn.SyncBatchNorm under gaiavision DynSyncBN
  * (configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:20-23).  Every rank allocates an IPC-shareable inbox of
