@@ -71,6 +71,15 @@ struct IgemmParams {
     int in_mul, base, step;  // input coord of tap t for output o:  o*in_mul + base + t*step
     int b_box_rows;       // rows of the weight box (<= 256)            (K-major B, forward)
     int b_mn;             // 1: B is MN-major (dgrad reads W[co][r][s][ci] in place: K = co rows, N = ci contiguous)
+    // n-tile geometry.  Normal: nt_w = 256, two accumulator buffers of 256 TMEM columns (the epilogue of tile i overlaps the
+    // main loop of tile i+1).  WIDE (CTA pairs, long K loops, Cout a multiple of 320 / 384): nt_w = 320 or 384 in ONE
+    // 384-column accumulator -- Cout = 320 is one balanced tile instead of 256 + 64 (the 64-column units cost the same
+    // per K chunk: the main loop is bound by operand delivery, not by the MMA), the A tile is read once instead of twice.
+    // Two MMAs per K step (N = 256, then N = nt_w - 256); each CTA of the pair stages 128 + h2 weight rows.
+    int nt_w, wide, h2;
+    int even;             // wide + K-major B: two MMAs of N = nt_w / 2 each (CTA r stages rows [hp r, hp r + hp) and
+                          // [2 hp + hp r, ...), hp = nt_w / 4) instead of N = 256 followed by a small N = nt_w - 256 one
+    int stages, stage_bytes;
     // epilogue
     int direct;           // 1: per-thread global stores (fp32 out or unaligned), 0: TMA store
     int out_f32;
@@ -85,17 +94,19 @@ struct IgemmParams {
     double* stats;
 };
 
-template <int CG>
+template <int CG, bool WIDE>
 __global__ void __launch_bounds__(kIgThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
              const __grid_constant__ IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr int kIgStages = IgCfg<CG>::kStages;
-    constexpr int kIgStageBytes = IgCfg<CG>::kStageBytes;
+    constexpr int kIgStages = IgCfg<CG>::kStages;           // compile-time MAXIMUM (barrier arrays, shared-memory carve-up)
+    // ring geometry: the pair ring's 5 x 32 KB, or (wide tiles) 4 x 40 KB -- compile-time, like everything `WIDE` selects
+    constexpr int n_stages = WIDE ? 4 : kIgStages;
+    constexpr int stage_bytes = WIDE ? (kIgABytes + 24 * 1024) : IgCfg<CG>::kStageBytes;
     uint8_t* stage_base = smem;
-    uint8_t* staging = smem + kIgStages * kIgStageBytes;
+    uint8_t* staging = smem + kIgStages * IgCfg<CG>::kStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kIgStagingBytes);
     uint64_t* full_bar = bars;                  // [kIgStages]
     uint64_t* empty_bar = bars + kIgStages;     // [kIgStages]
@@ -148,6 +159,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int nt = unit % p.n_tiles;
     const int mu0 = unit / p.n_tiles;
     const int tiles_hw = p.tiles_h * p.tiles_w;
+    constexpr bool wide = WIDE;
     if (threadIdx.x == 0) trace(1);
 
     if (warp == 0) {
@@ -164,15 +176,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const int rem = mt - img * tiles_hw;
                 const int h0 = (rem / p.tiles_w) * p.TH;
                 const int w0 = (rem % p.tiles_w) * p.TW;
-                const int n0 = nt * 256;
+                const int n0 = nt * p.nt_w;
                 int n_valid = p.Cout - n0;
-                if (n_valid > 256) n_valid = 256;
+                if (n_valid > p.nt_w) n_valid = p.nt_w;
                 // this CTA's share of the weight tile: all of it, or (pair) n_half channels from n0 + rank * n_half
                 const int n_half = ((n_valid + 15) & ~15) / CG;
                 const int nb0 = n0 + rank * (CG == 2 ? n_half : 0);
                 const int b_boxes = ((CG == 2 ? n_half : n_valid) + 63) >> 6;   // MN-major B: [64 k-rows][64 n] boxes
                 // (pair: the leader's barrier counts the bytes of BOTH CTAs; their shares have the same size)
-                const uint32_t tx_bytes = CG * (kIgABytes + (p.b_mn ? b_boxes * 8192 : p.b_box_rows * 128));
+                uint32_t tx_bytes = CG * (kIgABytes + (p.b_mn ? b_boxes * 8192 : p.b_box_rows * 128));
+                // wide tile: accumulator column j <-> channel n0 + j needs CTA r to stage rows [128 r, 128 r + 128) for the
+                // N = 256 MMA and rows [256 + h2 r, 256 + h2 r + h2) for the second one
+                if (wide) tx_bytes = CG * (kIgABytes + (p.b_mn ? 3 * 8192 : (128 + p.h2) * 128));   // (even split: 2 hp = 128 + h2)
                 for (int r = 0; r < p.taps_h; ++r) {
                     const int ih = h0 * p.in_mul + p.base + r * p.step;
                     for (int s = 0; s < p.taps_w; ++s) {
@@ -180,7 +195,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             if (tr_i < 64) trace(16 + tr_i++);
-                            uint8_t* a_dst = stage_base + stage * kIgStageBytes;
+                            uint8_t* a_dst = stage_base + stage * stage_bytes;
                             uint8_t* b_dst = a_dst + kIgABytes;
                             if (CG == 1) {
                                 mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -194,7 +209,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             } else {
                                 if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                                 tma_load_4d_pair(a_dst, &tmA, &full_bar[stage], kc * 64, iw, ih, img);
-                                if (p.b_mn) {
+                                if (wide) {
+                                    const int c1 = n0 + rank * 128, c2 = n0 + 256 + rank * p.h2;
+                                    if (p.b_mn) {
+                                        tma_load_4d_pair(b_dst, &tmB, &full_bar[stage], c1, s, r, kc * 64);
+                                        tma_load_4d_pair(b_dst + 8192, &tmB, &full_bar[stage], c1 + 64, s, r, kc * 64);
+                                        tma_load_4d_pair(b_dst + 16384, &tmB, &full_bar[stage], c2, s, r, kc * 64);
+                                    } else if (p.even) {   // two boxes of hp = nt_w / 4 rows (b_box_rows == hp)
+                                        const int hp = p.nt_w >> 2;
+                                        tma_load_4d_pair(b_dst, &tmB, &full_bar[stage], kc * 64, s, r, n0 + rank * hp);
+                                        tma_load_4d_pair(b_dst + hp * 128, &tmB, &full_bar[stage], kc * 64, s, r,
+                                                         n0 + 2 * hp + rank * hp);
+                                    } else {      // weight boxes of 32 rows (b_box_rows == 32)
+                                        for (int j = 0; j < 4; ++j)
+                                            tma_load_4d_pair(b_dst + j * 4096, &tmB, &full_bar[stage], kc * 64, s, r, c1 + 32 * j);
+                                        for (int j = 0; j < (p.h2 >> 5); ++j)
+                                            tma_load_4d_pair(b_dst + (4 + j) * 4096, &tmB, &full_bar[stage], kc * 64, s, r,
+                                                             c2 + 32 * j);
+                                    }
+                                } else if (p.b_mn) {
                                     for (int j = 0; j < b_boxes; ++j)
                                         tma_load_4d_pair(b_dst + j * 8192, &tmB, &full_bar[stage], nb0 + j * 64, s, r,
                                                          kc * 64);
@@ -202,7 +235,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                     tma_load_4d_pair(b_dst, &tmB, &full_bar[stage], kc * 64, s, r, nb0);
                                 }
                             }
-                            if (++stage == kIgStages) { stage = 0; phase ^= 1; }
+                            if (++stage == n_stages) { stage = 0; phase ^= 1; }
                         }
                     }
                 }
@@ -218,10 +251,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             int tr_i = 0;
             const int iters = p.taps_h * p.taps_w * p.kchunks;
             for (int mu = mu0; mu < m_units; mu += groups) {
-                int n_valid = p.Cout - nt * 256;
-                if (n_valid > 256) n_valid = 256;
-                const uint32_t umma_n = (n_valid + 15) & ~15;
+                int n_valid = p.Cout - nt * p.nt_w;
+                if (n_valid > p.nt_w) n_valid = p.nt_w;
+                const bool even = wide && p.even != 0;
+                const uint32_t n1 = even ? static_cast<uint32_t>(p.nt_w >> 1) : 256u;          // columns of the first MMA
+                const uint32_t umma_n = wide ? n1 : static_cast<uint32_t>((n_valid + 15) & ~15);
                 const uint32_t idesc = make_idesc_bf16(128 * CG, umma_n, false, p.b_mn != 0);
+                const uint32_t idesc2 = make_idesc_bf16(128 * CG, even ? n1 : static_cast<uint32_t>(2 * p.h2), false, p.b_mn != 0);
+                const uint32_t b2_off = even ? static_cast<uint32_t>((p.nt_w >> 2) * 128) : 128u * 128u;   // K-major part 2
                 if (CG == 2) mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
                 else mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after_sync();
@@ -232,7 +269,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after_sync();
                     if (tr_i < 64) trace(80 + tr_i++);
-                    const uint32_t a_addr = smem_u32(stage_base + stage * kIgStageBytes);
+                    const uint32_t a_addr = smem_u32(stage_base + stage * stage_bytes);
                     const uint32_t b_addr = a_addr + kIgABytes;
                     int krem = p.Kc - kc * 64;
                     const int ksteps = krem >= 64 ? 4 : (krem + 15) >> 4;
@@ -243,27 +280,35 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                                       : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
                         if (CG == 2) umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, accumulate);
                         else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+                        if (wide) {   // second part of the wide tile: accumulator columns [256, 256 + 2 h2)
+                            const uint64_t bdesc2 = p.b_mn ? make_smem_desc_sw128(b_addr + 16384 + k * 2048, 8192, 1024)
+                                                           : make_smem_desc_sw128(b_addr + b2_off + k * 32, 16, 1024);
+                            umma_bf16_ss_pair(d_tmem + n1, adesc, bdesc2, idesc2, accumulate);
+                        }
                         accumulate = 1;
                     }
                     // frees the smem slot (of both CTAs) once these MMAs retire
                     if (CG == 2) umma_commit_pair(&empty_bar[stage]);
                     else umma_commit(&empty_bar[stage]);
                     if (++kc == p.kchunks) kc = 0;
-                    if (++stage == kIgStages) { stage = 0; phase ^= 1; }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
                 if (CG == 2) umma_commit_pair(&tfull_bar[acc]);
                 else umma_commit(&tfull_bar[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                if (wide) acc_phase ^= 1;           // ONE accumulator (up to 384 columns): the same buffer every tile
+                else {
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
             }
         }
     } else {
         // =========================== epilogue (warps 2..17) ===========================
-        // 16 warps = 4 sub-tile groups x 4 TMEM sub-partitions: group `sub` owns accumulator columns [64 sub, 64 sub + 64)
-        // (one TMA-store box), warp quarter q its 32 rows.  All four sub-tiles of a tile drain CONCURRENTLY -- the
-        // per-tile epilogue is instruction-issue bound, so it is spread over all four schedulers (4 warps each) --
-        // each group through its own 16 KB staging slot, named barrier and TMA-store thread:
-        //   TMEM -> registers -> affine / residual / ReLU -> bf16 -> swizzled staging -> TMA store.
+        // 16 warps = 4 sub-tile groups x 4 TMEM sub-partitions: group `sub` owns the 64-column sub-tiles sub, sub + 4 (the
+        // second only exists in a wide tile of 320 / 384 columns) -- one TMA-store box each -- warp quarter q its 32 rows.
+        // The sub-tiles of a round drain CONCURRENTLY -- the per-tile epilogue is instruction-issue bound, so it is spread
+        // over all four schedulers (4 warps each) -- each group through its own 16 KB staging slot, named barrier and
+        // TMA-store thread:   TMEM -> registers -> affine / residual / ReLU -> bf16 -> swizzled staging -> TMA store.
         // DynBN statistics: every lane re-reads the 32 rows its own warp just staged (column pair = lane,
         // conflict-free) and keeps sum / sum^2 in registers across ALL tiles of the CTA; fp64 atomics once at the end.
         const int q = warp & 3;            // TMEM sub-partition of this warp (hardware rule: warp id % 4)
@@ -283,12 +328,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint32_t wr = (slot_u32 + row * 128) ^ (static_cast<uint32_t>(row & 7) << 4);
         const uint32_t st_lane = (static_cast<uint32_t>(lane >> 2) << 4) | (static_cast<uint32_t>(lane & 3) << 2);
         const uint32_t st_base = slot_u32 + q * (32 * 128);
-        uint64_t st_s2 = 0ull, st_q2 = 0ull;   // statistics of this lane's column pair, packed (col, col + 1) fp32x2
-        const int n0 = nt * 256;
+        // statistics of this lane's column pair, packed (col, col + 1) fp32x2, one set per round (sub-tiles sub, sub + 4)
+        uint64_t st_s2a = 0ull, st_q2a = 0ull, st_s2b = 0ull, st_q2b = 0ull;   // (scalars: a dynamically indexed array would live in local memory)
+        const int n0 = nt * p.nt_w;
         int n_valid = p.Cout - n0;
-        if (n_valid > 256) n_valid = 256;
+        if (n_valid > p.nt_w) n_valid = p.nt_w;
+        const int nsub = (n_valid + 63) >> 6;              // 64-column sub-tiles of this n-tile (<= 4, wide: 5 or 6)
         const int nchunks = (n_valid + 31) >> 5;
-        const bool has_cols = sub * 64 < n_valid;          // does this group own any column of the n-tile?
         const bool res_tma = (!p.direct) && (p.residual != nullptr);
         for (int mu = mu0; mu < m_units; mu += groups) {
             const int mt = mu * CG + rank;
@@ -300,213 +346,232 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const bool valid = (img < p.N) && (h < p.Ho) && (w < p.Wo);
             const long long pix = (static_cast<long long>(img) * p.Ho + h) * p.Wo + w;
 
-            if (!p.direct && has_cols) {
-                // the previous tile's store must have finished READING the slot before anybody refills it; with a
-                // residual the refill is the TMA load of the residual tile IN PLACE (it overlaps the MMA main loop of
-                // this tile; the epilogue adds it at the very positions it overwrites)
-                if (g_tid == 0) {
-                    tma_store_wait_read0();
-                    if (res_tma) {
-                        mbar_arrive_expect_tx(&res_bar[sub], 128 * 128);
-                        tma_load_4d(slot, &tmR, &res_bar[sub], n0 + sub * 64, w0, h0, img);
-                    }
-                }
-                if (!res_tma) named_bar_sync(1 + sub, 128);
-            }
-
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after_sync();
-            if (g_tid == 0 && sub == 0 && tr_t < 16) trace(144 + 4 * tr_t);
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + sub * 64;
-
-            if (!has_cols) {
-                // nothing to drain for this group: still hand the accumulator back
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
-            } else if (p.direct) {
 #pragma unroll 1
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = sub * 2 + cc;
-                    if (c >= nchunks) break;
-                    uint32_t raw[32];
-                    tmem_ld_32x32b_x32(t_addr + cc * 32, raw);
-                    tmem_ld_wait();
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                    const int col0 = n0 + c * 32;
-                    if (p.scale != nullptr) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.Cout) v[i] *= __ldg(p.scale + col0 + i);
-                    }
-                    if (p.shift != nullptr) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.Cout) v[i] += __ldg(p.shift + col0 + i);
-                    }
-                    if (p.residual != nullptr && valid) {
-                        const __nv_bfloat16* rp = p.residual + pix * p.res_ld + col0;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (col0 + i < p.Cout) v[i] += __bfloat162float(rp[i]);
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                    }
-                    if (valid) {
-                        if (p.out_f32) {
-                            float* op = reinterpret_cast<float*>(p.out) + pix * p.out_ld + col0;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (col0 + i < p.Cout) op[i] = v[i];
-                        } else {
-                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + col0;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (col0 + i < p.Cout) op[i] = __float2bfloat16_rn(v[i]);
+            for (int rd = 0; rd < (WIDE ? 2 : 1); ++rd) {
+                const int st = sub + 4 * rd;                       // sub-tile of this round
+                if (rd == 1 && st >= nsub) break;                  // (round 0 always runs: it hands the accumulator back)
+                const bool has_cols = st < nsub;                   // does this group own any column in this round?
+                const bool last_round = st + 4 >= nsub;            // the accumulator is released after the last drain
+                if (!p.direct && has_cols) {
+                    // the previous store must have finished READING the slot before anybody refills it; with a
+                    // residual the refill is the TMA load of the residual tile IN PLACE (it overlaps the MMA main loop of
+                    // this tile; the epilogue adds it at the very positions it overwrites)
+                    if (g_tid == 0) {
+                        tma_store_wait_read0();
+                        if (res_tma) {
+                            mbar_arrive_expect_tx(&res_bar[sub], 128 * 128);
+                            tma_load_4d(slot, &tmR, &res_bar[sub], n0 + st * 64, w0, h0, img);
                         }
                     }
+                    if (!res_tma) named_bar_sync(1 + sub, 128);
                 }
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
-            } else {
-                // the sub-tile drains in four 16-column groups through two alternating register sets: the TMEM load of
-                // group g+1 is in flight while group g is converted and staged (18 warps leave 96 registers per thread)
-                uint32_t ra[16], rb[16];
-                const int ngrp = min(4, (n_valid - sub * 64 + 15) >> 4);   // 16-column groups with active columns
-                tmem_ld_32x32b_x16(t_addr, ra);
-                if (res_tma) mbar_wait(&res_bar[sub], res_phase);
-                tmem_ld_wait();
-                auto stage_group = [&](const uint32_t (&raw)[16], int g) {
-                    float v[16];
+
+                if (rd == 0) {
+                    mbar_wait(&tfull_bar[acc], acc_phase);
+                    tc_fence_after_sync();
+                    if (g_tid == 0 && sub == 0 && tr_t < 16) trace(144 + 4 * tr_t);
+                }
+                const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + st * 64;
+
+                if (!has_cols) {
+                    // nothing to drain for this group: still hand the accumulator back
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
+                } else if (p.direct) {
+#pragma unroll 1
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int c = st * 2 + cc;
+                        if (c >= nchunks) break;
+                        uint32_t raw[32];
+                        tmem_ld_32x32b_x32(t_addr + cc * 32, raw);
+                        tmem_ld_wait();
+                        float v[32];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
-                    const int col0 = n0 + sub * 64 + g * 16;
-                    if (p.scale != nullptr || p.shift != nullptr) {
-                        if (col0 + 16 <= p.Cout) {       // whole group inside the active width: vector loads
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                        const int col0 = n0 + c * 32;
+                        if (p.scale != nullptr) {
 #pragma unroll
-                            for (int g4 = 0; g4 < 4; ++g4) {
-                                if (p.scale != nullptr) {
-                                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + g4);
-                                    v[g4 * 4 + 0] *= s4.x; v[g4 * 4 + 1] *= s4.y;
-                                    v[g4 * 4 + 2] *= s4.z; v[g4 * 4 + 3] *= s4.w;
-                                }
-                                if (p.shift != nullptr) {
-                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.shift + col0) + g4);
-                                    v[g4 * 4 + 0] += b4.x; v[g4 * 4 + 1] += b4.y;
-                                    v[g4 * 4 + 2] += b4.z; v[g4 * 4 + 3] += b4.w;
-                                }
+                            for (int i = 0; i < 32; ++i)
+                                if (col0 + i < p.Cout) v[i] *= __ldg(p.scale + col0 + i);
+                        }
+                        if (p.shift != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (col0 + i < p.Cout) v[i] += __ldg(p.shift + col0 + i);
+                        }
+                        if (p.residual != nullptr && valid) {
+                            const __nv_bfloat16* rp = p.residual + pix * p.res_ld + col0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (col0 + i < p.Cout) v[i] += __bfloat162float(rp[i]);
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        if (valid) {
+                            if (p.out_f32) {
+                                float* op = reinterpret_cast<float*>(p.out) + pix * p.out_ld + col0;
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    if (col0 + i < p.Cout) op[i] = v[i];
+                            } else {
+                                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + col0;
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    if (col0 + i < p.Cout) op[i] = __float2bfloat16_rn(v[i]);
                             }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (col0 + i < p.Cout) {
-                                    if (p.scale != nullptr) v[i] *= __ldg(p.scale + col0 + i);
-                                    if (p.shift != nullptr) v[i] += __ldg(p.shift + col0 + i);
-                                }
                         }
                     }
-                    if (res_tma) {
+                    if (last_round) {
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
+                    }
+                } else {
+                    // the sub-tile drains in four 16-column groups through two alternating register sets: the TMEM load of
+                    // group g+1 is in flight while group g is converted and staged (18 warps leave 96 registers per thread)
+                    uint32_t ra[16], rb[16];
+                    const int ngrp = min(4, (n_valid - st * 64 + 15) >> 4);   // 16-column groups with active columns
+                    tmem_ld_32x32b_x16(t_addr, ra);
+                    if (res_tma) mbar_wait(&res_bar[sub], res_phase);
+                    tmem_ld_wait();
+                    auto stage_group = [&](const uint32_t (&raw)[16], int g) {
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+                        const int col0 = n0 + st * 64 + g * 16;
+                        if (p.scale != nullptr || p.shift != nullptr) {
+                            if (col0 + 16 <= p.Cout) {       // whole group inside the active width: vector loads
+#pragma unroll
+                                for (int g4 = 0; g4 < 4; ++g4) {
+                                    if (p.scale != nullptr) {
+                                        const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + g4);
+                                        v[g4 * 4 + 0] *= s4.x; v[g4 * 4 + 1] *= s4.y;
+                                        v[g4 * 4 + 2] *= s4.z; v[g4 * 4 + 3] *= s4.w;
+                                    }
+                                    if (p.shift != nullptr) {
+                                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.shift + col0) + g4);
+                                        v[g4 * 4 + 0] += b4.x; v[g4 * 4 + 1] += b4.y;
+                                        v[g4 * 4 + 2] += b4.z; v[g4 * 4 + 3] += b4.w;
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (col0 + i < p.Cout) {
+                                        if (p.scale != nullptr) v[i] *= __ldg(p.scale + col0 + i);
+                                        if (p.shift != nullptr) v[i] += __ldg(p.shift + col0 + i);
+                                    }
+                            }
+                        }
+                        if (res_tma) {
+#pragma unroll
+                            for (int g8 = 0; g8 < 2; ++g8) {
+                                const uint4 u = lds128(wr ^ ((g * 2 + g8) << 4));
+                                v[g8 * 8 + 0] += bf16_lo(u.x); v[g8 * 8 + 1] += bf16_hi(u.x);
+                                v[g8 * 8 + 2] += bf16_lo(u.y); v[g8 * 8 + 3] += bf16_hi(u.y);
+                                v[g8 * 8 + 4] += bf16_lo(u.z); v[g8 * 8 + 5] += bf16_hi(u.z);
+                                v[g8 * 8 + 6] += bf16_lo(u.w); v[g8 * 8 + 7] += bf16_hi(u.w);
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        if (!valid) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = 0.f;  // keeps OOB pixels out of the statistics
+                        }
 #pragma unroll
                         for (int g8 = 0; g8 < 2; ++g8) {
-                            const uint4 u = lds128(wr ^ ((g * 2 + g8) << 4));
-                            v[g8 * 8 + 0] += bf16_lo(u.x); v[g8 * 8 + 1] += bf16_hi(u.x);
-                            v[g8 * 8 + 2] += bf16_lo(u.y); v[g8 * 8 + 3] += bf16_hi(u.y);
-                            v[g8 * 8 + 4] += bf16_lo(u.z); v[g8 * 8 + 5] += bf16_hi(u.z);
-                            v[g8 * 8 + 6] += bf16_lo(u.w); v[g8 * 8 + 7] += bf16_hi(u.w);
+                            uint4 u;
+                            u.x = pack_bf16x2(v[g8 * 8 + 0], v[g8 * 8 + 1]);
+                            u.y = pack_bf16x2(v[g8 * 8 + 2], v[g8 * 8 + 3]);
+                            u.z = pack_bf16x2(v[g8 * 8 + 4], v[g8 * 8 + 5]);
+                            u.w = pack_bf16x2(v[g8 * 8 + 6], v[g8 * 8 + 7]);
+                            sts128(wr ^ ((g * 2 + g8) << 4), u);
+                        }
+                    };
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (g < ngrp) {
+                            if (g + 1 < ngrp) {
+                                if (g & 1) tmem_ld_32x32b_x16(t_addr + (g + 1) * 16, ra);
+                                else tmem_ld_32x32b_x16(t_addr + (g + 1) * 16, rb);
+                            }
+                            if (g & 1) stage_group(rb, g);
+                            else stage_group(ra, g);
+                            if (g + 1 < ngrp) tmem_ld_wait();
+                            if (last_round && g == (ngrp > 1 ? ngrp - 2 : 0)) {
+                                // the last group of this warp's accumulator share is in registers -> hand the buffer back
+                                tc_fence_before_sync();
+                                __syncwarp();
+                                if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
+                                if (g_tid == 0 && sub == 0 && tr_t < 16) trace(145 + 4 * tr_t);
+                            }
                         }
                     }
-                    if (p.relu) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                    // make the staged rows visible to the TMA engine, then one thread of the group stores the box while
+                    // every warp accumulates the statistics of the rows it staged
+                    fence_proxy_async_smem();
+                    named_bar_sync(1 + sub, 128);
+                    if (g_tid == 0) {
+                        tma_store_4d(&tmC, slot, n0 + st * 64, w0, h0, img);
+                        tma_store_commit();
+                        if (sub == 0 && tr_t < 16) trace(146 + 4 * tr_t);
                     }
-                    if (!valid) {
+                    if (p.stats != nullptr && st * 64 + lane * 2 < n_valid) {
+                        // lane owns columns (2*lane, 2*lane+1) of the sub-tile over the 32 rows its warp staged: 32
+                        // conflict-free LDS.32 (row r: chunk (lane>>2) ^ (r & 7), word lane & 3) -> packed fp32x2
+                        // accumulation (FADD2 / FFMA2) of both columns at once
+                        uint64_t s2 = rd == 0 ? st_s2a : st_s2b, q2 = rd == 0 ? st_q2a : st_q2b;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = 0.f;  // keeps OOB pixels out of the statistics
-                    }
-#pragma unroll
-                    for (int g8 = 0; g8 < 2; ++g8) {
-                        uint4 u;
-                        u.x = pack_bf16x2(v[g8 * 8 + 0], v[g8 * 8 + 1]);
-                        u.y = pack_bf16x2(v[g8 * 8 + 2], v[g8 * 8 + 3]);
-                        u.z = pack_bf16x2(v[g8 * 8 + 4], v[g8 * 8 + 5]);
-                        u.w = pack_bf16x2(v[g8 * 8 + 6], v[g8 * 8 + 7]);
-                        sts128(wr ^ ((g * 2 + g8) << 4), u);
-                    }
-                };
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    if (g < ngrp) {
-                        if (g + 1 < ngrp) {
-                            if (g & 1) tmem_ld_32x32b_x16(t_addr + (g + 1) * 16, ra);
-                            else tmem_ld_32x32b_x16(t_addr + (g + 1) * 16, rb);
+                        for (int r = 0; r < 32; ++r) {
+                            const uint32_t wv = lds32(st_base + r * 128 + (st_lane ^ ((r & 7) << 4)));
+                            const uint64_t pv = pack_f32x2(bf16_lo(wv), bf16_hi(wv));
+                            s2 = add_f32x2(s2, pv);
+                            q2 = fma_f32x2(pv, pv, q2);
                         }
-                        if (g & 1) stage_group(rb, g);
-                        else stage_group(ra, g);
-                        if (g + 1 < ngrp) tmem_ld_wait();
-                        if (g == (ngrp > 1 ? ngrp - 2 : 0)) {
-                            // the last group of this warp's accumulator share is in registers -> hand the buffer back
-                            tc_fence_before_sync();
-                            __syncwarp();
-                            if (lane == 0) ig_release_acc<CG>(&tempty_bar[acc]);
-                            if (g_tid == 0 && sub == 0 && tr_t < 16) trace(145 + 4 * tr_t);
-                        }
+                        if (rd == 0) { st_s2a = s2; st_q2a = q2; } else { st_s2b = s2; st_q2b = q2; }
                     }
+                    if (res_tma) res_phase ^= 1;
                 }
-                // make the staged rows visible to the TMA engine, then one thread of the group stores the box while
-                // every warp accumulates the statistics of the rows it staged
-                fence_proxy_async_smem();
-                named_bar_sync(1 + sub, 128);
-                if (g_tid == 0) {
-                    tma_store_4d(&tmC, slot, n0 + sub * 64, w0, h0, img);
-                    tma_store_commit();
-                    if (sub == 0 && tr_t < 16) trace(146 + 4 * tr_t);
-                }
-                if (p.stats != nullptr && sub * 64 + lane * 2 < n_valid) {
-                    // lane owns columns (2*lane, 2*lane+1) of the sub-tile over the 32 rows its warp staged: 32
-                    // conflict-free LDS.32 (row r: chunk (lane>>2) ^ (r & 7), word lane & 3) -> packed fp32x2
-                    // accumulation (FADD2 / FFMA2) of both columns at once
-                    uint64_t s2 = st_s2, q2 = st_q2;
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) {
-                        const uint32_t wv = lds32(st_base + r * 128 + (st_lane ^ ((r & 7) << 4)));
-                        const uint64_t pv = pack_f32x2(bf16_lo(wv), bf16_hi(wv));
-                        s2 = add_f32x2(s2, pv);
-                        q2 = fma_f32x2(pv, pv, q2);
-                    }
-                    st_s2 = s2; st_q2 = q2;
-                }
-                if (res_tma) res_phase ^= 1;
             }
             if (g_tid == 0 && sub == 0 && tr_t < 16) trace(147 + 4 * tr_t);
             ++tr_t;
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            if (wide) acc_phase ^= 1;
+            else {
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
         }
         if (!p.direct && g_tid == 0) tma_store_wait_all0();
         if (p.stats != nullptr) {
-            // one flush per kernel: the 4 row-quarters are summed through the now idle staging buffer, then one column
-            // per thread goes out with two fp64 atomics
+            // one flush per kernel: the 4 row-quarters are summed through the now idle staging buffer, then every column
+            // goes out with two fp64 atomics.  red: [4 quarters][1024]: sums at 0..511, squares at 512..1023
             named_bar_sync(5, 512);
-            float* red = reinterpret_cast<float*>(staging);        // [4 quarters][512]: sums 0..255, squares 256..511
-            red[q * 512 + sub * 64 + lane * 2] = f32x2_lo(st_s2);
-            red[q * 512 + sub * 64 + lane * 2 + 1] = f32x2_hi(st_s2);
-            red[q * 512 + 256 + sub * 64 + lane * 2] = f32x2_lo(st_q2);
-            red[q * 512 + 256 + sub * 64 + lane * 2 + 1] = f32x2_hi(st_q2);
+            float* red = reinterpret_cast<float*>(staging);
+            {
+                const int c = sub * 64 + lane * 2;
+                red[q * 1024 + c] = f32x2_lo(st_s2a);
+                red[q * 1024 + c + 1] = f32x2_hi(st_s2a);
+                red[q * 1024 + 512 + c] = f32x2_lo(st_q2a);
+                red[q * 1024 + 512 + c + 1] = f32x2_hi(st_q2a);
+                const int c2 = c + 256;                                  // round 1: sub-tile sub + 4
+                red[q * 1024 + c2] = f32x2_lo(st_s2b);
+                red[q * 1024 + c2 + 1] = f32x2_hi(st_s2b);
+                red[q * 1024 + 512 + c2] = f32x2_lo(st_q2b);
+                red[q * 1024 + 512 + c2 + 1] = f32x2_hi(st_q2b);
+            }
             named_bar_sync(5, 512);
-            const int c = threadIdx.x - 64;
-            if (c < 256) {
+            for (int c = threadIdx.x - 64; c < n_valid; c += 512) {
                 const int col = n0 + c;
-                if (col < p.Cout) {
-                    const float su = red[c] + red[512 + c] + red[1024 + c] + red[1536 + c];
-                    const float sq = red[256 + c] + red[768 + c] + red[1280 + c] + red[1792 + c];
-                    atomicAdd(p.stats + col, static_cast<double>(su));
-                    atomicAdd(p.stats + p.Cout + col, static_cast<double>(sq));
-                }
+                const float su = red[c] + red[1024 + c] + red[2048 + c] + red[3072 + c];
+                const float sq = red[512 + c] + red[1536 + c] + red[2560 + c] + red[3584 + c];
+                atomicAdd(p.stats + col, static_cast<double>(su));
+                atomicAdd(p.stats + p.Cout + col, static_cast<double>(sq));
             }
         }
     }
@@ -554,7 +619,6 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     p.tiles_h = (int)gs_ceil_div(L.Ho, p.TH);
     p.tiles_w = (int)gs_ceil_div(L.Wo, p.TW);
     p.m_tiles = L.N * p.tiles_h * p.tiles_w;
-    p.n_tiles = (int)gs_ceil_div(L.Cout, 256);
     p.Cout = L.Cout; p.Kc = L.Kc; p.kchunks = (int)gs_ceil_div(L.Kc, 64);
     p.taps_h = L.kh; p.taps_w = L.kw;
     p.in_mul = L.in_mul; p.base = L.base; p.step = L.step;
@@ -562,8 +626,27 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     // the epilogue, where the lock-step of a pair costs a little); GS_IGEMM_CTA_GROUP=1 forces the single-CTA kernel.
     static const int cg_env = [] { const char* e = getenv("GS_IGEMM_CTA_GROUP"); return e ? atoi(e) : 2; }();
     static const int cg_min_iters = [] { const char* e = getenv("GS_IGEMM_PAIR_MIN_ITERS"); return e ? atoi(e) : 8; }();
-    const int cg = (cg_env == 2 && p.m_tiles >= 2 && L.kh * L.kw * p.kchunks >= cg_min_iters) ? 2 : 1;
-    p.b_box_rows = (L.Cout >= 256 ? 256 : gs_round_up(L.Cout, 16)) / cg;
+    const int iters = L.kh * L.kw * p.kchunks;
+    const int cg = (cg_env == 2 && p.m_tiles >= 2 && iters >= cg_min_iters) ? 2 : 1;
+    const bool tma_store_ok = !L.out_f32 && (L.out_ld % 8 == 0) && (L.Cout % 8 == 0) &&
+                              ((reinterpret_cast<uintptr_t>(L.out) & 15) == 0);
+    // wide n-tiles (one 320 / 384-column accumulator instead of 256 + 64 / 256 + 128): pairs, long K loops (the epilogue
+    // of a single-buffered accumulator does not overlap the next tile's main loop), widths that tile evenly
+    static const int wide_env = [] { const char* e = getenv("GS_IGEMM_WIDE"); return e ? atoi(e) : 1; }();
+    static const int wide_min_iters = [] { const char* e = getenv("GS_IGEMM_WIDE_MIN_ITERS"); return e ? atoi(e) : 16; }();
+    p.nt_w = 256; p.wide = 0; p.h2 = 0;
+    if (wide_env && cg == 2 && iters >= wide_min_iters && tma_store_ok && L.Cout > 256) {
+        if (L.Cout % 320 == 0) p.nt_w = 320;
+        else if (L.Cout % 384 == 0) p.nt_w = 384;
+        if (p.nt_w != 256) { p.wide = 1; p.h2 = (p.nt_w - 256) / 2; }
+    }
+    static const int even_env = [] { const char* e = getenv("GS_IGEMM_WIDE_EVEN"); return e ? atoi(e) : 1; }();
+    p.even = (p.wide && !L.b_mn && even_env) ? 1 : 0;
+    p.n_tiles = (int)gs_ceil_div(L.Cout, p.nt_w);
+    if (cg == 1) { p.stages = IgCfg<1>::kStages; p.stage_bytes = IgCfg<1>::kStageBytes; }
+    else if (!p.wide) { p.stages = IgCfg<2>::kStages; p.stage_bytes = IgCfg<2>::kStageBytes; }
+    else { p.stages = 4; p.stage_bytes = kIgABytes + 24 * 1024; }     // 4 x 40 KB = the pair ring's 5 x 32 KB
+    p.b_box_rows = p.wide ? (p.even ? p.nt_w / 4 : 32) : (L.Cout >= 256 ? 256 : gs_round_up(L.Cout, 16)) / cg;
     p.b_mn = L.b_mn;
     p.out = L.out; p.out_ld = L.out_ld; p.out_f32 = L.out_f32; p.relu = L.relu;
     p.scale = L.scale; p.shift = L.shift;
@@ -571,8 +654,6 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     p.stats = L.stats;
     GS_REQUIRE(L.fuse == nullptr, "dgrad: the fused BN-backward reduction was removed (measured slower than gs_bn_bwd_reduce); "
                                   "pass fuse = NULL");
-    const bool tma_store_ok = !L.out_f32 && (L.out_ld % 8 == 0) && (L.Cout % 8 == 0) &&
-                              ((reinterpret_cast<uintptr_t>(L.out) & 15) == 0);
     p.direct = tma_store_ok ? 0 : 1;
     GS_REQUIRE(!(p.direct && L.stats), "conv: statistics need the bf16 TMA-store epilogue (Co %% 8 == 0)");
     if (L.residual) {
@@ -629,9 +710,11 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     }
     static bool attr_set = false;
     if (!attr_set) {
-        GS_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GS_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         IgCfg<1>::kSmemBytes));
-        GS_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GS_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        IgCfg<2>::kSmemBytes));
+        GS_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         IgCfg<2>::kSmemBytes));
         attr_set = true;
     }
@@ -642,9 +725,14 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     if (groups > m_units) groups = m_units;
     const int grid = groups * p.n_tiles * cg;
     if (cg == 1) {
-        gs::launch<2>(igemm_kernel<1>, dim3(grid), dim3(kIgThreads), IgCfg<1>::kSmemBytes, stream, tmA, tmB, tmC, tmR, p);
+        gs::launch<2>(igemm_kernel<1, false>, dim3(grid), dim3(kIgThreads), IgCfg<1>::kSmemBytes, stream, tmA, tmB, tmC, tmR, p);
     } else {
-        gs::launch_pair<2>(igemm_kernel<2>, dim3(grid), dim3(kIgThreads), IgCfg<2>::kSmemBytes, stream, tmA, tmB, tmC, tmR, p);
+        if (p.wide)
+            gs::launch_pair<2>(igemm_kernel<2, true>, dim3(grid), dim3(kIgThreads), IgCfg<2>::kSmemBytes, stream, tmA, tmB, tmC,
+                               tmR, p);
+        else
+            gs::launch_pair<2>(igemm_kernel<2, false>, dim3(grid), dim3(kIgThreads), IgCfg<2>::kSmemBytes, stream, tmA, tmB, tmC,
+                               tmR, p);
     }
     GS_LAUNCHED();
     return 0;

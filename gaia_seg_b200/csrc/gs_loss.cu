@@ -140,7 +140,7 @@ constexpr int kBwdMaxRegion = 512; // output pixels per tile edge the tap tables
 
 struct BwdSmem {
     // byte offsets into the dynamic shared memory block (all 16-byte aligned)
-    int logits, G, T, acc, xt_i, xt_w, yt_i, yt_w, xr, yr, total;
+    int logits, G, T, acc, rec, xt_i, xt_w, yt_i, yt_w, xr, yr, total;
 };
 
 __host__ __device__ inline BwdSmem bwd_smem_layout(int K, int KC, int XW, int R) {
@@ -152,6 +152,7 @@ __host__ __device__ inline BwdSmem bwd_smem_layout(int K, int KC, int XW, int R)
     L.G = take(R * XW * kcp * 4);
     L.T = take(R * kBwdTile * kcp * 4);
     L.acc = take(kBwdTile * kBwdTile * kcp * 4);
+    L.rec = take(R * XW * 8);          // the strip's per-pixel records, staged with coalesced, independent loads
     L.xt_i = take(XW * 8);
     L.xt_w = take(XW * 8);
     L.yt_i = take(kBwdMaxRegion * 8);
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(kBwdThreads) upsample_ce_bwd_kernel(const floa
     float* sG = reinterpret_cast<float*>(smem_bwd + L.G);
     float* sT = reinterpret_cast<float*>(smem_bwd + L.T);
     float* sA = reinterpret_cast<float*>(smem_bwd + L.acc);
+    PixRec* sR = reinterpret_cast<PixRec*>(smem_bwd + L.rec);
     int2* xti = reinterpret_cast<int2*>(smem_bwd + L.xt_i);
     float2* xtw = reinterpret_cast<float2*>(smem_bwd + L.xt_w);
     int2* yti = reinterpret_cast<int2*>(smem_bwd + L.yt_i);
@@ -247,6 +249,15 @@ __global__ void __launch_bounds__(kBwdThreads) upsample_ce_bwd_kernel(const floa
         for (int i = tid; i < kBwdTile * kBwdTile * kcp; i += kBwdThreads) sA[i] = 0.f;
         for (int yb = 0; yb < YH; yb += R) {
             const int rows = min(R, YH - yb);
+            // ---- phase 0: the strip's records -> shared memory (one independent load per thread: the round-trip to L2 is
+            // paid once per strip instead of once per pixel of every thread's serial loop) ----
+            if (kc == 0 || K > KC) {
+                for (int p = tid; p < rows * XW; p += kBwdThreads) {
+                    const int r = p / XW, xx = p - r * XW;
+                    sR[p] = rec[((long long)n * H + (ylo + yb + r)) * W + (xlo + xx)];
+                }
+                __syncthreads();
+            }
             // ---- phase 1: soft-max gradient terms of the strip, once per pixel (kBwdKSplit lanes share a pixel) ----
             for (int it = tid; it < rows * XW * kBwdKSplit; it += kBwdThreads) {
                 const int q = it & (kBwdKSplit - 1);
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(kBwdThreads) upsample_ce_bwd_kernel(const floa
                 const int r = p / XW, xx = p - r * XW;
                 const int2 yi = yti[yb + r], xi = xti[xx];
                 float* g = sG + (size_t)(r * XW + xx) * kcp;
-                const PixRec pr = rec[((long long)n * H + (ylo + yb + r)) * W + (xlo + xx)];
+                const PixRec pr = sR[p];
                 const bool inside = yi.x >= i0 - 1 && yi.y <= i0 + th && xi.x >= j0 - 1 && xi.y <= j0 + tw;
                 if (pr.label < 0 || !inside) {
                     for (int kk = q; kk < kn; kk += kBwdKSplit) g[kk] = 0.f;

@@ -380,7 +380,38 @@ BIG_CONV_CASES = [
     ('s2_3x3_160_s2',      2, 128, 256, 160, 160, 3, 2, 1, 1, 160, 160),        # stride-2 (zero-inserted dgrad)
     ('s2_ds_1x1_320_640',  2, 128, 256, 320, 640, 1, 2, 0, 1, 320, 640),
     ('stem_3x3_32_64',     2, 256, 512, 32, 64, 3, 1, 1, 1, 32, 64),            # P = 262144
+    # wide n-tiles (one 320 / 384-column accumulator, two MMAs per K step): 384 = stage-4 width 384, prefix slices, ragged
+    ('s4_3x3_384_d4',      2, 64, 128, 384, 384, 3, 1, 4, 4, 640, 640),
+    ('s4_1x1_1536_384',    2, 64, 128, 1536, 384, 1, 1, 0, 1, 2560, 640),
+    ('s4_1x1_384_1536',    2, 64, 128, 384, 1536, 1, 1, 0, 1, 640, 2560),
+    ('wide_ragged_640',    3, 37, 53, 192, 640, 3, 1, 1, 1, 192, 640),
 ]
+
+
+def wide_tile_epilogue_checks(gs):
+    """The wide n-tile path (Cout = 320 in ONE accumulator, second drain round of every epilogue group) with the FULL
+    epilogue: per-channel scale / shift, residual (TMA-loaded into the staging slot), ReLU, and the DynBN statistics."""
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    out = []
+    for Co in (320, 384):
+        case = (f'wide_epi{Co}', 2, 24, 40, 128, Co, 3, 1, 1, 1, 160, Co)
+        conv, x, g = C._mk_conv(case, dev, gs)
+        scale = torch.rand(Co, generator=g) + 0.5
+        shift = torch.randn(Co, generator=g)
+        res = bf16r(torch.randn(2, Co, 24, 40, generator=g))
+        ref = F.conv2d(x.double(), conv.weight.detach().cpu().double()[:Co, :128], None, 1, 1, 1)
+        ref = torch.relu(ref * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1) + res.double())
+        z, _, _, _ = Fg.conv_forward(Fg.as_act(x.to(dev)), conv, Co, scale=scale.to(dev), shift=shift.to(dev),
+                                     residual=Fg.as_act(res.to(dev)), relu=True)
+        torch.cuda.synchronize()
+        out.append(check_bf16(z.float(), ref, f'wide_tile[{Co}].scale_shift_res_relu'))
+        y, stats, _, _ = Fg.conv_forward(Fg.as_act(x.to(dev)), conv, Co, want_stats=True)
+        torch.cuda.synchronize()
+        yr = y.float().double().cpu()
+        out.append(check_f32(stats, torch.cat([yr.sum((0, 2, 3)), (yr * yr).sum((0, 2, 3))]), f'wide_tile[{Co}].stats', 1e-4))
+    return out
+
 
 
 def big_conv_case_checks(case, gs):

@@ -43,6 +43,10 @@ def test_conv_values_at_benchmark_shapes(gs, case):
     _assert_all(P.big_conv_case_checks(case, gs))
 
 
+def test_wide_tile_epilogue(gs):
+    _assert_all(P.wide_tile_epilogue_checks(gs))
+
+
 def test_full_depth_stage(gs):
     _assert_all(P.deep_stage_checks(gs))
 
