@@ -468,6 +468,15 @@ class GraphedTrainStep:
         self.pool_gb = pool_gb
         self.graph_after, self.max_graphs = graph_after, max_graphs
         self.seen, self.graphs = {}, OrderedDict()
+        # ONE stepper (= one stream) per optimizer: autograd's gradient accumulators remember the stream they were created
+        # on, a second stepper on the same parameters would make a captured backward depend on uncaptured work of the
+        # first one's stream (cudaErrorStreamCaptureIsolation)
+        prev = getattr(optimizer, '_gs_stepper', None)
+        if prev is not None and prev() is not None and prev() is not self and max_graphs > 0:
+            raise F_gs.GsError('GraphedTrainStep: this optimizer is already driven by another GraphedTrainStep; use ONE '
+                               'stepper per model and key the sub-nets through arch_key')
+        import weakref
+        optimizer._gs_stepper = weakref.ref(self)
         # every iteration (eager, capture, replay) runs on ONE dedicated side stream: a graph may only be captured on a
         # stream whose tensors carry no dependency on uncaptured work of another stream (autograd would otherwise
         # insert cross-stream waits during the captured backward: cudaErrorStreamCaptureIsolation)

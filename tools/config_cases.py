@@ -120,12 +120,15 @@ def config3(dev):
     data = batch(2, 512, 1024, 19, dev, 3)
     res = {'config': 3, 'workload': 'dynamic ResNet-101 (OS8 V1c supernet) + DeepLabV3 ASPP head, bf16 fwd+bwd+SGD, '
                                     '2x3x512x1024, 19 classes'}
+    # ONE GraphedTrainStep (= one stream) per model, keyed by the sub-net, as IterBasedRunner drives it.  (Round 1 built a
+    # second stepper -- a second stream -- for the second sub-net of the SAME parameters; autograd's gradient accumulators
+    # remember the stream they were created on, so the captured backward then depended on uncaptured work of the first
+    # stepper's stream: cudaErrorStreamCaptureIsolation.  The product path never does that.)
+    stepper = gs.GraphedTrainStep(model, opt, graph_after=2 if os.environ.get('CONFIG3_GRAPH', '1') == '1' else 10 ** 9,
+                                  max_graphs=2, pool_gb=16)
     for name, arch in (('R101', R101), ('MAX', MAX)):
         model.manipulate_arch(arch)
-        # open item (round 1): inside THIS script the capture of config 3 trips cudaErrorStreamCaptureIsolation in the autograd
-        # engine's end-of-backward stream sync; the same model / sub-net / size captures fine on its own
-        # (tools/graph_fullsize.py), so config 3 is timed eagerly here
-        step = train_fn(model, opt, data, key=name, graph=os.environ.get('CONFIG3_GRAPH', '0') == '1')
+        step = lambda name=name: stepper(name, data)
         ms = timed(step, 5, 3)
         out = step()
         res[name] = dict(ms_per_step=round(ms, 2), imgs_per_s=round(2e3 / ms, 1), loss=float(out['loss']),
