@@ -29,7 +29,8 @@ class BnBwdFuse(Structure):
 
 class SyncDesc(Structure):
     """struct gs_sync_desc (include/gaiaseg_b200.h): the SyncBN peer exchange a DynBN kernel runs itself."""
-    _fields_ = [('peer_inboxes', c_void_p), ('rank', c_int32), ('world', c_int32), ('seq_dev', c_void_p)]
+    _fields_ = [('peer_inboxes', c_void_p), ('rank', c_int32), ('world', c_int32), ('seq_dev', c_void_p),
+                ('phase', c_int32), ('reserved', c_int32)]
 
 
 class AugParams(Structure):
@@ -57,6 +58,7 @@ PROTOTYPES = {
     'gs_reset_launch_count': (None, []),
     'gs_debug_set_trace': (_I, [_P]),
     'gs_conv2d_fwd': (_I, [_G, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    'gs_conv2d_fwd_syncbn': (_I, [_G, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     'gs_conv2d_dgrad_workspace_bytes': (_L, [_G]),
     'gs_conv2d_dgrad': (_I, [_G, _P, _P, _P, _P, _I, _P, _P, _P]),
     'gs_conv2d_wgrad': (_I, [_G, _P, _P, _P, _P]),
@@ -67,8 +69,8 @@ PROTOTYPES = {
     'gs_bn_apply': (_I, [_P, _I, _P, _P, _P, _I, _I, _P, _I, _L, _I, _P]),
     'gs_bn_apply_train': (_I, [_P, _I, _P, _D, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _P, _I, _L, _I, _P, _P]),
     'gs_bn_bwd': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _D, _L, _I, _P, _I, _P, _I, _P, _P, _P, _P]),
-    'gs_bn_bwd_reduce': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _L, _I, _P, _P]),
-    'gs_bn_bwd_apply': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _D, _L, _I, _P, _I, _P, _I, _P, _P, _P]),
+    'gs_bn_bwd_reduce': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _L, _I, _P, _P, _P]),
+    'gs_bn_bwd_apply': (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _D, _L, _I, _P, _I, _P, _I, _P, _P, _P, _P]),
     'gs_affine_bwd': (_I, [_P, _I, _P, _I, _P, _L, _I, _P, _I, _P, _I, _P]),
     'gs_bn_bwd_param': (_I, [_P, _I, _P, _P, _I, _P]),
     'gs_maxpool3x3s2_fwd': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),

@@ -27,6 +27,10 @@ struct SyncArgs {
     int rank, world;
     unsigned long long* seq_dev;
     unsigned long long timeout_ns;
+    // 0: the kernel runs the whole exchange (push + poll); 1: PUSH only (a producer kernel: its last block sends the final
+    // local sums and leaves the sequence counter alone); 2: POLL only (the consumer of a phase-1 producer).  Splitting the
+    // exchange puts the NVLink flight time behind the producer's tail and the consumer's launch instead of on the chain.
+    int phase;
 };
 
 __device__ __forceinline__ void st_u64_sys(unsigned long long* p, unsigned long long v) {
@@ -51,6 +55,27 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// PUSH half, by all `nthreads` threads of the LAST block of a producer kernel (every other block's atomics on `stats` are
+// fenced before that block took its ticket): the final local sums, read through L2, go to every peer's inbox under the
+// tag of the NEXT exchange.  The sequence counter is bumped by the consumer's poll.
+__device__ __forceinline__ void syncbn_push_block(const double* __restrict__ stats, int n, const PeerPtrs& peers, int rank,
+                                                  int world, const unsigned long long* seq_dev, int tid, int nthreads) {
+    const unsigned long long seq = __ldcg(seq_dev) + 1;
+    const unsigned long long tag = (seq & 0xFFFFFFFFull) << 32;
+    const int slot = static_cast<int>(seq % kCommSlots);
+    for (int i = tid; i < n; i += nthreads) {
+        const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(__ldcg(stats + i)));
+        const unsigned long long w0 = (b & 0xFFFFFFFFull) | tag, w1 = (b >> 32) | tag;
+        for (int r = 0; r < world; ++r) {
+            if (r == rank) continue;
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(
+                peers.p[r] + (static_cast<size_t>(slot) * world + rank) * kCommSlotDoubles + i);
+            st_u64_sys(dst, w0);
+            st_u64_sys(dst + 1, w1);
+        }
+    }
+}
+
 // All `nthreads` threads of ONE block call this (tid = 0 .. nthreads-1).  stats[0..n) holds the LOCAL sums on entry and
 // the sums over all ranks on return.  dgamma / dbeta (may be NULL; then n = 2C: [sum g | sum g*xhat]) are incremented by
 // the LOCAL sums first -- the BN parameter gradients, averaged later by the gradient all-reduce.
@@ -58,7 +83,7 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned l
 __device__ __forceinline__ void syncbn_exchange_block(double* __restrict__ stats, int n, const PeerPtrs& peers, int rank,
                                                       int world, unsigned long long* seq_dev, float* __restrict__ dgamma,
                                                       float* __restrict__ dbeta, unsigned long long timeout_ns, int tid,
-                                                      int nthreads) {
+                                                      int nthreads, bool push = true) {
     const unsigned long long seq = *seq_dev + 1;     // every thread reads the counter; thread 0 bumps it at the very end
     const unsigned long long tag = (seq & 0xFFFFFFFFull) << 32;
     const int slot = static_cast<int>(seq % kCommSlots);
@@ -68,7 +93,7 @@ __device__ __forceinline__ void syncbn_exchange_block(double* __restrict__ stats
         const double v = stats[i];
         const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
         const unsigned long long w0 = (b & 0xFFFFFFFFull) | tag, w1 = (b >> 32) | tag;
-        for (int r = 0; r < world; ++r) {
+        for (int r = 0; push && r < world; ++r) {      // (push == false: the producer kernel has sent them already)
             if (r == rank) continue;
             unsigned long long* dst = reinterpret_cast<unsigned long long*>(
                 peers.p[r] + (static_cast<size_t>(slot) * world + rank) * kCommSlotDoubles + i);

@@ -23,6 +23,7 @@
 #include "../../include/gaiaseg_b200.h"
 #include "gs_host.h"
 #include "gs_ptx.cuh"
+#include "gs_comm.cuh"
 
 namespace gs {
 
@@ -92,7 +93,32 @@ struct IgemmParams {
     long long res_ld;
     // non-NULL: per-channel sum / sum^2 of the stored (bf16-rounded) output, fp64 [2 * Cout] (DynBN forward statistics)
     double* stats;
+    // SyncBN over several ranks (sync.world > 1, needs stats): the LAST CTA to flush its statistics pushes the rank's final
+    // sums to every peer inbox over NVLink -- conv and the send half of the statistic all-reduce in one kernel; the BN
+    // apply kernel polls.  sync_ticket: zero-initialised 64-bit word counting the CTAs that have flushed.
+    SyncArgs sync;
+    unsigned long long* sync_ticket;
 };
+
+// Fused send half of the SyncBN all-reduce (several ranks), called by the 512 epilogue threads after their statistic
+// atomics: every CTA fences and takes a ticket; the last one sees the rank's final sums in L2 and stores them into the
+// peers' inboxes (flag-in-data protocol, gs_comm.cuh).  Out of line: it runs once per kernel and must not cost the main
+// loop any registers.
+__device__ __noinline__ void ig_syncbn_push(const IgemmParams& p, uint8_t* staging) {
+    volatile uint32_t* is_last = reinterpret_cast<volatile uint32_t*>(staging + 16384);   // behind the `red` scratch
+    __threadfence();
+    named_bar_sync(5, 512);
+    if (threadIdx.x == 64) {
+        const unsigned long long ticket = atomicAdd(p.sync_ticket, 1ull);
+        *is_last = (ticket + 1 == static_cast<unsigned long long>(gridDim.x)) ? 1u : 0u;
+    }
+    named_bar_sync(5, 512);
+    if (*is_last) {
+        __threadfence();
+        syncbn_push_block(p.stats, 2 * p.Cout, p.sync.peers, p.sync.rank, p.sync.world, p.sync.seq_dev,
+                          static_cast<int>(threadIdx.x) - 64, 512);
+    }
+}
 
 template <int CG, bool WIDE>
 __global__ void __launch_bounds__(kIgThreads, 1)
@@ -573,6 +599,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 atomicAdd(p.stats + col, static_cast<double>(su));
                 atomicAdd(p.stats + p.Cout + col, static_cast<double>(sq));
             }
+            if (p.sync.world > 1) ig_syncbn_push(p, staging);
         }
     }
 
@@ -605,6 +632,7 @@ struct IgemmLaunch {
     void* out; long long out_ld; int out_f32;
     const float* scale; const float* shift; const void* residual; long long res_ld; int relu; double* stats;
     const gs_bn_bwd_fuse* fuse;   // reserved, must be NULL
+    const gs_sync_desc* sync;     // forward only: push the final statistics to the SyncBN peers (phase 1)
 };
 
 static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
@@ -652,6 +680,24 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     p.scale = L.scale; p.shift = L.shift;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(L.residual); p.res_ld = L.res_ld;
     p.stats = L.stats;
+    p.sync = SyncArgs{};
+    p.sync.world = 1;
+    p.sync_ticket = nullptr;
+    if (L.sync != nullptr && L.sync->world > 1) {
+        GS_REQUIRE(L.stats != nullptr, "conv: the SyncBN push needs the statistics accumulator");
+        GS_REQUIRE(L.sync->phase == 1, "conv: sync descriptor must have phase == 1 (push only), got %d", L.sync->phase);
+        GS_REQUIRE(L.sync->world <= kCommMaxWorld && L.sync->rank >= 0 && L.sync->rank < L.sync->world &&
+                       L.sync->peer_inboxes != nullptr && L.sync->seq_dev != nullptr,
+                   "conv: bad sync descriptor (rank %d / world %d)", L.sync->rank, L.sync->world);
+        GS_REQUIRE(2 * L.Cout <= kCommSlotDoubles, "conv: %d channels exceed the exchange slot", L.Cout);
+        for (int r = 0; r < L.sync->world; ++r)
+            p.sync.peers.p[r] = reinterpret_cast<ulonglong2*>(const_cast<void*>(L.sync->peer_inboxes[r]));
+        p.sync.rank = L.sync->rank;
+        p.sync.world = L.sync->world;
+        p.sync.seq_dev = reinterpret_cast<unsigned long long*>(L.sync->seq_dev);
+        p.sync.phase = 1;
+        p.sync_ticket = reinterpret_cast<unsigned long long*>(L.stats + 2 * L.Cout);   // first scratch word behind the sums
+    }
     GS_REQUIRE(L.fuse == nullptr, "dgrad: the fused BN-backward reduction was removed (measured slower than gs_bn_bwd_reduce); "
                                   "pass fuse = NULL");
     p.direct = tma_store_ok ? 0 : 1;
@@ -1136,6 +1182,12 @@ extern "C" int gs_debug_set_trace(void* device_buffer_u64x256) {
 extern "C" int gs_conv2d_fwd(const gs_conv_geom* g, const void* x, const void* w_krsc, void* y, const float* scale,
                              const float* shift, const void* residual, int32_t res_ld, int32_t flags, double* stats,
                              void* stream) {
+    return gs_conv2d_fwd_syncbn(g, x, w_krsc, y, scale, shift, residual, res_ld, flags, stats, nullptr, stream);
+}
+
+extern "C" int gs_conv2d_fwd_syncbn(const gs_conv_geom* g, const void* x, const void* w_krsc, void* y, const float* scale,
+                                    const float* shift, const void* residual, int32_t res_ld, int32_t flags, double* stats,
+                                    const gs_sync_desc* sync, void* stream) {
     if (check_geom(g)) return -1;
     IgemmLaunch L{};
     L.a_ptr = x; L.a_C = g->Ci; L.a_ld = g->x_ld; L.a_H = g->H; L.a_W = g->W; L.a_estride = g->stride;
@@ -1144,7 +1196,7 @@ extern "C" int gs_conv2d_fwd(const gs_conv_geom* g, const void* x, const void* w
     L.in_mul = g->stride; L.base = -g->pad; L.step = g->dil;
     L.out = y; L.out_ld = g->y_ld; L.out_f32 = (flags & GS_EPI_OUT_F32) ? 1 : 0;
     L.scale = scale; L.shift = shift; L.residual = residual; L.res_ld = res_ld;
-    L.relu = (flags & GS_EPI_RELU) ? 1 : 0; L.stats = stats;
+    L.relu = (flags & GS_EPI_RELU) ? 1 : 0; L.stats = stats; L.sync = sync;
     return launch_igemm(L, static_cast<cudaStream_t>(stream));
 }
 

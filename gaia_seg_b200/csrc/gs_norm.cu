@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
     if (FROM_STATS && t.sync.world > 1) {
         if (blockIdx.x == 0) {
             syncbn_exchange_block(const_cast<double*>(t.stats), 2 * t.C, t.sync.peers, t.sync.rank, t.sync.world,
-                                  t.sync.seq_dev, nullptr, nullptr, t.sync.timeout_ns, threadIdx.x, blockDim.x);
+                                  t.sync.seq_dev, nullptr, nullptr, t.sync.timeout_ns, threadIdx.x, blockDim.x,
+                                  t.sync.phase != 2);   // phase 2: the conv kernel's last CTA has pushed the sums
             __threadfence();
             __syncthreads();
             if (threadIdx.x == 0) st_release_gpu(t.flag, 1ull);
@@ -260,10 +261,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
                                                             const float* __restrict__ invstd,
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift, long long P, int C,
-                                                            int C8, int Vc, int R, double* __restrict__ sums) {
+                                                            int C8, int Vc, int R, double* __restrict__ sums,
+                                                            SyncArgs sync, unsigned long long* __restrict__ ticket) {
     pdl_sync();
     constexpr bool HAS_Z = (MASK == 1);
     __shared__ float red[256 * 16];
+    __shared__ unsigned int is_last;
     const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
     const long long S = (long long)gridDim.x * R;
     for (int cv0 = 0; cv0 < C8; cv0 += Vc) {
@@ -318,6 +321,18 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
         }
         block_reduce16_atomic(sg, sx, red, Vc, R, cv0, C8, C, sums);
     }
+    if (sync.world > 1 && sync.phase == 1) {
+        // send half of the SyncBN exchange: the last block to finish sees the rank's final sums and pushes them to the
+        // peers, so the NVLink flight overlaps this kernel's tail and the launch of gs_bn_bwd_apply (which polls)
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1ull) + 1 == static_cast<unsigned long long>(gridDim.x)) ? 1u : 0u;
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            syncbn_push_block(sums, 2 * C, sync.peers, sync.rank, sync.world, sync.seq_dev, threadIdx.x, blockDim.x);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -336,11 +351,31 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
                                                            long long P, int C, int C8, int Vc, int R,
                                                            uint4* __restrict__ dy, long long dy_ld8,
                                                            uint4* __restrict__ dres, long long dres_ld8,
-                                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           SyncArgs sync, unsigned long long* __restrict__ flag) {
     pdl_sync();
     constexpr bool HAS_Z = (MASK == 1);
     const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
     const long long S = (long long)gridDim.x * R;
+    if (sync.world > 1) {
+        // several ranks: `sums` holds the LOCAL sums and gs_bn_bwd_reduce's last block has pushed them.  Block 0 adds
+        // the parameter gradients from the local sums, polls the peers' contributions, writes the group sums in place
+        // and releases the other blocks (no exchange launch between the two passes).
+        if (blockIdx.x == 0) {
+            syncbn_exchange_block(const_cast<double*>(sums), 2 * C, sync.peers, sync.rank, sync.world, sync.seq_dev, dgamma,
+                                  dbeta, sync.timeout_ns, threadIdx.x, blockDim.x, sync.phase != 2);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) st_release_gpu(flag, 1ull);
+        } else {
+            if (threadIdx.x == 0) {
+                while (ld_acquire_gpu(flag) == 0ull) {}
+            }
+            __syncthreads();
+        }
+        dgamma = nullptr;
+        dbeta = nullptr;
+    }
     for (int cv = cx; cv < C8; cv += Vc) {
         float mu[8], is[8], k0[8], k1[8], k2[8], sc[8], sh[8];
         load8f(mean + cv * 8, mu);
@@ -351,8 +386,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
             const int c = cv * 8 + i;
             const float g = gamma ? __ldg(gamma + c) : 1.f;
             k0[i] = g * is[i];                                               // gamma * invstd
-            k1[i] = static_cast<float>(sums[c] * inv_count);                 // mean of g
-            k2[i] = static_cast<float>(sums[C + c] * inv_count);             // mean of g*xhat
+            // (several ranks: block 0 has just rewritten the sums -> read them through L2)
+            k1[i] = static_cast<float>((sync.world > 1 ? __ldcg(sums + c) : sums[c]) * inv_count);           // mean of g
+            k2[i] = static_cast<float>((sync.world > 1 ? __ldcg(sums + C + c) : sums[C + c]) * inv_count);   // mean of g*xhat
             if (blockIdx.x == 0 && ry == 0) {   // parameter gradients (single-rank case: local sums == group sums)
                 if (dgamma) dgamma[c] += static_cast<float>(sums[C + c]);
                 if (dbeta) dbeta[c] += static_cast<float>(sums[c]);
@@ -608,6 +644,262 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const uint4* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// one-pass backward, CHANNEL-PARTITIONED over thread-block clusters.
+// The BN reductions are per channel, so nothing forces a grid-wide barrier: cluster k owns the channel vectors
+// [k Vc, k Vc + Vc) for ALL pixels, CTA r of the cluster the pixel range [r Pc, r Pc + Pc).  Phase 1 streams dz / y (/ z)
+// once and leaves per-CTA partial sums in shared memory; ONE hardware cluster barrier; every CTA sums the partials of its
+// cluster over distributed shared memory in rank order (deterministic -- no atomics, no zero-filled accumulator);
+// phase 2 re-reads the CTA's own pixels (L1 / L2 hits: the CTA touched exactly these lines microseconds ago) and writes
+// dy (/ dres).  One launch instead of two, no co-residency requirement across clusters (no cooperative launch, so it runs
+// beside the side-stream weight gradients), and with several ranks each cluster runs the SyncBN exchange for ITS channels
+// (CTA 0 pushes, every CTA polls the rank's own inbox) -- no exchange launch and no single-block bottleneck.
+// scratch: one zero-initialised 64-bit word (clusters that finished the exchange; the last one bumps the sequence).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cl_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cl_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cl_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double cl_ld_f64(const double* local, uint32_t cta) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(local));
+    uint32_t ra;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(cta));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+template <int MASK, bool HAS_DRES>
+__global__ void __launch_bounds__(512) bn_bwd_cluster_kernel(const uint4* __restrict__ dz, long long dz_ld8,
+                                                             const uint4* __restrict__ y, long long y_ld8,
+                                                             const uint4* __restrict__ z, long long z_ld8,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd,
+                                                             const float* __restrict__ scale,
+                                                             const float* __restrict__ shift,
+                                                             const float* __restrict__ gamma, double inv_count,
+                                                             long long P, int C, int C8, int Vc, uint4* __restrict__ dy,
+                                                             long long dy_ld8, uint4* __restrict__ dres,
+                                                             long long dres_ld8, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, SyncArgs sync,
+                                                             unsigned long long* __restrict__ scratch) {
+    pdl_sync();
+    constexpr bool HAS_Z = (MASK == 1);
+    __shared__ float wred[16 * 8 * 16];     // [warp][cx][16] warp totals (Vc <= 8, <= 16 warps)
+    __shared__ double part[8 * 16];         // [cx][16] this CTA's partial sums (read by the whole cluster)
+    __shared__ float kf[8 * 16];            // [cx][16] mean(g) | mean(g * xhat) of this cluster's channels
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int CL = static_cast<int>(cl_nctarank()), r = static_cast<int>(cl_ctarank());
+    const int group = blockIdx.x / CL;
+    const int cx = tid % Vc, ry = tid / Vc, R = blockDim.x / Vc;     // Vc is a power of two <= 8: lane % Vc == cx
+    const int cv = group * Vc + cx;
+    const bool act = cv < C8;
+    const long long Pc = (P + CL - 1) / CL;
+    const long long p0 = r * Pc, p1 = (p0 + Pc < P) ? p0 + Pc : P;
+    float mu[8], is[8], sc[8], sh[8];
+    if (act) {
+        load8f(mean + cv * 8, mu);
+        load8f(invstd + cv * 8, is);
+        if (MASK == 2) { load8f(scale + cv * 8, sc); load8f(shift + cv * 8, sh); }
+    }
+    // the exchange's sequence number: read BEFORE the first cluster barrier -- the last cluster bumps the counter once every
+    // cluster has finished its exchange, and every CTA of every cluster reads it ahead of its own barrier, so nobody can see
+    // the bumped value
+    const unsigned long long seq0 = sync.world > 1 ? __ldcg(sync.seq_dev) + 1 : 0ull;
+    // ---------------- phase 1: partial sums of g and g * xhat over this CTA's pixels ----------------
+    float sg[8], sx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sg[i] = 0.f; sx[i] = 0.f; }
+    if (act) {
+        long long p = p0 + ry;
+        for (; p + 3 * R < p1; p += 4 * R) {
+            uint4 a[4], b[4], c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a[u] = __ldg(dz + (p + u * R) * dz_ld8 + cv);      // (default caching: phase 2 re-reads these lines)
+                b[u] = __ldg(y + (p + u * R) * y_ld8 + cv);
+                if (HAS_Z) c[u] = __ldg(z + (p + u * R) * z_ld8 + cv);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float g[8], yy[8], zz[8];
+                unpack8(a[u], g);
+                unpack8(b[u], yy);
+                if (HAS_Z) unpack8(c[u], zz);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    bool dead = HAS_Z && !(zz[i] > 0.f);
+                    if (MASK == 2) dead = !(fmaf(yy[i], sc[i], sh[i]) > 0.f);
+                    const float gi = dead ? 0.f : g[i];
+                    sg[i] += gi;
+                    sx[i] = fmaf(gi, (yy[i] - mu[i]) * is[i], sx[i]);
+                }
+            }
+        }
+        for (; p < p1; p += R) {
+            float g[8], yy[8], zz[8];
+            unpack8(__ldg(dz + p * dz_ld8 + cv), g);
+            unpack8(__ldg(y + p * y_ld8 + cv), yy);
+            if (HAS_Z) unpack8(__ldg(z + p * z_ld8 + cv), zz);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                bool dead = HAS_Z && !(zz[i] > 0.f);
+                if (MASK == 2) dead = !(fmaf(yy[i], sc[i], sh[i]) > 0.f);
+                const float gi = dead ? 0.f : g[i];
+                sg[i] += gi;
+                sx[i] = fmaf(gi, (yy[i] - mu[i]) * is[i], sx[i]);
+            }
+        }
+    }
+    // warp: lanes with the same cx (lane % Vc) hold partials of the same channels
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        for (int o = 16; o >= Vc; o >>= 1) {
+            sg[i] += __shfl_xor_sync(0xFFFFFFFFu, sg[i], o);
+            sx[i] += __shfl_xor_sync(0xFFFFFFFFu, sx[i], o);
+        }
+    }
+    if (lane < Vc) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            wred[(warp * 8 + lane) * 16 + i] = sg[i];
+            wred[(warp * 8 + lane) * 16 + 8 + i] = sx[i];
+        }
+    }
+    __syncthreads();
+    const int nval = Vc * 16;                 // thread t < nval owns value (cx = t / 16, j = t % 16)
+    if (tid < nval) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; ++w) s += static_cast<double>(wred[(w * 8 + (tid >> 4)) * 16 + (tid & 15)]);
+        part[tid] = s;
+    }
+    cl_sync();                                // partials of every CTA of the cluster are visible
+    double tot = 0.0;
+    if (tid < nval)
+        for (int q = 0; q < CL; ++q) tot += cl_ld_f64(part + tid, static_cast<uint32_t>(q));
+    cl_sync();                                // nobody reads a peer's shared memory after this point (CTAs may exit)
+    if (tid < nval) {
+        const int vcv = group * Vc + (tid >> 4), j = tid & 15;
+        const bool vact = vcv < C8;
+        const int c = vcv * 8 + (j & 7);
+        if (vact && r == 0) {                 // parameter gradients from the LOCAL sums
+            if (j < 8) { if (dbeta) dbeta[c] += static_cast<float>(tot); }
+            else if (dgamma) dgamma[c] += static_cast<float>(tot);
+        }
+        if (sync.world > 1) {
+            const unsigned long long seq = seq0;
+            const unsigned long long tag = (seq & 0xFFFFFFFFull) << 32;
+            const int slot = static_cast<int>(seq % kCommSlots);
+            const int gi = (j < 8 ? 0 : C) + c;                          // index in the [sum g | sum g*xhat] layout
+            if (vact) {
+                if (r == 0) {
+                    const unsigned long long bb = static_cast<unsigned long long>(__double_as_longlong(tot));
+                    const unsigned long long w0 = (bb & 0xFFFFFFFFull) | tag, w1 = (bb >> 32) | tag;
+                    for (int q = 0; q < sync.world; ++q) {
+                        if (q == sync.rank) continue;
+                        unsigned long long* dst = reinterpret_cast<unsigned long long*>(
+                            sync.peers.p[q] + (static_cast<size_t>(slot) * sync.world + sync.rank) * kCommSlotDoubles + gi);
+                        st_u64_sys(dst, w0);
+                        st_u64_sys(dst + 1, w1);
+                    }
+                }
+                const ulonglong2* inbox = sync.peers.p[sync.rank] + static_cast<size_t>(slot) * sync.world * kCommSlotDoubles;
+                const unsigned long long t0 = gtimer();
+                double s = 0.0;
+                for (int q = 0; q < sync.world; ++q) {
+                    if (q == sync.rank) { s += tot; continue; }
+                    const ulonglong2* src = inbox + static_cast<size_t>(q) * kCommSlotDoubles + gi;
+                    ulonglong2 w = ld_v2_sys(src);
+                    unsigned int spins = 0;
+                    while ((w.x & 0xFFFFFFFF00000000ull) != tag || (w.y & 0xFFFFFFFF00000000ull) != tag) {
+                        if ((++spins & 1023u) == 0 && gtimer() - t0 > sync.timeout_ns) {
+                            printf("gaiaseg_b200: SyncBN peer exchange (bn_bwd cluster) timed out (rank %d waiting for rank %d, seq %llu)\n",
+                                   sync.rank, q, seq);
+                            __trap();
+                        }
+                        w = ld_v2_sys(src);
+                    }
+                    s += __longlong_as_double(static_cast<long long>((w.x & 0xFFFFFFFFull) | (w.y << 32)));
+                }
+                tot = s;
+            }
+        }
+        kf[tid] = static_cast<float>(tot * inv_count);
+    }
+    __syncthreads();
+    if (sync.world > 1 && r == 0 && tid == 0) {
+        // every cluster read the sequence number before it pushed; the LAST cluster to finish its exchange bumps it
+        __threadfence();
+        const unsigned long long done = atomicAdd(scratch, 1ull);
+        if (done + 1 == static_cast<unsigned long long>(gridDim.x / CL)) *sync.seq_dev = seq0;
+    }
+    if (!act) return;
+    // ---------------- phase 2: dy = gamma*invstd*( g - mean(g) - xhat*mean(g*xhat) ); dres = g ----------------
+    float k0[8], k1[8], k2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float g = gamma ? __ldg(gamma + cv * 8 + i) : 1.f;
+        k0[i] = g * is[i];
+        k1[i] = kf[cx * 16 + i];
+        k2[i] = kf[cx * 16 + 8 + i];
+    }
+    long long p = p0 + ry;
+    for (; p + 3 * R < p1; p += 4 * R) {
+        uint4 va[4], vb[4], vc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            va[u] = __ldg(dz + (p + u * R) * dz_ld8 + cv);
+            vb[u] = __ldg(y + (p + u * R) * y_ld8 + cv);
+            if (HAS_Z) vc[u] = __ldg(z + (p + u * R) * z_ld8 + cv);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float g[8], yy[8], zz[8], o[8];
+            unpack8(va[u], g);
+            unpack8(vb[u], yy);
+            if (HAS_Z) unpack8(vc[u], zz);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                bool dead = HAS_Z && !(zz[i] > 0.f);
+                if (MASK == 2) dead = !(fmaf(yy[i], sc[i], sh[i]) > 0.f);
+                const float gi = dead ? 0.f : g[i];
+                g[i] = gi;
+                const float xh = (yy[i] - mu[i]) * is[i];
+                o[i] = k0[i] * (gi - k1[i] - xh * k2[i]);
+            }
+            stg_stream(dy + (p + u * R) * dy_ld8 + cv, pack8(o));
+            if (HAS_DRES) stg_stream(dres + (p + u * R) * dres_ld8 + cv, pack8(g));
+        }
+    }
+    for (; p < p1; p += R) {
+        float g[8], yy[8], zz[8], o[8];
+        unpack8(__ldg(dz + p * dz_ld8 + cv), g);
+        unpack8(__ldg(y + p * y_ld8 + cv), yy);
+        if (HAS_Z) unpack8(__ldg(z + p * z_ld8 + cv), zz);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            bool dead = HAS_Z && !(zz[i] > 0.f);
+            if (MASK == 2) dead = !(fmaf(yy[i], sc[i], sh[i]) > 0.f);
+            const float gi = dead ? 0.f : g[i];
+            g[i] = gi;
+            const float xh = (yy[i] - mu[i]) * is[i];
+            o[i] = k0[i] * (gi - k1[i] - xh * k2[i]);
+        }
+        stg_stream(dy + p * dy_ld8 + cv, pack8(o));
+        if (HAS_DRES) stg_stream(dres + p * dres_ld8 + cv, pack8(g));
+    }
+}
+
 // eval-mode / frozen BN backward: dy = scale * g (no statistics terms); dres = g
 template <bool HAS_Z, bool HAS_DRES>
 __global__ void __launch_bounds__(256) affine_bwd_kernel(const uint4* __restrict__ dz, long long dz_ld8,
@@ -695,6 +987,7 @@ static int make_sync(const gs_sync_desc* d, SyncArgs* out, const char* what) {
     out->world = d->world;
     out->seq_dev = reinterpret_cast<unsigned long long*>(d->seq_dev);
     out->timeout_ns = comm_timeout_ns();
+    out->phase = d->phase;
     return 0;
 }
 
@@ -792,7 +1085,8 @@ extern "C" int gs_bn_apply_train(const void* y, int32_t y_ld, const double* stat
 
 extern "C" int gs_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z,
                                 int32_t z_ld, const float* mean, const float* invstd, const float* scale,
-                                const float* shift, int32_t relu, int64_t P, int32_t C, double* sums, void* stream) {
+                                const float* shift, int32_t relu, int64_t P, int32_t C, double* sums,
+                                const gs_sync_desc* sync, void* stream) {
     if (check_act(dz, dz_ld, C, "bn_bwd_reduce dz") || check_act(y, y_ld, C, "bn_bwd_reduce y")) return -1;
     if (z && check_act(z, z_ld, C, "bn_bwd_reduce z")) return -1;
     GS_REQUIRE(mean && invstd && sums, "bn_bwd_reduce: null pointer");
@@ -802,10 +1096,15 @@ extern "C" int gs_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* y, in
     const int grid = reduce_grid(m, P);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int mask = !relu ? 0 : (z ? 1 : 2);
+    SyncArgs sa;
+    if (make_sync(sync, &sa, "bn_bwd_reduce")) return -1;
+    GS_REQUIRE(sa.world <= 1 || (sa.phase == 1 && C <= kCommSlotDoubles / 2),
+               "bn_bwd_reduce: sync descriptor must have phase == 1 and C <= %d", kCommSlotDoubles / 2);
+    unsigned long long* ticket = reinterpret_cast<unsigned long long*>(sums + 2 * C);   // first scratch word behind the sums
 #define GS_BWD_REDUCE(MK)                                                                                            \
     gs::launch(bn_bwd_reduce_kernel<MK>, dim3(grid), dim3(m.threads), 0, st,                                                             \
         reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8,                  \
-        reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, scale, shift, P, C, m.C8, m.Vc, m.R, sums)
+        reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, scale, shift, P, C, m.C8, m.Vc, m.R, sums, sa, ticket)
     if (mask == 0) GS_BWD_REDUCE(0);
     else if (mask == 1) GS_BWD_REDUCE(1);
     else GS_BWD_REDUCE(2);
@@ -818,7 +1117,7 @@ extern "C" int gs_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* y, int
                                const float* mean, const float* invstd, const float* scale, const float* shift,
                                int32_t relu, const float* gamma, const double* sums, double count, int64_t P, int32_t C,
                                void* dy, int32_t dy_ld, void* dres, int32_t dres_ld, float* dgamma, float* dbeta,
-                               void* stream) {
+                               const gs_sync_desc* sync, void* stream) {
     if (check_act(dz, dz_ld, C, "bn_bwd_apply dz") || check_act(y, y_ld, C, "bn_bwd_apply y") ||
         check_act(dy, dy_ld, C, "bn_bwd_apply dy"))
         return -1;
@@ -832,11 +1131,17 @@ extern "C" int gs_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* y, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const double inv_count = 1.0 / count;
     const int mask = !relu ? 0 : (z ? 1 : 2);
+    SyncArgs sa;
+    if (make_sync(sync, &sa, "bn_bwd_apply")) return -1;
+    GS_REQUIRE(sa.world <= 1 || C <= kCommSlotDoubles / 2, "bn_bwd_apply: %d channels exceed the exchange slot", C);
+    // second scratch word behind the sums: "group sums final" flag (zero on entry)
+    unsigned long long* flag = reinterpret_cast<unsigned long long*>(const_cast<double*>(sums) + 2 * C) + 1;
 #define GS_BWD_APPLY(MK, HD)                                                                                         \
     gs::launch(bn_bwd_apply_kernel<MK, HD>, dim3(grid), dim3(m.threads), 0, st,                                                          \
         reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8,                  \
         reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, scale, shift, gamma, sums, inv_count, P, C, m.C8, \
-        m.Vc, m.R, reinterpret_cast<uint4*>(dy), dy_ld / 8, reinterpret_cast<uint4*>(dres), dres_ld / 8, dgamma, dbeta)
+        m.Vc, m.R, reinterpret_cast<uint4*>(dy), dy_ld / 8, reinterpret_cast<uint4*>(dres), dres_ld / 8, dgamma, dbeta, \
+        sa, flag)
     if (dres) {
         if (mask == 0) GS_BWD_APPLY(0, true);
         else if (mask == 1) GS_BWD_APPLY(1, true);
@@ -869,6 +1174,60 @@ extern "C" int gs_bn_bwd(const void* dz, int32_t dz_ld, const void* y, int32_t y
     const ColMap m = make_colmap(C);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int mask = !relu ? 0 : (z ? 1 : 2);
+    static const int kind = env_int("GS_BN_FUSED_KIND", 1);   // 1: channel-partitioned clusters (default), 0: grid barrier
+    if (kind == 1) {
+        // geometry: Vc channel vectors per cluster (16 Vc contiguous bytes per pixel), G = ceil(C8 / Vc) clusters of CL CTAs
+        // (CL pixel ranges).  Widest Vc <= 4 that still gives ~one wave of CTAs with the largest cluster; then the largest
+        // power-of-two CL with G * CL <= target.
+        static const int cl_max = env_int("GS_BN_CL_MAX", 16), target = env_int("GS_BN_CL_TARGET", 296);
+        static const int vc_max = env_int("GS_BN_CL_VC", 4), threads_env = env_int("GS_BN_CL_THREADS", 256);
+        int Vc = vc_max;
+        while (Vc > 1 && ((m.C8 + Vc - 1) / Vc) * cl_max < 128) Vc >>= 1;
+        const int G = (m.C8 + Vc - 1) / Vc;
+        int CL = 1;
+        while (CL * 2 <= cl_max && G * CL * 2 <= target) CL *= 2;
+        int threads = threads_env;
+        while (threads > 64 && (long long)(threads / Vc) * CL * 4 > P) threads >>= 1;   // tiny maps: keep every row busy
+        const double inv_count = 1.0 / count;
+        unsigned long long* scratch = reinterpret_cast<unsigned long long*>(sums + 2 * C);   // zeroed word behind the sums
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(G * CL);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+#define GS_BWD_CL(MK, HD)                                                                                               \
+    do {                                                                                                                \
+        static bool np = false;                                                                                         \
+        if (!np) {                                                                                                      \
+            GS_CUDA_OK(cudaFuncSetAttribute(bn_bwd_cluster_kernel<MK, HD>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); \
+            np = true;                                                                                                  \
+        }                                                                                                               \
+        GS_CUDA_OK(cudaLaunchKernelEx(&cfg, bn_bwd_cluster_kernel<MK, HD>, reinterpret_cast<const uint4*>(dz),          \
+                                      (long long)(dz_ld / 8), reinterpret_cast<const uint4*>(y), (long long)(y_ld / 8), \
+                                      reinterpret_cast<const uint4*>(z), (long long)(z_ld / 8), mean, invstd, scale,    \
+                                      shift, gamma, inv_count, (long long)P, (int)C, m.C8, Vc,                         \
+                                      reinterpret_cast<uint4*>(dy), (long long)(dy_ld / 8),                            \
+                                      reinterpret_cast<uint4*>(dres), (long long)(dres_ld / 8), dgamma, dbeta, sa,     \
+                                      scratch));                                                                        \
+    } while (0)
+        if (dres) {
+            if (mask == 0) GS_BWD_CL(0, true);
+            else if (mask == 1) GS_BWD_CL(1, true);
+            else GS_BWD_CL(2, true);
+        } else {
+            if (mask == 0) GS_BWD_CL(0, false);
+            else if (mask == 1) GS_BWD_CL(1, false);
+            else GS_BWD_CL(2, false);
+        }
+#undef GS_BWD_CL
+        GS_LAUNCHED();
+        return 0;
+    }
     // the blocks wait on one another (grid barrier): COOPERATIVE launch, grid <= what is co-resident by construction
     static const int bps = env_int("GS_BN_FUSED_BLOCKS_PER_SM", 2), ppt = env_int("GS_BN_FUSED_PPT", 8);
     const int grid = colmap_grid(m, P, ppt, num_sms() * bps);

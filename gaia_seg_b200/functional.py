@@ -261,7 +261,7 @@ def _geom(N, H, W, Ci, Co, Ci_max, Co_max, kh, kw, stride, pad, dil, x_ld, y_ld)
     return ConvGeom(N, H, W, Ho, Wo, Ci, Co, Ci_max, Co_max, kh, kw, stride, pad, dil, x_ld, y_ld)
 
 
-def conv_forward(x, conv, Co, scale=None, shift=None, residual=None, relu=False, out_f32=False, want_stats=False):
+def conv_forward(x, conv, Co, scale=None, shift=None, residual=None, relu=False, out_f32=False, want_stats=False, sync=None):
     """y = epi(conv(x, W[:Co, :Ci])).  Returns (y, stats, a_operand, geom): `a_operand` is the tensor the
     weight gradient must be taken against (x itself, or the im2col matrix of the image conv)."""
     _lib.require_device()
@@ -305,8 +305,12 @@ def conv_forward(x, conv, Co, scale=None, shift=None, residual=None, relu=False,
     if residual is not None:
         residual = as_act(residual)
         res_ld = act_ld(residual)
-    _timed_call('fwd', g, 'gs_conv2d_fwd', ctypes.byref(g), a.data_ptr(), krsc.data_ptr(), y.data_ptr(), _ptr(scale), _ptr(shift),
-                _ptr(residual), res_ld, flags, _ptr(stats), st)
+    if sync is not None:     # several ranks: the conv kernel's last CTA pushes the statistics to the SyncBN peers
+        _timed_call('fwd', g, 'gs_conv2d_fwd_syncbn', ctypes.byref(g), a.data_ptr(), krsc.data_ptr(), y.data_ptr(), _ptr(scale),
+                    _ptr(shift), _ptr(residual), res_ld, flags, _ptr(stats), sync, st)
+    else:
+        _timed_call('fwd', g, 'gs_conv2d_fwd', ctypes.byref(g), a.data_ptr(), krsc.data_ptr(), y.data_ptr(), _ptr(scale), _ptr(shift),
+                    _ptr(residual), res_ld, flags, _ptr(stats), st)
     return y, stats, a, g
 
 
@@ -365,8 +369,20 @@ def conv_dgrad(conv, dy, g, x_shape, add=None):
 # GS_BN_FUSED_BWD=1: one cooperative kernel for the BN backward (single rank; measured SLOWER than reduce + apply, kept as
 # an experiment); GS_SYNCBN_FOLD=1: block 0 of the forward apply kernel runs the SyncBN exchange itself instead of a separate
 # gs_syncbn_allreduce launch (parity-green at N = 2, no measurable gain there: 59.4 vs 59.1 ms per cycle)
-FUSED_BN_BWD = os.environ.get('GS_BN_FUSED_BWD', '0')    # measured slower than reduce + apply at N = 1 (profiles/r02_experiments.md); single rank only
-FOLD_EXCHANGE = os.environ.get('GS_SYNCBN_FOLD', '0') != '0'
+# BN backward in ONE launch (gs_bn_bwd: channel-partitioned clusters, csrc/gs_norm.cu) instead of reduce + apply:
+#   '0' (default) never | '1' always | 'auto' when one activation is at most GS_BN_FUSED_MAX_MB.
+# Parity-tested (tests/test_gpu_path.py::test_bn_backward_one_pass_and_two_kernels) but MEASURED SLOWER inside the training
+# step (profiles/r02_experiments.md): the 16-CTA clusters are placed as a unit and hold up the side-stream weight gradients,
+# which costs more than the saved launch.  Kept as an option; with several ranks each cluster exchanges its own channels.
+FUSED_BN_BWD = os.environ.get('GS_BN_FUSED_BWD', '0')
+FUSED_BN_MAX_BYTES = float(os.environ.get('GS_BN_FUSED_MAX_MB', '24')) * 1e6
+# SyncBN statistic exchange over NVLink peer memory (several ranks), GS_SYNCBN_FOLD:
+#   0  one small exchange kernel per BN layer and direction between producer and consumer;
+#   1  folded into the consumer: block 0 of gs_bn_apply_train pushes + polls, the other blocks wait on a flag;
+#   2  SPLIT: the producer kernel (conv forward / BN-backward reduction) pushes the final local sums from its last block --
+#      compute and the send half of the collective in one kernel -- and the consumer (BN apply / BN-backward apply) polls:
+#      no exchange launch, and the NVLink flight overlaps the producer's tail and the consumer's launch.
+FOLD_EXCHANGE = int(os.environ.get('GS_SYNCBN_FOLD', '2'))
 
 
 def bn_batch_mode(bn):
@@ -457,8 +473,9 @@ class PeerExchange:
         self.own, self.ptrs = own, table
         self.seq = torch.zeros(1, dtype=torch.int64, device=torch.device('cuda', torch.cuda.current_device()))
         # descriptor handed to the DynBN kernels that run the exchange themselves (gs_bn_apply_train / gs_bn_bwd)
-        self.desc = _lib.SyncDesc(ctypes.cast(self.ptrs, ctypes.c_void_p), self.rank, self.world, self.seq.data_ptr())
-        self.desc_ref = ctypes.byref(self.desc)
+        mk = lambda phase: _lib.SyncDesc(ctypes.cast(self.ptrs, ctypes.c_void_p), self.rank, self.world, self.seq.data_ptr(), phase, 0)
+        self.desc, self.desc_push, self.desc_poll = mk(0), mk(1), mk(2)     # whole exchange | producer half | consumer half
+        self.desc_ref, self.push_ref, self.poll_ref = (ctypes.byref(d) for d in (self.desc, self.desc_push, self.desc_poll))
 
     def all_reduce(self, stats, dgamma=None, dbeta=None):
         call('gs_syncbn_allreduce', stats.data_ptr(), stats.numel(), self.ptrs, self.rank, self.world, self.seq.data_ptr(),
@@ -566,16 +583,31 @@ def _sync_group(bn):
     return pg, world
 
 
-def bn_train_apply(bn, y, stats, C, residual=None, relu=False):
+def syncbn_push_desc(bn):
+    """Descriptor for the PRODUCER of `bn`'s statistics (GS_SYNCBN_FOLD=2, several ranks, peer memory available), else None."""
+    if FOLD_EXCHANGE != 2:
+        return None
+    pg, world = _sync_group(bn)
+    if world <= 1:
+        return None
+    ex = PeerExchange.get(pg)
+    return ex.push_ref if ex else None
+
+
+def bn_train_apply(bn, y, stats, C, residual=None, relu=False, pushed=False):
     """all-reduce the packed (sum, sumsq) over the SyncBN group, then ONE kernel: finalize (mean / invstd / scale /
     shift, running-stat update of the channel prefix) + normalise + residual + ReLU.  Returns (z, aff, count)."""
     pg, world = _sync_group(bn)
     sync = None
     if world > 1:
         ex = PeerExchange.get(pg)
-        if ex and FOLD_EXCHANGE:
+        if ex and pushed:
+            sync = ex.poll_ref            # the producer of `stats` has pushed them: block 0 of the apply kernel only polls
+        elif ex and FOLD_EXCHANGE == 1:
             sync = ex.desc_ref            # block 0 of the apply kernel exchanges the sums itself: no extra launch
         else:
+            if pushed:
+                raise GsError('bn_train_apply: statistics were pushed but the peer exchange is not available')
             stats_all_reduce(stats, pg)
     count = float(_pixels(y)) * world
     aff = torch.empty((4, C), dtype=torch.float32, device=y.device)
@@ -615,22 +647,25 @@ def bn_backward(bn, dz, y, aff, count, zmask, relu, want_dres):
     sums = zeros_f64(2 * C + 2, dev)[:2 * C]
     dy = new_act(N, C, H, W, dev)
     dres = new_act(N, C, H, W, dev) if want_dres else None
-    if FUSED_BN_BWD == '1' and world == 1:
-        # ONE cooperative launch: reduce -> grid barrier -> (peer exchange by block 0, parameter gradients from the local
-        # sums) -> apply; the second pass over dz / y comes from L2
+    fused = FUSED_BN_BWD == '1' or (FUSED_BN_BWD == 'auto' and P * C * 2 <= FUSED_BN_MAX_BYTES)
+    if fused and (world == 1 or ex):
+        # ONE launch: partial sums -> cluster barrier (-> per-cluster peer exchange, parameter gradients from the local
+        # sums) -> apply; the second pass over dz / y comes from L1 / L2
         call('gs_bn_bwd', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),
              invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, _ptr(bn.weight), sums.data_ptr(),
              float(count), P, C, dy.data_ptr(), C, _ptr(dres), C, dgam, dbet, ex.desc_ref if world > 1 else None, st)
         return dy, dres
+    split = ex is not None and bool(ex) and FOLD_EXCHANGE == 2      # reduce pushes, apply polls: no exchange launch
     call('gs_bn_bwd_reduce', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),
-         invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, P, C, sums.data_ptr(), st)
-    if world > 1:
+         invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, P, C, sums.data_ptr(),
+         ex.push_ref if split else None, st)
+    if world > 1 and not split:
         # parameter gradients come from the LOCAL sums (the gradient all-reduce averages them later): same kernel
         stats_all_reduce(sums, pg, dgam, dbet)
         dgam = dbet = None
     call('gs_bn_bwd_apply', dz.data_ptr(), act_ld(dz), y.data_ptr(), act_ld(y), _ptr(zmask), zl, mean.data_ptr(),
          invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), 1 if relu else 0, _ptr(bn.weight), sums.data_ptr(),
-         float(count), P, C, dy.data_ptr(), C, _ptr(dres), C, dgam, dbet, st)
+         float(count), P, C, dy.data_ptr(), C, _ptr(dres), C, dgam, dbet, ex.poll_ref if split else None, st)
     return dy, dres
 
 
@@ -679,8 +714,9 @@ def cba_forward(x, conv, bn=None, relu=False, residual=None, Co=None, save=True)
     Co = conv.width_state if Co is None else Co
     rec = LayerRec() if save else None
     if bn is not None and bn_batch_mode(bn):
-        y, stats, a, g = conv_forward(x, conv, Co, shift=_bias(conv, Co), want_stats=True)
-        z, aff, count = bn_train_apply(bn, y, stats, Co, residual, relu)
+        push = syncbn_push_desc(bn)
+        y, stats, a, g = conv_forward(x, conv, Co, shift=_bias(conv, Co), want_stats=True, sync=push)
+        z, aff, count = bn_train_apply(bn, y, stats, Co, residual, relu, pushed=push is not None)
         mode = 'bn_batch'
     else:
         y = None

@@ -140,7 +140,20 @@ typedef struct gs_sync_desc {
     const void* const* peer_inboxes; /* [world] inbox of every rank (own + gs_ipc_open'ed), as for gs_syncbn_allreduce */
     int32_t rank, world;
     void* seq_dev;                    /* device-resident int64 sequence counter shared by ALL exchanges of the group */
+    int32_t phase;                    /* 0: push + poll inside this kernel; 1: PUSH only (producer: gs_conv2d_fwd_syncbn,
+                                         gs_bn_bwd_reduce -- the last block sends the final local sums); 2: POLL only (the
+                                         consumer of such a producer: gs_bn_apply_train, gs_bn_bwd_apply) */
+    int32_t reserved;
 } gs_sync_desc;
+
+/* gs_conv2d_fwd + the PUSH half of the SyncBN statistic exchange (sync->phase == 1, several ranks): the last CTA to flush
+ * its share of `stats` sends the rank's final sums to every peer inbox over NVLink, so the flight time overlaps the tail
+ * of the conv kernel and the launch of gs_bn_apply_train (called with phase == 2, which polls).  stats: fp64 [2*Co + 2],
+ * zero on entry (the two trailing words are scratch: CTA ticket counter, consumer flag).  sync == NULL: gs_conv2d_fwd.
+ * replaces: conv -> torch.nn.SyncBatchNorm all_reduce (configs/_dynamic_/models/pspnet_ar50to101v2_gsync.py:20-23). */
+int gs_conv2d_fwd_syncbn(const gs_conv_geom* g, const void* x, const void* w_krsc, void* y, const float* scale,
+                         const float* shift, const void* residual, int32_t res_ld, int32_t flags, double* stats,
+                         const gs_sync_desc* sync, void* stream);
 
 /* Training-mode apply with the finalize step folded into the kernel prologue (one launch instead of two):
  * scale / shift are derived from the (all-reduced) sums, block 0 stores aff = [mean | invstd | scale | shift]
@@ -155,7 +168,9 @@ int gs_bn_apply_train(const void* y, int32_t y_ld, const double* stats, double c
  *       else [fma(y, scale, shift) > 0], bit-identical to the forward's test and one tensor read cheaper. */
 int gs_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z, int32_t z_ld,
                      const float* mean, const float* invstd, const float* scale, const float* shift, int32_t relu,
-                     int64_t P, int32_t C, double* sums, void* stream);
+                     int64_t P, int32_t C, double* sums, const gs_sync_desc* sync, void* stream);
+/* (sync != NULL, phase == 1, several ranks: the last block pushes the final local sums to the peers; sums is then
+ *  fp64 [2*C + 2] with two zeroed scratch words.) */
 
 /* Fused backward: pass 1 (below) -> grid barrier -> [SyncBN exchange of the sums by block 0, parameter gradients from the
  * LOCAL sums] -> pass 2 (below) in ONE cooperative launch; the second pass over dz / y / z comes from L2.
@@ -174,7 +189,10 @@ int gs_bn_bwd(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const 
 int gs_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* y, int32_t y_ld, const void* z, int32_t z_ld,
                     const float* mean, const float* invstd, const float* scale, const float* shift, int32_t relu,
                     const float* gamma, const double* sums, double count, int64_t P, int32_t C, void* dy, int32_t dy_ld,
-                    void* dres, int32_t dres_ld, float* dgamma, float* dbeta, void* stream);
+                    void* dres, int32_t dres_ld, float* dgamma, float* dbeta, const gs_sync_desc* sync, void* stream);
+/* (sync != NULL, phase == 2, several ranks: `sums` holds the LOCAL sums whose push gs_bn_bwd_reduce has issued; block 0
+ *  accumulates dgamma / dbeta from them, polls the peers' contributions, writes the group sums in place and releases the
+ *  other blocks.) */
 
 /* Backward of a per-channel affine (+ReLU) with FIXED statistics (eval-mode / frozen BN, conv bias):
  *   g = dz * [z > 0];  dy = scale * g;  dres = g. */

@@ -659,3 +659,61 @@ def loss_full_size_checks(gs):
         torch.cuda.synchronize()
         out.append(dict(name=tag + '.dlogits_bitwise_reproducible', ok=bool(torch.equal(lg.grad, lg2.grad)), err=0.0, tol=0))
     return out
+
+
+def bn_bwd_one_pass_checks(gs):
+    """DynBN backward: the ONE-launch channel-partitioned cluster kernel (gs_bn_bwd) and the reduce + apply pair against an
+    fp64 restatement of F.batch_norm's backward on the channel prefix -- every mask mode (none / recomputed from y /
+    from the stored output with a residual gradient), ragged channel counts (C8 not a power of two), a pixel count that
+    is no multiple of anything, and the benchmark's stage-1 / stage-3 sizes."""
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    out = []
+    cases = [  # N, C, Cmax, H, W, relu, residual
+        (3, 40, 64, 9, 14, True, False), (3, 40, 64, 9, 14, False, False), (2, 72, 80, 17, 23, True, True),
+        (1, 8, 8, 5, 7, True, False), (2, 320, 320, 64, 128, True, False), (2, 64, 80, 128, 256, True, False),
+        (2, 1280, 1280, 32, 32, True, True), (2, 160, 160, 64, 128, False, False)]
+    saved = Fg.FUSED_BN_BWD
+    try:
+        for (N, C, Cmax, H, W, relu, has_res) in cases:
+            g = torch.Generator().manual_seed(C * 7 + H)
+            bn = gs.DynamicBatchNorm2d(Cmax).to(dev).train()
+            with torch.no_grad():
+                bn.weight.copy_(torch.rand(Cmax, generator=g) + 0.5)
+                bn.bias.copy_(torch.randn(Cmax, generator=g) * 0.1)
+            y = Fg.as_act((torch.randn(N, C, H, W, generator=g) * 2 + 0.5).to(dev))
+            res = Fg.as_act(torch.randn(N, C, H, W, generator=g).to(dev)) if has_res else None
+            dz = Fg.as_act(torch.randn(N, C, H, W, generator=g).to(dev))
+            z, aff, count = Fg.bn_train_apply(bn, y, Fg.bn_stats(y), C, res, relu)
+            torch.cuda.synchronize()
+            y64, dz64, z64 = y.double().cpu(), dz.double().cpu(), z.double().cpu()
+            mean, invstd = aff[0].double().cpu().view(1, C, 1, 1), aff[1].double().cpu().view(1, C, 1, 1)
+            gam = bn.weight[:C].double().cpu().view(1, C, 1, 1)
+            gg = dz64 * (z64 > 0) if relu else dz64
+            xh = (y64 - mean) * invstd
+            m = float(N * H * W)
+            sg, sx = gg.sum((0, 2, 3), keepdim=True), (gg * xh).sum((0, 2, 3), keepdim=True)
+            dy_ref = gam * invstd * (gg - sg / m - xh * sx / m)
+            tag = f'bn_bwd[N{N},C{C},{H}x{W},relu={int(relu)},res={int(has_res)}]'
+            got = {}
+            for mode in ('0', '1'):
+                Fg.FUSED_BN_BWD = mode
+                bn.weight.grad = None
+                bn.bias.grad = None
+                dy, dres = Fg.bn_backward(bn, dz, y, aff, count, z if has_res else None, relu, has_res)
+                torch.cuda.synchronize()
+                name = tag + ('.one_pass' if mode == '1' else '.two_kernels')
+                out.append(check_bf16(dy.float().cpu(), dy_ref.float(), name + '.dy', 4.0))
+                out.append(check_f32(bn.weight.grad[:C].cpu(), sx.view(C).float(), name + '.dgamma', 2e-3))
+                out.append(check_f32(bn.bias.grad[:C].cpu(), sg.view(C).float(), name + '.dbeta', 2e-3))
+                if Cmax > C:
+                    out.append(dict(name=name + '.inactive_grads_zero', tol=0,
+                                    ok=bool((bn.weight.grad[C:] == 0).all() and (bn.bias.grad[C:] == 0).all()), err=0.0))
+                if has_res:
+                    out.append(dict(name=name + '.dres_exact', ok=bool((dres.float().cpu() == gg.float()).all()), err=0.0, tol=0))
+                got[mode] = dy.float().cpu()
+            # the two paths differ only in the summation order of the per-channel sums
+            out.append(check_bf16(got['1'], got['0'], tag + '.one_pass_vs_two_kernels', 2.0))
+    finally:
+        Fg.FUSED_BN_BWD = saved
+    return out

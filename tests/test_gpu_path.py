@@ -43,6 +43,10 @@ def test_conv_values_at_benchmark_shapes(gs, case):
     _assert_all(P.big_conv_case_checks(case, gs))
 
 
+def test_bn_backward_one_pass_and_two_kernels(gs):
+    _assert_all(P.bn_bwd_one_pass_checks(gs))
+
+
 def test_wide_tile_epilogue(gs):
     _assert_all(P.wide_tile_epilogue_checks(gs))
 
