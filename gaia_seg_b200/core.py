@@ -456,11 +456,12 @@ class DynamicConvModule(nn.Module, DynamicMixin):
         self.width_state = width
         self.conv.manipulate_width(width)
 
-    def forward(self, x, channel_record=None):
+    def forward(self, x, channel_record=None, grad_carrier=None):
         if channel_record is not None:
             raise NotImplementedError('channel_record (segmented input slice) is handled by DynamicPSPHead')
         if getattr(self, '_deploying', False):
             self.conv.deploy_slice(x.size(1))
             if self.with_norm:
                 self.norm.deploy_slice(self.conv.width_state)
-        return F_gs.conv_bn_act(x, self.conv, self.norm, relu=self.with_activation, Co=self.conv.width_state)
+        return F_gs.conv_bn_act(x, self.conv, self.norm, relu=self.with_activation, Co=self.conv.width_state,
+                                grad_carrier=grad_carrier)

@@ -213,7 +213,9 @@ extern "C" int gs_syncbn_allreduce(double* stats, int32_t n, const void* const* 
     }
     int threads = ((n + 31) / 32) * 32;
     if (threads > kCommThreads) threads = kCommThreads;
-    gs::launch(syncbn_allreduce_kernel, dim3(1), dim3(kCommThreads), 0, static_cast<cudaStream_t>(stream), 
+    // PDL kind 8: the single exchange block is dispatched while the producer of `stats` still runs (it waits in
+    // griddepcontrol.wait), so the exchange starts the moment the producer completes instead of one launch latency later
+    gs::launch<8>(syncbn_allreduce_kernel, dim3(1), dim3(kCommThreads), 0, static_cast<cudaStream_t>(stream), 
         stats, n, pp, rank, world, reinterpret_cast<unsigned long long*>(seq_dev), dgamma, dbeta, comm_timeout_ns());
     (void)threads;
     GS_LAUNCHED();

@@ -57,7 +57,7 @@ int encode_tmap_4d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, con
 }
 
 bool pdl_enabled(int kind_bit) {
-    static const int mask = [] { const char* e = getenv("GS_PDL"); return e == nullptr ? 6 : atoi(e); }();
+    static const int mask = [] { const char* e = getenv("GS_PDL"); return e == nullptr ? 14 : atoi(e); }();
     return (mask & kind_bit) != 0;
 }
 

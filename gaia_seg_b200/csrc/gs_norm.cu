@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                        const uint4* __restrict__ res, long long res_ld8, int relu,
                                                        uint4* __restrict__ z, long long z_ld8, long long P, int C8,
-                                                       int Vc, int R, BnTrainArgs t) {
+                                                       int Vc, int R, const __grid_constant__ BnTrainArgs t) {
     pdl_sync();
     const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
     const long long S = (long long)gridDim.x * R;
@@ -248,12 +248,49 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// SyncBN exchange halves of the two backward kernels (several ranks, GS_SYNCBN_FOLD=2).  Out of line on purpose: they run
+// once per kernel, and inlined they changed the load scheduling of the streaming loops (fewer loads in flight: the
+// reduction kernels got 20 % slower on a single rank).
+// ------------------------------------------------------------------------------------------------
+// send half: the last block to finish sees the rank's final sums and pushes them to the peers, so the NVLink flight
+// overlaps this kernel's tail and the launch of gs_bn_bwd_apply (which polls)
+__device__ __noinline__ void bn_reduce_push_tail(const SyncArgs& sync, const double* sums, int C, unsigned long long* ticket) {
+    __shared__ unsigned int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1ull) + 1 == static_cast<unsigned long long>(gridDim.x)) ? 1u : 0u;
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        syncbn_push_block(sums, 2 * C, sync.peers, sync.rank, sync.world, sync.seq_dev, threadIdx.x, blockDim.x);
+    }
+}
+// receive half: block 0 adds the parameter gradients from the LOCAL sums, polls the peers' contributions, writes the group
+// sums in place and releases the other blocks
+__device__ __noinline__ void bn_apply_poll_head(const SyncArgs& sync, double* sums, int C, float* dgamma, float* dbeta,
+                                                unsigned long long* flag) {
+    if (blockIdx.x == 0) {
+        syncbn_exchange_block(sums, 2 * C, sync.peers, sync.rank, sync.world, sync.seq_dev, dgamma, dbeta, sync.timeout_ns,
+                              threadIdx.x, blockDim.x, sync.phase != 2);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_gpu(flag, 1ull);
+    } else {
+        if (threadIdx.x == 0) {
+            while (ld_acquire_gpu(flag) == 0ull) {}
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward pass 1: per-channel sums of g and g*xhat, g = dz * [z > 0]
 // ------------------------------------------------------------------------------------------------
 // MASK: 0 = no activation, 1 = ReLU mask from the stored output z (needed when a residual was added),
 //       2 = ReLU mask recomputed from y: [fma(y, scale, shift) > 0] -- bit-identical to the forward's test and one
 //           tensor read cheaper.
-template <int MASK>
+// SYNC: several ranks with the split exchange (the single-rank instantiation carries no exchange code at all)
+template <int MASK, bool SYNC>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restrict__ dz, long long dz_ld8,
                                                             const uint4* __restrict__ y, long long y_ld8,
                                                             const uint4* __restrict__ z, long long z_ld8,
@@ -262,11 +299,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift, long long P, int C,
                                                             int C8, int Vc, int R, double* __restrict__ sums,
-                                                            SyncArgs sync, unsigned long long* __restrict__ ticket) {
+                                                            const __grid_constant__ SyncArgs sync,
+                                                            unsigned long long* __restrict__ ticket) {
     pdl_sync();
     constexpr bool HAS_Z = (MASK == 1);
     __shared__ float red[256 * 16];
-    __shared__ unsigned int is_last;
     const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
     const long long S = (long long)gridDim.x * R;
     for (int cv0 = 0; cv0 < C8; cv0 += Vc) {
@@ -321,24 +358,13 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
         }
         block_reduce16_atomic(sg, sx, red, Vc, R, cv0, C8, C, sums);
     }
-    if (sync.world > 1 && sync.phase == 1) {
-        // send half of the SyncBN exchange: the last block to finish sees the rank's final sums and pushes them to the
-        // peers, so the NVLink flight overlaps this kernel's tail and the launch of gs_bn_bwd_apply (which polls)
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1ull) + 1 == static_cast<unsigned long long>(gridDim.x)) ? 1u : 0u;
-        __syncthreads();
-        if (is_last) {
-            __threadfence();
-            syncbn_push_block(sums, 2 * C, sync.peers, sync.rank, sync.world, sync.seq_dev, threadIdx.x, blockDim.x);
-        }
-    }
+    if (SYNC) bn_reduce_push_tail(sync, sums, C, ticket);
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward pass 2: dy = gamma*invstd*( g - sum_g/count - xhat*sum_gx/count ); dres = g
 // ------------------------------------------------------------------------------------------------
-template <int MASK, bool HAS_DRES>
+template <int MASK, bool HAS_DRES, bool SYNC>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ dz, long long dz_ld8,
                                                            const uint4* __restrict__ y, long long y_ld8,
                                                            const uint4* __restrict__ z, long long z_ld8,
@@ -352,27 +378,17 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
                                                            uint4* __restrict__ dy, long long dy_ld8,
                                                            uint4* __restrict__ dres, long long dres_ld8,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           SyncArgs sync, unsigned long long* __restrict__ flag) {
+                                                           const __grid_constant__ SyncArgs sync,
+                                                           unsigned long long* __restrict__ flag) {
     pdl_sync();
     constexpr bool HAS_Z = (MASK == 1);
     const int cx = threadIdx.x % Vc, ry = threadIdx.x / Vc;
     const long long S = (long long)gridDim.x * R;
-    if (sync.world > 1) {
+    if (SYNC) {
         // several ranks: `sums` holds the LOCAL sums and gs_bn_bwd_reduce's last block has pushed them.  Block 0 adds
         // the parameter gradients from the local sums, polls the peers' contributions, writes the group sums in place
         // and releases the other blocks (no exchange launch between the two passes).
-        if (blockIdx.x == 0) {
-            syncbn_exchange_block(const_cast<double*>(sums), 2 * C, sync.peers, sync.rank, sync.world, sync.seq_dev, dgamma,
-                                  dbeta, sync.timeout_ns, threadIdx.x, blockDim.x, sync.phase != 2);
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) st_release_gpu(flag, 1ull);
-        } else {
-            if (threadIdx.x == 0) {
-                while (ld_acquire_gpu(flag) == 0ull) {}
-            }
-            __syncthreads();
-        }
+        bn_apply_poll_head(sync, const_cast<double*>(sums), C, dgamma, dbeta, flag);
         dgamma = nullptr;
         dbeta = nullptr;
     }
@@ -387,8 +403,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
             const float g = gamma ? __ldg(gamma + c) : 1.f;
             k0[i] = g * is[i];                                               // gamma * invstd
             // (several ranks: block 0 has just rewritten the sums -> read them through L2)
-            k1[i] = static_cast<float>((sync.world > 1 ? __ldcg(sums + c) : sums[c]) * inv_count);           // mean of g
-            k2[i] = static_cast<float>((sync.world > 1 ? __ldcg(sums + C + c) : sums[C + c]) * inv_count);   // mean of g*xhat
+            k1[i] = static_cast<float>((SYNC ? __ldcg(sums + c) : sums[c]) * inv_count);           // mean of g
+            k2[i] = static_cast<float>((SYNC ? __ldcg(sums + C + c) : sums[C + c]) * inv_count);   // mean of g*xhat
             if (blockIdx.x == 0 && ry == 0) {   // parameter gradients (single-rank case: local sums == group sums)
                 if (dgamma) dgamma[c] += static_cast<float>(sums[C + c]);
                 if (dbeta) dbeta[c] += static_cast<float>(sums[c]);
@@ -479,7 +495,8 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const uint4* __res
                                                            uint4* __restrict__ dy, long long dy_ld8,
                                                            uint4* __restrict__ dres, long long dres_ld8,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           SyncArgs sync, unsigned long long* __restrict__ scratch) {
+                                                           const __grid_constant__ SyncArgs sync,
+                                                           unsigned long long* __restrict__ scratch) {
     pdl_sync();
     constexpr bool HAS_Z = (MASK == 1);
     __shared__ float red[256 * 8];
@@ -691,7 +708,8 @@ __global__ void __launch_bounds__(512) bn_bwd_cluster_kernel(const uint4* __rest
                                                              long long P, int C, int C8, int Vc, uint4* __restrict__ dy,
                                                              long long dy_ld8, uint4* __restrict__ dres,
                                                              long long dres_ld8, float* __restrict__ dgamma,
-                                                             float* __restrict__ dbeta, SyncArgs sync,
+                                                             float* __restrict__ dbeta,
+                                                             const __grid_constant__ SyncArgs sync,
                                                              unsigned long long* __restrict__ scratch) {
     pdl_sync();
     constexpr bool HAS_Z = (MASK == 1);
@@ -1102,7 +1120,7 @@ extern "C" int gs_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* y, in
                "bn_bwd_reduce: sync descriptor must have phase == 1 and C <= %d", kCommSlotDoubles / 2);
     unsigned long long* ticket = reinterpret_cast<unsigned long long*>(sums + 2 * C);   // first scratch word behind the sums
 #define GS_BWD_REDUCE(MK)                                                                                            \
-    gs::launch(bn_bwd_reduce_kernel<MK>, dim3(grid), dim3(m.threads), 0, st,                                                             \
+    gs::launch(sa.world > 1 ? bn_bwd_reduce_kernel<MK, true> : bn_bwd_reduce_kernel<MK, false>, dim3(grid), dim3(m.threads), 0, st, \
         reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8,                  \
         reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, scale, shift, P, C, m.C8, m.Vc, m.R, sums, sa, ticket)
     if (mask == 0) GS_BWD_REDUCE(0);
@@ -1137,7 +1155,7 @@ extern "C" int gs_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* y, int
     // second scratch word behind the sums: "group sums final" flag (zero on entry)
     unsigned long long* flag = reinterpret_cast<unsigned long long*>(const_cast<double*>(sums) + 2 * C) + 1;
 #define GS_BWD_APPLY(MK, HD)                                                                                         \
-    gs::launch(bn_bwd_apply_kernel<MK, HD>, dim3(grid), dim3(m.threads), 0, st,                                                          \
+    gs::launch(sa.world > 1 ? bn_bwd_apply_kernel<MK, HD, true> : bn_bwd_apply_kernel<MK, HD, false>, dim3(grid), dim3(m.threads), 0, st, \
         reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8,                  \
         reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, scale, shift, gamma, sums, inv_count, P, C, m.C8, \
         m.Vc, m.R, reinterpret_cast<uint4*>(dy), dy_ld / 8, reinterpret_cast<uint4*>(dres), dres_ld / 8, dgamma, dbeta, \

@@ -382,7 +382,9 @@ FUSED_BN_MAX_BYTES = float(os.environ.get('GS_BN_FUSED_MAX_MB', '24')) * 1e6
 #   2  SPLIT: the producer kernel (conv forward / BN-backward reduction) pushes the final local sums from its last block --
 #      compute and the send half of the collective in one kernel -- and the consumer (BN apply / BN-backward apply) polls:
 #      no exchange launch, and the NVLink flight overlaps the producer's tail and the consumer's launch.
-FOLD_EXCHANGE = int(os.environ.get('GS_SYNCBN_FOLD', '2'))
+# Default 0 -- MEASURED (profiles/r02_experiments.md, N = 2): 0 -> 59.0 ms, 1 -> 58.6-60 ms, 2 -> 64.6 ms per cycle: the
+# fences + ticket at the tail of every producer and the flag wait of every consumer block cost more than the launch saved.
+FOLD_EXCHANGE = int(os.environ.get('GS_SYNCBN_FOLD', '0'))
 
 
 def bn_batch_mode(bn):
@@ -869,21 +871,46 @@ class ConvBnActFn(torch.autograd.Function):
     conv weight) by the kernels; autograd only routes activation gradients."""
 
     @staticmethod
-    def forward(ctx, x, residual, weight, conv, bn, relu, Co):
+    def forward(ctx, x, residual, weight, conv, bn, relu, Co, carrier=None):
         save = any(ctx.needs_input_grad)
         z, rec = cba_forward(x, conv, bn, relu, residual, Co, save=save)
-        ctx.rec = rec
+        ctx.rec, ctx.carrier = rec, carrier
         return z
 
     @staticmethod
     def backward(ctx, dz):
-        dx, dres = cba_backward(ctx.rec, dz, need_dx=ctx.needs_input_grad[0])
-        ctx.rec = None
-        return dx, dres, None, None, None, None, None
+        # a second consumer of x (the skip branch of a concat, see GradCarrier) hands its gradient over here: it is summed
+        # in the dgrad epilogue instead of by a separate strided add pass of the autograd engine
+        add = ctx.carrier.take() if ctx.carrier is not None else None
+        need_dx = ctx.needs_input_grad[0]
+        dx, dres = cba_backward(ctx.rec, dz, need_dx=need_dx, dx_add=add if need_dx else None)
+        ctx.rec = ctx.carrier = None
+        return dx, dres, None, None, None, None, None, None
 
 
-def conv_bn_act(x, conv, bn=None, relu=False, residual=None, Co=None):
-    return ConvBnActFn.apply(x, residual, conv.weight, conv, bn, relu, Co)
+SKIP_GRAD_CARRIER = os.environ.get('GS_SKIP_CARRIER', '1') != '0'   # 0: let autograd add the two gradients (A/B, tests)
+
+
+class GradCarrier:
+    """Side channel for the gradient of a tensor x that feeds BOTH a conv layer and a channel concat (FCN head with
+    concat_input, fcn_head.py:68-81): the concat's backward deposits its channel-slice VIEW of the incoming gradient here
+    instead of returning it, and the conv layer's backward -- which by data dependency runs later -- adds it inside its
+    dgrad epilogue.  Saves autograd's accumulation pass over two differently-pitched [N, C, H, W] tensors."""
+    __slots__ = ('g',)
+
+    def __init__(self):
+        self.g = None
+
+    def put(self, g):
+        self.g = g
+
+    def take(self):
+        g, self.g = self.g, None
+        return g
+
+
+def conv_bn_act(x, conv, bn=None, relu=False, residual=None, Co=None, grad_carrier=None):
+    return ConvBnActFn.apply(x, residual, conv.weight, conv, bn, relu, Co, grad_carrier)
 
 
 class BottleneckFn(torch.autograd.Function):
@@ -1009,7 +1036,7 @@ class CatFn(torch.autograd.Function):
     VIEWS of the incoming gradient (the kernels take pitches), i.e. free."""
 
     @staticmethod
-    def forward(ctx, *xs):
+    def forward(ctx, carrier, *xs):
         xs = [as_act(x) for x in xs]
         N, _, H, W = xs[0].shape
         Cs = [x.shape[1] for x in xs]
@@ -1018,7 +1045,7 @@ class CatFn(torch.autograd.Function):
         for x, C in zip(xs, Cs):
             call('gs_copy_channels', x.data_ptr(), act_ld(x), out[:, off:off + C].data_ptr(), sum(Cs), P, C, st)
             off += C
-        ctx.Cs = Cs
+        ctx.Cs, ctx.carrier = Cs, carrier
         return out
 
     @staticmethod
@@ -1028,11 +1055,16 @@ class CatFn(torch.autograd.Function):
         for C in ctx.Cs:
             outs.append(d[:, off:off + C])
             off += C
-        return tuple(outs)
+        if ctx.carrier is not None and ctx.needs_input_grad[1]:
+            ctx.carrier.put(outs[0])          # picked up by the conv layer that also consumes xs[0] (GradCarrier)
+            outs[0] = None
+        ctx.carrier = None
+        return (None,) + tuple(outs)
 
 
-def cat_channels(xs):
-    return CatFn.apply(*xs)
+def cat_channels(xs, skip_carrier=None):
+    """Channel concat.  skip_carrier: see GradCarrier -- xs[0]'s gradient goes through the carrier instead of autograd."""
+    return CatFn.apply(skip_carrier, *xs)
 
 
 # parity tests inject the Bernoulli draw here: callable(N, C, keep, device) -> fp32 [N, C] mask with values in

@@ -7,6 +7,7 @@ reference semantics -- bilinear resize of the logits to the label size (align_co
 ignore_index averaged over ALL pixels times loss_weight, and top-1 accuracy over all pixels -- but runs them
 as ONE fused kernel pair on the low-resolution logits (gaia_seg_b200.functional.upsample_ce).
 """
+import torch
 import torch.nn as nn
 
 from . import functional as F_gs
@@ -117,9 +118,18 @@ class DynamicFCNHead(FCNHead, DynamicMixin):
 
     def forward(self, inputs):
         x = self._transform_inputs(inputs)
-        output = self.convs(x)
+        carrier = None
+        if (self.concat_input and self.num_convs > 0 and F_gs.SKIP_GRAD_CARRIER and torch.is_grad_enabled()
+                and x.requires_grad):
+            # x feeds convs[0] AND the concat: the concat's share of dL/dx is added inside convs[0]'s dgrad epilogue
+            carrier = F_gs.GradCarrier()
+            output = self.convs[0](x, grad_carrier=carrier)
+            for m in list(self.convs)[1:]:
+                output = m(output)
+        else:
+            output = self.convs(x)
         if self.concat_input:
-            output = self.conv_cat(F_gs.cat_channels([x, output]))
+            output = self.conv_cat(F_gs.cat_channels([x, output], skip_carrier=carrier))
         return self.cls_seg(output)
 
     def forward_train(self, inputs, img_metas, gt_semantic_seg, train_cfg, **kwargs):

@@ -717,3 +717,50 @@ def bn_bwd_one_pass_checks(gs):
     finally:
         Fg.FUSED_BN_BWD = saved
     return out
+
+
+def fcn_head_skip_gradient_checks(gs):
+    """FCN head with concat_input (fcn_head.py:68-81): x feeds convs[0] AND the concat.  The product path adds the concat's
+    share of dL/dx inside convs[0]'s dgrad epilogue (functional.GradCarrier); it must equal autograd's own accumulation of
+    the two gradients (same kernels, GS_SKIP_CARRIER=0 behaviour) and the fp32 oracle head."""
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    out = []
+    for num_convs in (1, 2):
+        torch.manual_seed(11 + num_convs)
+        kw = dict(in_channels=48, channels=32, num_classes=19, num_convs=num_convs, concat_input=True, dropout_ratio=0.0,
+                  conv_cfg=dict(type='DynConv2d'), norm_cfg=dict(type='DynBN', requires_grad=True), in_index=0)
+        oh = O.DynamicFCNHead(**kw)
+        C.randomize(oh, seed=3)
+        head = gs.DynamicFCNHead(**kw)
+        head.load_state_dict(oh.state_dict(), strict=True)
+        head = head.to(dev).train()
+        x = bf16r(torch.randn(2, 48, 12, 20))
+        dz = bf16r(torch.randn(2, 19, 12, 20))
+        grads = {}
+        saved = Fg.SKIP_GRAD_CARRIER
+        try:
+            for mode in (True, False):
+                Fg.SKIP_GRAD_CARRIER = mode
+                head.zero_grad(set_to_none=True)
+                xg = Fg.as_act(x.to(dev)).requires_grad_(True)
+                y = head.forward([xg])
+                y.backward(dz.to(dev).to(y.dtype).contiguous(memory_format=torch.channels_last))
+                Fg.wgrad_join()
+                torch.cuda.synchronize()
+                grads[mode] = (xg.grad.float().cpu(), {n: p.grad.float().cpu().clone() for n, p in head.named_parameters()
+                                                       if p.grad is not None})
+        finally:
+            Fg.SKIP_GRAD_CARRIER = saved
+        tag = f'fcn_head_skip[num_convs={num_convs}]'
+        out.append(check_bf16(grads[True][0], grads[False][0], tag + '.dx_carrier_vs_autograd_sum', 3.0))
+        worst = max(float((grads[True][1][n] - g).abs().max()) for n, g in grads[False][1].items())
+        out.append(dict(name=tag + '.param_grads_identical', ok=worst == 0.0, err=worst, tol=0))
+        # fp32 oracle head on the same parameters
+        oh.train()
+        xo = x.clone().requires_grad_(True)
+        oh.forward([xo]).backward(dz)
+        # (fp32 oracle without bf16 storage between the 2-3 conv + train-mode-BN layers: judged in relative L2 -- 0.08 is
+        #  1 - cos of 3e-3, the stage tests' bound; a lost skip gradient would show as > 0.5)
+        out.append(rel_l2(grads[True][0], xo.grad, 8e-2, tag + '.dx_vs_oracle_rel_l2'))
+    return out

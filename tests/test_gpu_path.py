@@ -47,6 +47,10 @@ def test_bn_backward_one_pass_and_two_kernels(gs):
     _assert_all(P.bn_bwd_one_pass_checks(gs))
 
 
+def test_fcn_head_skip_gradient_in_dgrad_epilogue(gs):
+    _assert_all(P.fcn_head_skip_gradient_checks(gs))
+
+
 def test_wide_tile_epilogue(gs):
     _assert_all(P.wide_tile_epilogue_checks(gs))
 
