@@ -1,10 +1,6 @@
-export GS_COMM_TIMEOUT_S=60
-N=${N:-2}
-python -m pytest tests -m gpu -q -p no:cacheprovider -x 2>&1 | tail -3 | cut -c 1-700
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-run() { env "$@" timeout 300 $TR bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline --no-infer --no-profile > gpurun_out/tmpN.json 2> gpurun_out/tmpN.err; tail -1 gpurun_out/tmpN.json | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('$*', round(d['value'],1), round(d['ms_per_step'],2), (d.get('parity_multi') or {}).get('ok'))" || tail -5 gpurun_out/tmpN.err; }
-run GS_PDL=30
-run GS_PDL=14
-run GS_PDL=6
-run GS_PDL=30
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_path.py -m gpu -q -p no:cacheprovider -x -k "conv or stage or model or full" 2>&1 | tail -3 | cut -c 1-700
+for d in 0 1; do GS_IGEMM_DEEP_RING=$d python tools/conv_trace.py 64,128,96,96,3,1,1 64,128,384,96,1,1,1 128,256,64,64,3,1,1 256,512,32,32,3,1,1 64,128,192,192,3,2,1 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('deep=$d', d['shape'], 'last_epi_ns', d['last_epi_ns'], 'cold_us', d['cold_us'])"; done
