@@ -29,7 +29,8 @@ unsigned long long comm_timeout_ns();
 // the tail of kernel i on the same stream (~1050 conv + ~1100 BN launches of 10-40 us per sandwich cycle), while
 // griddepcontrol.wait still orders every global-memory access after the COMPLETION of all earlier kernels -- the
 // semantics of a plain stream are unchanged.  Legal inside captured CUDA graphs (programmatic edges).  GS_PDL=0 disables it.
-// GS_PDL is a bit mask: 1 = memory-bound kernels, 2 = igemm (conv fwd / dgrad), 4 = wgrad, 8 = the one-block SyncBN
+// GS_PDL is a bit mask: 1 = memory-bound kernels (except the three DynBN training kernels, which have their own bits:
+// 16 = BN apply forward, 32 = BN-backward reduce, 64 = BN-backward apply), 2 = igemm (conv fwd / dgrad), 4 = wgrad, 8 = the one-block SyncBN
 // exchange kernel (several ranks; its block is dispatched while the producer of the sums still runs: 57.3 -> 55.7 ms per
 // cycle at N = 2).  Default 14, MEASURED on the
 // sandwich cycle (profiles/r02_pdl_sweep.md): early-scheduled blocks of the memory-bound kernels take the scheduling gaps

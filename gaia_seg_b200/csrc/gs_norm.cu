@@ -1090,11 +1090,11 @@ extern "C" int gs_bn_apply_train(const void* y, int32_t y_ld, const double* stat
         t.flag = reinterpret_cast<unsigned long long*>(const_cast<double*>(stats) + 2 * C) + 1;
     }
     if (residual)
-        gs::launch(bn_apply_kernel<true, true>, dim3(grid), dim3(m.threads), 0, st, 
+        gs::launch<16>(bn_apply_kernel<true, true>, dim3(grid), dim3(m.threads), 0, st, 
             reinterpret_cast<const uint4*>(y), y_ld / 8, nullptr, nullptr, reinterpret_cast<const uint4*>(residual),
             res_ld / 8, relu, reinterpret_cast<uint4*>(z), z_ld / 8, P, m.C8, m.Vc, m.R, t);
     else
-        gs::launch(bn_apply_kernel<false, true>, dim3(grid), dim3(m.threads), 0, st, 
+        gs::launch<16>(bn_apply_kernel<false, true>, dim3(grid), dim3(m.threads), 0, st, 
             reinterpret_cast<const uint4*>(y), y_ld / 8, nullptr, nullptr, nullptr, 0, relu,
             reinterpret_cast<uint4*>(z), z_ld / 8, P, m.C8, m.Vc, m.R, t);
     GS_LAUNCHED();
@@ -1120,7 +1120,7 @@ extern "C" int gs_bn_bwd_reduce(const void* dz, int32_t dz_ld, const void* y, in
                "bn_bwd_reduce: sync descriptor must have phase == 1 and C <= %d", kCommSlotDoubles / 2);
     unsigned long long* ticket = reinterpret_cast<unsigned long long*>(sums + 2 * C);   // first scratch word behind the sums
 #define GS_BWD_REDUCE(MK)                                                                                            \
-    gs::launch(sa.world > 1 ? bn_bwd_reduce_kernel<MK, true> : bn_bwd_reduce_kernel<MK, false>, dim3(grid), dim3(m.threads), 0, st, \
+    gs::launch<32>(sa.world > 1 ? bn_bwd_reduce_kernel<MK, true> : bn_bwd_reduce_kernel<MK, false>, dim3(grid), dim3(m.threads), 0, st, \
         reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8,                  \
         reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, scale, shift, P, C, m.C8, m.Vc, m.R, sums, sa, ticket)
     if (mask == 0) GS_BWD_REDUCE(0);
@@ -1155,7 +1155,7 @@ extern "C" int gs_bn_bwd_apply(const void* dz, int32_t dz_ld, const void* y, int
     // second scratch word behind the sums: "group sums final" flag (zero on entry)
     unsigned long long* flag = reinterpret_cast<unsigned long long*>(const_cast<double*>(sums) + 2 * C) + 1;
 #define GS_BWD_APPLY(MK, HD)                                                                                         \
-    gs::launch(sa.world > 1 ? bn_bwd_apply_kernel<MK, HD, true> : bn_bwd_apply_kernel<MK, HD, false>, dim3(grid), dim3(m.threads), 0, st, \
+    gs::launch<64>(sa.world > 1 ? bn_bwd_apply_kernel<MK, HD, true> : bn_bwd_apply_kernel<MK, HD, false>, dim3(grid), dim3(m.threads), 0, st, \
         reinterpret_cast<const uint4*>(dz), dz_ld / 8, reinterpret_cast<const uint4*>(y), y_ld / 8,                  \
         reinterpret_cast<const uint4*>(z), z_ld / 8, mean, invstd, scale, shift, gamma, sums, inv_count, P, C, m.C8, \
         m.Vc, m.R, reinterpret_cast<uint4*>(dy), dy_ld / 8, reinterpret_cast<uint4*>(dres), dres_ld / 8, dgamma, dbeta, \
