@@ -11,10 +11,15 @@
 //                                  N = up to 256 output channels, accumulators double-buffered
 //                                  in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
 //                                  the main loop of tile i+1.
-//       warps 2-5 epilogue      -- tcgen05.ld -> affine / residual / ReLU -> bf16 -> swizzled smem
-//                                  staging -> TMA store; per-channel sum / sum^2 (DynBN batch
-//                                  statistics) from the staged tile -> fp64 atomics.
-//   wgrad_kernel : weight gradient, split-K over pixels, both operands MN-major (pixels are K).
+//       warps 2-17 epilogue     -- 4 sub-tile groups x 4 TMEM sub-partitions: tcgen05.ld -> affine /
+//                                  residual / ReLU -> bf16 -> swizzled smem staging -> TMA store;
+//                                  per-channel sum / sum^2 (DynBN batch statistics) from the staged
+//                                  tile, kept in registers across the CTA's tiles -> fp64 atomics.
+//       Instantiations: <1> one CTA per tile (short K loops), <2, false> CTA pairs (cta_group::2,
+//       M = 256, half of the weight tile per CTA), <2, true> pairs with one 320 / 384-column
+//       accumulator (wide n-tiles).  Launched with programmatic dependent launch (gs_host.h).
+//   wgrad_kernel : weight gradient, stream-K over (item, 64-pixel chunk), both operands MN-major
+//       (pixels are K), fp32 red.global.add into the active prefix of the flat gradient.
 //
 // GEMM view (forward):  Y[pix, co] = sum_{r,s,ci} X[pix shifted by (r,s), ci] * W[co, r, s, ci]
 #include <cuda_bf16.h>

@@ -6,9 +6,10 @@
 //   forward : one thread per OUTPUT pixel, 4-tap lerp of the K low-res logits on the fly, online
 //             soft-max (max / sum-exp / first arg-max in one sweep); writes an 8-byte record
 //             (log-sum-exp, label or -1) per pixel for the backward pass.
-//   backward: GATHER form, one thread per (low-res cell, class): walks the output pixels whose taps
-//             touch the cell, re-interpolates its class logit, p = exp(v - lse) and accumulates
-//             w * (p - [label == k]).  No atomics, deterministic.
+//   backward: one CTA per TILE of low-res cells (all classes), the only writer of its dlogits: the
+//             soft-max terms of every output pixel are computed once per CTA, the bilinear weights are
+//             applied separably through shared memory, one coalesced store.  No atomics,
+//             deterministic (details at the kernel below).
 // Source-index arithmetic is ATen's area_pixel_compute_source_index (align_corners = False), fp32.
 //
 // Algorithmic bytes per call: logits N*h*w*K*4 (read) + labels N*H*W*8 (read) + records N*H*W*8
