@@ -59,6 +59,7 @@ PROTOTYPES = {
     'gs_debug_set_trace': (_I, [_P]),
     'gs_conv2d_fwd': (_I, [_G, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     'gs_conv2d_fwd_syncbn': (_I, [_G, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    'gs_conv2d_fwd_bn': (_I, [_G, _P, _P, _P, _P, _P, _D, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _P, _I, _P]),
     'gs_conv2d_dgrad_workspace_bytes': (_L, [_G]),
     'gs_conv2d_dgrad': (_I, [_G, _P, _P, _P, _P, _I, _P, _P, _P]),
     'gs_conv2d_wgrad': (_I, [_G, _P, _P, _P, _P]),

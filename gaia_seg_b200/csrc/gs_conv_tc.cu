@@ -103,7 +103,193 @@ struct IgemmParams {
     // apply kernel polls.  sync_ticket: zero-initialised 64-bit word counting the CTAs that have flushed.
     SyncArgs sync;
     unsigned long long* sync_ticket;
+    // Fused DynBN apply (training forward, gs_conv2d_fwd_bn): after its last tile every CTA flushes its statistics, the
+    // persistent grid meets at ONE barrier (all CTAs are co-resident by construction: grid <= SM count, one CTA per SM),
+    // and each CTA normalises the tiles IT has just written -- y comes back from L2, z = relu?(y * scale + shift (+ res))
+    // is written once -- so the training forward of a conv + BN layer is one launch instead of two.
+    struct BnTail {
+        int on;
+        int relu;
+        double inv_count, unbias;
+        const float* gamma;
+        const float* beta;
+        float* rm;
+        float* rv;
+        float momentum, eps;
+        float* aff;                       // [4][C]: mean, invstd, scale, shift (for the backward pass)
+        const __nv_bfloat16* res;         // residual added AFTER the normalisation (bn3 of a bottleneck), may be NULL
+        long long res_ld;
+        __nv_bfloat16* z;
+        long long z_ld;
+        unsigned long long* barrier;      // zero-initialised arrival counter (first scratch word behind the sums)
+        unsigned long long timeout_ns;
+        int tw_shift;                     // log2(TW)
+    } bn;
 };
+
+__device__ __forceinline__ uint4 ld_cg_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_na_v4(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// The tail of gs_conv2d_fwd_bn, run by the 512 epilogue threads (e = 0..511) after the statistic flush.  Out of line: it
+// runs once per kernel and must not cost the main loop any registers.
+// Thread map: the n-tile has V = n_valid / 8 channel vectors; thread (cx = e % V, ry = e / V) owns vector cx (its scale /
+// shift stay in registers) and the pixel rows ry, ry + R, ... of every tile of the CTA -- a warp touches whole pixel rows
+// (V * 16 contiguous bytes).  The (tile, row) slots of a thread are walked as ONE stream through a rolling window of W
+// register buffers: a slot is refilled as soon as it has been consumed, so W 16-byte loads per tensor stay in flight per
+// thread across tile boundaries (with one CTA per SM nothing else hides the L2 latency), and the first window is issued
+// BEFORE the grid barrier -- the CTA's own tiles are complete by then.
+template <int CG, bool HAS_RES>
+__device__ __noinline__ void ig_bn_tail(const IgemmParams& p, int mu0, int groups, int m_units, int rank, int nt,
+                                        uint8_t* staging) {
+    constexpr int W = HAS_RES ? 4 : 8;
+    const int e = static_cast<int>(threadIdx.x) - 64;
+    const int n0 = nt * p.nt_w;
+    int n_valid = p.Cout - n0;
+    if (n_valid > p.nt_w) n_valid = p.nt_w;
+    const int V = n_valid >> 3;
+    const int R = 512 / V;
+    const int cx = e % V, ry = e / V;
+    const int c0 = n0 + cx * 8;
+    const int rpt = (128 + R - 1) / R;                                   // row slots per tile and thread
+    const int my_tiles = mu0 < m_units ? (m_units - mu0 + groups - 1) / groups : 0;
+    const int S = ry < R ? my_tiles * rpt : 0;                           // slots of this thread
+    const int tiles_hw = p.tiles_h * p.tiles_w;
+    const int tw_mask = p.TW - 1;
+    const __nv_bfloat16* const ybase = reinterpret_cast<const __nv_bfloat16*>(p.out) + c0;
+    const __nv_bfloat16* const rbase = p.bn.res + c0;
+    __nv_bfloat16* const zbase = p.bn.z + c0;
+    // slot cursor (slots are visited strictly in order)
+    int it_t = 0, it_j = 0, it_img = p.N, it_h0 = 0, it_w0 = 0;
+    auto setup_tile = [&](int t) {
+        const int mu = mu0 + t * groups;
+        it_img = p.N;
+        if (mu >= m_units) return;
+        const int mt = mu * CG + rank;
+        const int img = mt / tiles_hw;
+        const int rem = mt - img * tiles_hw;
+        it_img = img;                                                    // (phantom tile of a pair: img == N -> no pixel)
+        it_h0 = (rem / p.tiles_w) * p.TH;
+        it_w0 = (rem % p.tiles_w) * p.TW;
+    };
+    auto next_pix = [&]() -> int {
+        int pix = -1;
+        const int row = ry + it_j * R;
+        const int hh = it_h0 + (row >> p.bn.tw_shift), ww = it_w0 + (row & tw_mask);
+        if (it_img < p.N && row < 128 && hh < p.Ho && ww < p.Wo) pix = (it_img * p.Ho + hh) * p.Wo + ww;
+        if (++it_j == rpt) { it_j = 0; setup_tile(++it_t); }
+        return pix;
+    };
+    uint4 buf[W], rbuf[W];
+    int pixb[W];
+    if (e == 0) trace(208);
+    setup_tile(0);
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+        pixb[u] = u < S ? next_pix() : -1;
+        if (pixb[u] >= 0) {
+            buf[u] = ld_cg_v4(ybase + static_cast<long long>(pixb[u]) * p.out_ld);
+            if (HAS_RES) rbuf[u] = ld_nc_v4(rbase + static_cast<long long>(pixb[u]) * p.bn.res_ld);
+        }
+    }
+    // ---- grid barrier: every CTA's atomics on `stats` are globally visible afterwards
+    if (e == 0) trace(209);
+    __threadfence();
+    named_bar_sync(5, 512);
+    if (e == 0) {
+        trace(210);
+        __threadfence();
+        atomicAdd(p.bn.barrier, 1ull);
+        const unsigned long long want = gridDim.x;
+        const unsigned long long t0 = gtimer();
+        unsigned int spins = 0;
+        while (ld_acquire_gpu(p.bn.barrier) < want) {
+            if ((++spins & 1023u) == 0 && gtimer() - t0 > p.bn.timeout_ns) {
+                printf("gaiaseg_b200: conv + BN grid barrier timed out (CTA %d of %d)\n", static_cast<int>(blockIdx.x),
+                       static_cast<int>(gridDim.x));
+                __trap();
+            }
+        }
+        __threadfence();
+        trace(211);
+    }
+    named_bar_sync(5, 512);
+    // ---- finalize: ONE thread per channel of the n-tile turns the sums into scale / shift (fp64 only where cancellation
+    // can occur) and leaves them in the idle staging buffer; the CTA that owns the first pixel tile also stores them for
+    // the backward pass and updates the running statistics.  (Every thread reading the sums of its own 8 channels made
+    // 148 x 512 x 16 L2 reads of the same few lines: 13 us.)
+    float* const sm = reinterpret_cast<float*>(staging);       // [0, 512): scale, [512, 1024): shift
+    if (e < n_valid) {
+        const int c = n0 + e;
+        const double s1 = __ldcg(p.stats + c);
+        const double s2 = __ldcg(p.stats + p.Cout + c);
+        const double m = s1 * p.bn.inv_count;
+        double var = s2 * p.bn.inv_count - m * m;
+        if (var < 0.0) var = 0.0;
+        const float mf = static_cast<float>(m);
+        const float istd = rsqrtf(static_cast<float>(var) + p.bn.eps);
+        const float g = p.bn.gamma ? __ldg(p.bn.gamma + c) : 1.f;
+        const float b = p.bn.beta ? __ldg(p.bn.beta + c) : 0.f;
+        const float scv = g * istd;
+        const float shv = b - mf * scv;
+        sm[e] = scv;
+        sm[512 + e] = shv;
+        if (mu0 == 0 && rank == 0) {
+            p.bn.aff[c] = mf;
+            p.bn.aff[p.Cout + c] = istd;
+            p.bn.aff[2 * p.Cout + c] = scv;
+            p.bn.aff[3 * p.Cout + c] = shv;
+            if (p.bn.rm) p.bn.rm[c] = (1.f - p.bn.momentum) * p.bn.rm[c] + p.bn.momentum * mf;
+            if (p.bn.rv) p.bn.rv[c] = (1.f - p.bn.momentum) * p.bn.rv[c] + p.bn.momentum * static_cast<float>(var * p.bn.unbias);
+        }
+    }
+    named_bar_sync(5, 512);
+    if (S == 0) return;                       // (no barrier below this point)
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sc[i] = sm[cx * 8 + i];
+        sh[i] = sm[512 + cx * 8 + i];
+    }
+    if (e == 0) trace(212);
+    // ---- normalise: consume a slot, store z, refill the slot with the load W slots ahead
+    for (int base = 0; base < S; base += W) {
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+            if (pixb[u] >= 0) {
+                const uint32_t* w4 = reinterpret_cast<const uint32_t*>(&buf[u]);
+                const uint32_t* r4 = reinterpret_cast<const uint32_t*>(&rbuf[u]);
+                uint4 o;
+                uint32_t* o4 = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a = fmaf(bf16_lo(w4[j]), sc[2 * j], sh[2 * j]);
+                    float b = fmaf(bf16_hi(w4[j]), sc[2 * j + 1], sh[2 * j + 1]);
+                    if (HAS_RES) { a += bf16_lo(r4[j]); b += bf16_hi(r4[j]); }
+                    if (p.bn.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                    o4[j] = pack_bf16x2(a, b);
+                }
+                st_na_v4(zbase + static_cast<long long>(pixb[u]) * p.bn.z_ld, o);
+            }
+            pixb[u] = (base + W + u) < S ? next_pix() : -1;
+            if (pixb[u] >= 0) {
+                buf[u] = ld_cg_v4(ybase + static_cast<long long>(pixb[u]) * p.out_ld);
+                if (HAS_RES) rbuf[u] = ld_nc_v4(rbase + static_cast<long long>(pixb[u]) * p.bn.res_ld);
+            }
+        }
+    }
+    if (e == 0) trace(213);
+}
 
 // Fused send half of the SyncBN all-reduce (several ranks), called by the 512 epilogue threads after their statistic
 // atomics: every CTA fences and takes a ticket; the last one sees the rank's final sums in L2 and stores them into the
@@ -605,6 +791,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 atomicAdd(p.stats + p.Cout + col, static_cast<double>(sq));
             }
             if (p.sync.world > 1) ig_syncbn_push(p, staging);
+            if (p.bn.on) {
+                if (p.bn.res != nullptr) ig_bn_tail<CG, true>(p, mu0, groups, m_units, rank, nt, staging);
+                else ig_bn_tail<CG, false>(p, mu0, groups, m_units, rank, nt, staging);
+            }
         }
     }
 
@@ -638,6 +828,7 @@ struct IgemmLaunch {
     const float* scale; const float* shift; const void* residual; long long res_ld; int relu; double* stats;
     const gs_bn_bwd_fuse* fuse;   // reserved, must be NULL
     const gs_sync_desc* sync;     // forward only: push the final statistics to the SyncBN peers (phase 1)
+    const IgemmParams::BnTail* bn;   // forward only: fused DynBN apply (gs_conv2d_fwd_bn), NULL otherwise
 };
 
 static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
@@ -706,6 +897,17 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     GS_REQUIRE(L.fuse == nullptr, "dgrad: the fused BN-backward reduction was removed (measured slower than gs_bn_bwd_reduce); "
                                   "pass fuse = NULL");
     p.direct = tma_store_ok ? 0 : 1;
+    p.bn = IgemmParams::BnTail{};
+    if (L.bn != nullptr) {
+        GS_REQUIRE(tma_store_ok && L.stats != nullptr, "conv + BN: needs the bf16 TMA-store epilogue (Co %% 8 == 0) and a statistics buffer");
+        GS_REQUIRE(p.sync.world <= 1, "conv + BN: several ranks are not supported by the fused path (use gs_conv2d_fwd_syncbn + gs_bn_apply_train)");
+        p.bn = *L.bn;
+        p.bn.on = 1;
+        p.bn.barrier = reinterpret_cast<unsigned long long*>(L.stats + 2 * L.Cout);
+        p.bn.timeout_ns = 2000000000ull;    // all CTAs are co-resident: 2 s means a bug, trap instead of hanging the GPU
+        p.bn.tw_shift = 0;
+        while ((1 << p.bn.tw_shift) < p.TW) ++p.bn.tw_shift;
+    }
     GS_REQUIRE(!(p.direct && L.stats), "conv: statistics need the bf16 TMA-store epilogue (Co %% 8 == 0)");
     if (L.residual) {
         GS_REQUIRE(L.res_ld % 8 == 0 && L.Cout % 8 == 0 && (reinterpret_cast<uintptr_t>(L.residual) & 15) == 0,
@@ -1202,6 +1404,33 @@ extern "C" int gs_conv2d_fwd_syncbn(const gs_conv_geom* g, const void* x, const 
     L.out = y; L.out_ld = g->y_ld; L.out_f32 = (flags & GS_EPI_OUT_F32) ? 1 : 0;
     L.scale = scale; L.shift = shift; L.residual = residual; L.res_ld = res_ld;
     L.relu = (flags & GS_EPI_RELU) ? 1 : 0; L.stats = stats; L.sync = sync;
+    return launch_igemm(L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gs_conv2d_fwd_bn(const gs_conv_geom* g, const void* x, const void* w_krsc, void* y, const float* shift,
+                                double* stats, double count, const float* gamma, const float* beta, float* running_mean,
+                                float* running_var, float momentum, float eps, float* aff, const void* residual,
+                                int32_t res_ld, int32_t relu, void* z, int32_t z_ld, void* stream) {
+    if (check_geom(g)) return -1;
+    GS_REQUIRE(stats != nullptr && aff != nullptr && z != nullptr && count > 0, "conv + BN: null pointer / empty count");
+    GS_REQUIRE(z_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0, "conv + BN: z must be 16-byte aligned with a pitch multiple of 8");
+    GS_REQUIRE(residual == nullptr || (res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0),
+               "conv + BN: residual must be 16-byte aligned with a pitch multiple of 8");
+    IgemmParams::BnTail bn{};
+    bn.relu = relu ? 1 : 0;
+    bn.inv_count = 1.0 / count;
+    bn.unbias = count > 1.0 ? count / (count - 1.0) : 1.0;
+    bn.gamma = gamma; bn.beta = beta; bn.rm = running_mean; bn.rv = running_var; bn.momentum = momentum; bn.eps = eps;
+    bn.aff = aff;
+    bn.res = reinterpret_cast<const __nv_bfloat16*>(residual); bn.res_ld = res_ld;
+    bn.z = reinterpret_cast<__nv_bfloat16*>(z); bn.z_ld = z_ld;
+    IgemmLaunch L{};
+    L.a_ptr = x; L.a_C = g->Ci; L.a_ld = g->x_ld; L.a_H = g->H; L.a_W = g->W; L.a_estride = g->stride;
+    L.b_ptr = w_krsc; L.b_rows_max = g->Co_max; L.b_cols_max = g->Ci_max;
+    L.N = g->N; L.Ho = g->Ho; L.Wo = g->Wo; L.Cout = g->Co; L.Kc = g->Ci; L.kh = g->kh; L.kw = g->kw;
+    L.in_mul = g->stride; L.base = -g->pad; L.step = g->dil;
+    L.out = y; L.out_ld = g->y_ld; L.out_f32 = 0;
+    L.shift = shift; L.stats = stats; L.bn = &bn;
     return launch_igemm(L, static_cast<cudaStream_t>(stream));
 }
 

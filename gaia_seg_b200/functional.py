@@ -261,9 +261,21 @@ def _geom(N, H, W, Ci, Co, Ci_max, Co_max, kh, kw, stride, pad, dil, x_ld, y_ld)
     return ConvGeom(N, H, W, Ho, Wo, Ci, Co, Ci_max, Co_max, kh, kw, stride, pad, dil, x_ld, y_ld)
 
 
-def conv_forward(x, conv, Co, scale=None, shift=None, residual=None, relu=False, out_f32=False, want_stats=False, sync=None):
+# GS_CONV_BN_FUSE=1: training forward of conv -> DynBN (-> + residual) (-> ReLU) on a single rank is ONE launch
+# (gs_conv2d_fwd_bn: the persistent conv grid meets at a barrier after its statistic flush and normalises the tiles it has
+# just written); 0 (default): conv kernel + gs_bn_apply_train.  Parity-tested (tests/test_gpu_path.py::
+# test_conv_bn_one_launch_equals_two_kernels) and MEASURED SLOWER (profiles/r02_experiments.md: 53.2 vs 50.2 ms per cycle): with
+# one 576-thread CTA per SM and the shared memory taken by the operand ring the in-kernel apply pass streams at ~2.3-4 TB/s,
+# and flush -> barrier -> finalize cost ~6 us -- more than the launch they replace.  Several ranks always take the two-kernel
+# path (the statistic exchange sits between the two).
+CONV_BN_FUSE = os.environ.get('GS_CONV_BN_FUSE', '0') != '0'
+
+
+def conv_forward(x, conv, Co, scale=None, shift=None, residual=None, relu=False, out_f32=False, want_stats=False, sync=None,
+                 fuse_bn=None):
     """y = epi(conv(x, W[:Co, :Ci])).  Returns (y, stats, a_operand, geom): `a_operand` is the tensor the
-    weight gradient must be taken against (x itself, or the im2col matrix of the image conv)."""
+    weight gradient must be taken against (x itself, or the im2col matrix of the image conv).
+    fuse_bn = dict(bn=, residual=, relu=): the fused conv + DynBN apply launch; the dict receives z / aff / count."""
     _lib.require_device()
     krsc = conv_shadows(conv)
     kh, kw, stride, pad, dil = _conv_attrs(conv)
@@ -305,7 +317,29 @@ def conv_forward(x, conv, Co, scale=None, shift=None, residual=None, relu=False,
     if residual is not None:
         residual = as_act(residual)
         res_ld = act_ld(residual)
-    if sync is not None:     # several ranks: the conv kernel's last CTA pushes the statistics to the SyncBN peers
+    if fuse_bn is not None:
+        bn, bres = fuse_bn['bn'], fuse_bn['residual']
+        count = float(N * g.Ho * g.Wo)
+        aff = torch.empty((4, Co), dtype=torch.float32, device=dev)
+        upd = bn.training and bn.track_running_stats and bn.running_mean is not None
+        if upd and bn.momentum is None:
+            raise GsError('DynamicBatchNorm2d: momentum=None (cumulative average) is not supported on the CUDA path')
+        z = new_act(N, Co, g.Ho, g.Wo, dev)
+        bres_ld = 0
+        if bres is not None:
+            bres = as_act(bres)
+            bres_ld = act_ld(bres)
+        _timed_call('fwd', g, 'gs_conv2d_fwd_bn', ctypes.byref(g), a.data_ptr(), krsc.data_ptr(), y.data_ptr(), _ptr(shift),
+                    stats.data_ptr(), count, _ptr(bn.weight), _ptr(bn.bias),
+                    bn.running_mean.data_ptr() if upd else None, bn.running_var.data_ptr() if upd else None,
+                    float(bn.momentum if bn.momentum is not None else 0.0), float(bn.eps), aff.data_ptr(), _ptr(bres), bres_ld,
+                    1 if fuse_bn['relu'] else 0, z.data_ptr(), act_ld(z), st)
+        if upd:
+            bn._gs_nbt_pending = getattr(bn, '_gs_nbt_pending', 0) + 1
+            if _touched_bns is not None:
+                _touched_bns.append(bn)
+        fuse_bn['z'], fuse_bn['aff'], fuse_bn['count'] = z, aff, count
+    elif sync is not None:     # several ranks: the conv kernel's last CTA pushes the statistics to the SyncBN peers
         _timed_call('fwd', g, 'gs_conv2d_fwd_syncbn', ctypes.byref(g), a.data_ptr(), krsc.data_ptr(), y.data_ptr(), _ptr(scale),
                     _ptr(shift), _ptr(residual), res_ld, flags, _ptr(stats), sync, st)
     else:
@@ -717,8 +751,13 @@ def cba_forward(x, conv, bn=None, relu=False, residual=None, Co=None, save=True)
     rec = LayerRec() if save else None
     if bn is not None and bn_batch_mode(bn):
         push = syncbn_push_desc(bn)
-        y, stats, a, g = conv_forward(x, conv, Co, shift=_bias(conv, Co), want_stats=True, sync=push)
-        z, aff, count = bn_train_apply(bn, y, stats, Co, residual, relu, pushed=push is not None)
+        if CONV_BN_FUSE and push is None and _sync_group(bn)[1] == 1 and Co % 8 == 0:
+            fb = dict(bn=bn, residual=residual, relu=relu)
+            y, stats, a, g = conv_forward(x, conv, Co, shift=_bias(conv, Co), want_stats=True, fuse_bn=fb)
+            z, aff, count = fb['z'], fb['aff'], fb['count']
+        else:
+            y, stats, a, g = conv_forward(x, conv, Co, shift=_bias(conv, Co), want_stats=True, sync=push)
+            z, aff, count = bn_train_apply(bn, y, stats, Co, residual, relu, pushed=push is not None)
         mode = 'bn_batch'
     else:
         y = None

@@ -155,6 +155,20 @@ int gs_conv2d_fwd_syncbn(const gs_conv_geom* g, const void* x, const void* w_krs
                          const float* shift, const void* residual, int32_t res_ld, int32_t flags, double* stats,
                          const gs_sync_desc* sync, void* stream);
 
+/* gs_conv2d_fwd + gs_bn_apply_train in ONE launch (training forward of a conv -> DynBN (-> + residual) (-> ReLU) layer,
+ * single rank): the conv kernel is persistent with one CTA per SM, so after the statistic flush the whole grid meets at one
+ * barrier and every CTA normalises the tiles it has just written (y is re-read from L2).  Writes BOTH y (bf16, the conv
+ * output the backward pass needs) and z = relu?( y*scale + shift (+ residual) ), aff = [mean | invstd | scale | shift]
+ * ([4][Co] fp32) and the running-stat prefix exactly as gs_bn_apply_train does.  stats: fp64 [2*Co + 2], ZERO on entry (the
+ * first trailing word is the barrier's arrival counter); on return it holds the batch sums.  shift: conv bias or NULL.
+ * replaces: F.conv2d(x, W[:Co, :Ci]) -> F.batch_norm(training=True) (-> + identity) -> ReLU of gaiavision DynamicConv2d /
+ * DynBN inside DynamicBottleneck / DynamicConvModule (sites: gaiaseg/models/backbones/dynamic_resnet.py:267-300,
+ * gaiaseg/models/utils/dynamic_res_layer.py:92). */
+int gs_conv2d_fwd_bn(const gs_conv_geom* g, const void* x, const void* w_krsc, void* y, const float* shift, double* stats,
+                     double count, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     float momentum, float eps, float* aff, const void* residual, int32_t res_ld, int32_t relu, void* z,
+                     int32_t z_ld, void* stream);
+
 /* Training-mode apply with the finalize step folded into the kernel prologue (one launch instead of two):
  * scale / shift are derived from the (all-reduced) sums, block 0 stores aff = [mean | invstd | scale | shift]
  * ([4][C] fp32, needed by the backward pass) and updates running_mean / running_var (NULL to skip). */

@@ -764,3 +764,62 @@ def fcn_head_skip_gradient_checks(gs):
         #  1 - cos of 3e-3, the stage tests' bound; a lost skip gradient would show as > 0.5)
         out.append(rel_l2(grads[True][0], xo.grad, 8e-2, tag + '.dx_vs_oracle_rel_l2'))
     return out
+
+
+def conv_bn_fused_launch_checks(gs):
+    """gs_conv2d_fwd_bn (conv + DynBN apply in ONE launch: statistic flush -> grid barrier -> every CTA normalises its own
+    tiles) against the two-kernel path (gs_conv2d_fwd + gs_bn_apply_train) on the same inputs: conv output y identical,
+    z within 1 bf16 ulp (the fp64 statistic atomics arrive in a different order), aff / running statistics 1e-6 --
+    single-CTA and CTA-pair kernels, wide n-tiles (Cout 320), several tiles per CTA, a phantom tile (odd tile count),
+    ragged maps, channel-prefix slices of a wider BN, residual + ReLU, no ReLU, a conv bias."""
+    Fg = gs.functional
+    dev = torch.device('cuda')
+    out = []
+    cases = [  # name, N, H, W, Ci, Co, Co_max, k, dil, residual, relu, bias
+        ('1x1_short_k', 2, 32, 32, 64, 96, 160, 1, 1, False, True, False),
+        ('1x1_multi_tile', 2, 64, 128, 96, 384, 384, 1, 1, False, True, False),
+        ('1x1_res_1280', 2, 64, 128, 320, 1280, 1280, 1, 1, True, True, False),
+        ('3x3_pair_wide320', 2, 64, 128, 320, 320, 320, 3, 2, False, True, False),
+        ('3x3_pair_oddtiles', 3, 8, 16, 320, 320, 320, 3, 1, True, False, False),
+        ('3x3_ragged_bias', 1, 17, 23, 64, 80, 80, 3, 1, False, True, True),
+        ('1x1_pair_1280_320', 2, 64, 128, 1280, 320, 320, 1, 1, False, True, False),
+    ]
+    saved = Fg.CONV_BN_FUSE
+    try:
+        for (name, N, H, W, Ci, Co, Co_max, k, dil, has_res, relu, bias) in cases:
+            g = torch.Generator().manual_seed(Ci + 3 * Co + H)
+            conv = gs.DynamicConv2d(Ci, Co_max, k, padding=dil * (k // 2), dilation=dil, bias=bias).to(dev)
+            with torch.no_grad():
+                conv.weight.copy_(bf16r(torch.randn(conv.weight.shape, generator=g) * (2.0 / (Ci * k * k)) ** 0.5))
+                if bias:
+                    conv.bias.copy_(torch.randn(Co_max, generator=g) * 0.1)
+            x = Fg.as_act(torch.randn(N, Ci, H, W, generator=g).to(dev))
+            res = Fg.as_act(torch.randn(N, Co, H, W, generator=g).to(dev)) if has_res else None
+            Fg.conv_shadows(conv)                      # (the bf16 weight shadow is cast once, outside the launch count)
+            got = {}
+            for fuse in (False, True):
+                Fg.CONV_BN_FUSE = fuse
+                bn = gs.DynamicBatchNorm2d(Co_max).to(dev).train()
+                with torch.no_grad():
+                    gg = torch.Generator().manual_seed(Co)
+                    bn.weight.copy_(torch.rand(Co_max, generator=gg) + 0.5)
+                    bn.bias.copy_(torch.randn(Co_max, generator=gg) * 0.1)
+                n0 = gs._lib.launch_count()
+                z, rec = Fg.cba_forward(x, conv, bn, relu=relu, residual=res, Co=Co)
+                torch.cuda.synchronize()
+                got[fuse] = dict(z=z.float().cpu(), y=rec.y.float().cpu(), aff=rec.aff.cpu(), rm=bn.running_mean.cpu().clone(),
+                                 rv=bn.running_var.cpu().clone(), launches=gs._lib.launch_count() - n0)
+            a, b = got[True], got[False]
+            out.append(dict(name=f'conv_bn_fused[{name}].one_launch', ok=a['launches'] == 1 and b['launches'] == 2,
+                            err=float(a['launches']), tol=1))
+            out.append(dict(name=f'conv_bn_fused[{name}].y_identical', ok=bool(torch.equal(a['y'], b['y'])), err=0.0, tol=0))
+            out.append(check_bf16(a['z'], b['z'], f'conv_bn_fused[{name}].z', 1.0))
+            out.append(check_f32(a['aff'], b['aff'], f'conv_bn_fused[{name}].aff', 1e-6))
+            out.append(check_f32(a['rm'][:Co], b['rm'][:Co], f'conv_bn_fused[{name}].running_mean', 1e-6))
+            out.append(check_f32(a['rv'][:Co], b['rv'][:Co], f'conv_bn_fused[{name}].running_var', 1e-6))
+            out.append(dict(name=f'conv_bn_fused[{name}].stats_outside_prefix_untouched',
+                            ok=bool(torch.equal(a['rm'][Co:], b['rm'][Co:]) and torch.equal(a['rv'][Co:], b['rv'][Co:])),
+                            err=0.0, tol=0))
+    finally:
+        Fg.CONV_BN_FUSE = saved
+    return out

@@ -51,6 +51,10 @@ def test_fcn_head_skip_gradient_in_dgrad_epilogue(gs):
     _assert_all(P.fcn_head_skip_gradient_checks(gs))
 
 
+def test_conv_bn_one_launch_equals_two_kernels(gs):
+    _assert_all(P.conv_bn_fused_launch_checks(gs))
+
+
 def test_wide_tile_epilogue(gs):
     _assert_all(P.wide_tile_epilogue_checks(gs))
 
