@@ -754,8 +754,12 @@ def fcn_head_skip_gradient_checks(gs):
             Fg.SKIP_GRAD_CARRIER = saved
         tag = f'fcn_head_skip[num_convs={num_convs}]'
         out.append(check_bf16(grads[True][0], grads[False][0], tag + '.dx_carrier_vs_autograd_sum', 3.0))
-        worst = max(float((grads[True][1][n] - g).abs().max()) for n, g in grads[False][1].items())
-        out.append(dict(name=tag + '.param_grads_identical', ok=worst == 0.0, err=worst, tol=0))
+        # same kernels on the same inputs in both modes; the only freedom is the ORDER in which the stream-K units of the weight
+        # gradient add their fp32 partial sums (an item can be split over three units -> (a + b) + c vs (a + c) + b), so the
+        # parameter gradients agree to an fp32 rounding, not always bit for bit (seen once in ~6 full-suite runs)
+        worst = max(float((grads[True][1][n] - g).abs().max()) / (float(g.abs().max()) + 1e-30)
+                    for n, g in grads[False][1].items())
+        out.append(dict(name=tag + '.param_grads_equal_up_to_summation_order', ok=worst <= 1e-6, err=worst, tol=1e-6))
         # fp32 oracle head on the same parameters
         oh.train()
         xo = x.clone().requires_grad_(True)
