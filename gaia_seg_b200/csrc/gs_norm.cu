@@ -171,6 +171,20 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
         }
     }
     for (int cv = cx; cv < C8; cv += Vc) {
+        // software pipeline: the first batch of loads is issued BEFORE the per-channel prologue (it does not depend on the
+        // statistics), and inside the loop the next batch is in flight while the current one is normalised and stored --
+        // 8 x 16 bytes per tensor and thread in flight instead of 4, and the prologue's latency (fp64 sums -> scale / shift)
+        // overlaps the first memory round trip
+        long long p = (long long)blockIdx.x * R + ry;
+        uint4 v[4], rr[4];
+        bool have = p + 3 * S < P;
+        if (have) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = ldg_stream(y + (p + u * S) * y_ld8 + cv);
+                if (HAS_RES) rr[u] = ldg_stream(res + (p + u * S) * res_ld8 + cv);
+            }
+        }
         float sc[8], sh[8];
         if (FROM_STATS) {
 #pragma unroll
@@ -210,13 +224,16 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
                 for (int i = 0; i < 8; ++i) sh[i] = 0.f;
             }
         }
-        long long p = (long long)blockIdx.x * R + ry;
-        for (; p + 3 * S < P; p += 4 * S) {
-            uint4 v[4], rr[4];
+        while (have) {
+            const long long pn = p + 4 * S;
+            const bool hn = pn + 3 * S < P;
+            uint4 v2[4], rr2[4];
+            if (hn) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                v[u] = ldg_stream(y + (p + u * S) * y_ld8 + cv);
-                if (HAS_RES) rr[u] = ldg_stream(res + (p + u * S) * res_ld8 + cv);
+                for (int u = 0; u < 4; ++u) {
+                    v2[u] = ldg_stream(y + (pn + u * S) * y_ld8 + cv);
+                    if (HAS_RES) rr2[u] = ldg_stream(res + (pn + u * S) * res_ld8 + cv);
+                }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -231,6 +248,13 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
                 }
                 stg_stream(z + (p + u * S) * z_ld8 + cv, pack8(f));
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = v2[u];
+                if (HAS_RES) rr[u] = rr2[u];
+            }
+            p = pn;
+            have = hn;
         }
         for (; p < P; p += S) {
             float f[8], g[8];
